@@ -1,0 +1,158 @@
+/*
+ * libstac_b200 - C ABI of the B200-native (sm_100a) STAC-ST encoder-side hot path.
+ *
+ * The reference (amazon-science/stac-speech-translation) has no FFI: its hot path is
+ * six eager Python calls into SpeechBrain/PyTorch
+ *   (/root/reference/stac-st/inference.py:95-107, stac-st/train_multitask.py:59-78).
+ * Each entry point below replaces the arithmetic of one of those calls; the Python
+ * drop-in classes in stac_speech_translation_b200/ bind them with ctypes
+ * (INTEGRATION.md shows the binding and the HyperPyYAML override).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless named host_*;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on
+ *     it: no allocation, no synchronisation, no host reads of device memory;
+ *   - return value: 0 = ok, <0 = argument error (STAC_ERR_*), >0 = cudaError_t;
+ *   - tensors are dense row-major, fp32 unless the name says bf16
+ *     (bf16 = uint16_t storage of the upper half of an IEEE fp32);
+ *   - T  = 1 + L/160 frames, T1 = (T-1)/2+1, T2 = (T1-1)/2+1 (25 Hz).
+ */
+#ifndef STAC_B200_H_
+#define STAC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAC_B200_VERSION 100
+
+#define STAC_OK 0
+#define STAC_ERR_INVALID_ARGUMENT (-1)
+#define STAC_ERR_UNSUPPORTED_SHAPE (-2)
+#define STAC_ERR_DRIVER_ENTRY (-3)   /* cuTensorMapEncodeTiled not obtainable */
+#define STAC_ERR_TENSOR_MAP (-4)     /* cuTensorMapEncodeTiled failed */
+
+/* epilogue activation of the GEMM entry points */
+#define STAC_ACT_NONE 0
+#define STAC_ACT_GELU_ERF 1
+
+/* output element type selectors */
+#define STAC_DT_F32 0
+#define STAC_DT_BF16 1
+
+int stac_version(void);
+const char* stac_error_string(int code);
+
+/* ---------------------------------------------------------------------------
+ * a2  Fbank   -- replaces hparams.compute_features(wavs)
+ *     (/root/reference/stac-st/inference.py:95; yaml transformer_multitask.yaml:299-302)
+ * STFT(hamming 400, hop 160, centre zero pad) -> |.|^2 -> 80 triangular mel
+ * -> 10*log10(max(.,1e-10)); also the per-utterance maximum used by the top-dB clamp.
+ *
+ * tables: constant block built once by the host (layout: stac_fbank_tables_floats()
+ *         floats: window[400] | mel_start[80] | mel_count[80] | mel_weight[80][16]).
+ * utt_max_ordered: uint32[B], order-preserving encoding of the fp32 maximum; the
+ *         caller zero-fills it before the call (0 encodes "below every float").
+ */
+int stac_fbank_tables_floats(void);
+int stac_fbank_logmel(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_row_stride,
+                      const float* tables, float* logmel_db /*[B,T,80]*/,
+                      uint32_t* utt_max_ordered /*[B]*/, void* stream);
+
+/* top-dB clamp (+ optional global mean/std normalisation, a3) in one elementwise pass:
+ *   y = max(x, max_b - top_db);  if (mean) y = (y - mean[m]) / std[m]
+ * per_utterance != 0: max_b is utterance b's maximum, else the maximum over the batch.
+ * Replaces the tail of Filterbank._amplitude_to_DB and, with mean/std, the eval-mode
+ * modules.normalize(feats, wav_lens) (/root/reference/stac-st/inference.py:96).      */
+int stac_fbank_topdb_norm(const float* logmel_db, const uint32_t* utt_max_ordered,
+                          int per_utterance, float top_db,
+                          const float* mean /*[80] or NULL*/, const float* std /*[80] or NULL*/,
+                          int64_t batch, int64_t frames, int64_t n_mels, float* out, void* stream);
+
+/* a3 alone: y = (x - mean[m]) / std[m] over [rows, n_mels] */
+int stac_input_norm(const float* x, const float* mean, const float* std, int64_t rows,
+                    int64_t n_mels, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a4  ConvolutionFrontEnd -- replaces modules.CNN(feats)
+ *     (/root/reference/stac-st/inference.py:99; yaml :173-180)
+ * Block 0: reflect-pad 1, Conv2d(1->256, 3x3, stride 2) + bias, LayerNorm over (40,256)
+ *          eps 1e-5, LeakyReLU(0.01), fused in one kernel.
+ *   w0 [256][3(freq)][3(time)] (torch weight [256,1,3,3]), b0 [256], ln_g/ln_b [40*256].
+ *   out_mode STAC_DT_F32 : fp32 [B,T1,40,256]
+ *   out_mode STAC_DT_BF16: bf16 reflect-padded, parity-split planes
+ *        [B][4 = (t_par*2+f_par)][Tp2][21][256], Tp2 = (T1+3)/2, padded coords
+ *        tp = t1+1, fp = f1+1, plane = (tp&1)*2 + (fp&1), indices tp>>1, fp>>1
+ *        (the layout the tensor-core conv1 reads with unit-stride TMA boxes).
+ */
+int64_t stac_conv0_padded_elems(int64_t batch, int64_t t1);
+int stac_conv0_ln_lrelu(const float* feats /*[B,T,80]*/, const float* w0, const float* b0,
+                        const float* ln_g, const float* ln_b, int64_t batch, int64_t frames,
+                        void* out, int out_mode, void* stream);
+
+/* Block 1 convolution only (pre-LayerNorm), fp32 CUDA-core implicit GEMM:
+ *   x [B,T1,40,256] fp32, w1 torch layout [256(out),256(in),3(freq),3(time)], out [B,T2,20,256]. */
+int stac_conv1_f32(const float* x, const float* w1, const float* b1, int64_t batch, int64_t t1,
+                   float* out, void* stream);
+
+/* Block 1 convolution on tcgen05 tensor cores (bf16 operands, fp32 accumulate):
+ *   xpad: block-0 output in the padded parity-split bf16 layout above;
+ *   w1_packed: bf16 [9 = kt*3+kf][256(out)][256(in)];  out fp32 [B,T2,20,256] (pre-LN). */
+int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, const float* b1,
+                    int64_t batch, int64_t t1, float* out, void* stream);
+
+/* LayerNorm over a whole row of `dim` elements (dim = F*C = 10240 / 5120) + LeakyReLU. */
+int stac_group_ln_lrelu(const float* x, int64_t rows, int64_t dim, const float* gamma,
+                        const float* beta, float eps, float slope, void* out, int out_dtype,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a5-a7  TransformerMultiTask.encode() building blocks
+ *     (/root/reference/stac-st/modules/TransformerMultiTask.py:273-309)
+ */
+/* y = LayerNorm(x) * gamma + beta per row of `dim` (256/512/1024); either output may be NULL */
+int stac_layernorm(const float* x, int64_t rows, int64_t dim, const float* gamma, const float* beta,
+                   float eps, float* out_f32, uint16_t* out_bf16, void* stream);
+
+/* C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) + resid[(row % resid_period), N]
+ *   (resid NULL = none; resid_period 0 = row-aligned residual, may alias C).
+ * fp32 CUDA-core version (fp32 mode).                                                */
+int stac_gemm_f32(const float* a, const float* w, const float* bias, const float* resid,
+                  int64_t resid_period, int act, float* c, int64_t m, int64_t n, int64_t k,
+                  void* stream);
+
+/* tcgen05 version: bf16 A/W (K multiple of 64, 16-byte aligned rows), fp32 accumulation in
+ * TMEM, fused epilogue; c_dtype selects fp32 or bf16 output.
+ * vt_out/vt_cols: if vt_out != NULL the last `vt_cols` output columns (the V third of a
+ * packed QKV projection) are written transposed to vt_out as bf16 [B*H][64][t_pad]
+ * (t = row % seq_len, b = row / seq_len) instead of to C.                             */
+int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float* bias, const float* resid,
+                   int64_t resid_period, int act, void* c, int c_dtype, int64_t m, int64_t n,
+                   int64_t k, uint16_t* vt_out, int64_t vt_cols, int64_t seq_len, int64_t t_pad,
+                   void* stream);
+
+/* Multi-head self-attention with key-padding by valid length (head_dim 64):
+ *   qkv [B*T, 3*d] packed [q|k|v] with bias already added and q pre-scaled by 1/8,
+ *   kv_len int32[B] (keys j < kv_len[b] are attended), ctx [B*T, d].                  */
+int stac_mha_f32(const float* qkv, const int32_t* kv_len, int64_t batch, int64_t seq_len,
+                 int64_t d_model, int64_t n_head, float* ctx, void* stream);
+int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int32_t* kv_len, int64_t batch,
+                  int64_t seq_len, int64_t t_pad, int64_t d_model, int64_t n_head, uint16_t* ctx,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------
+ * a8/a9  CTC head -- replaces hparams.log_softmax(modules.ctc_lin(enc_out)) and
+ *        p_ctc.argmax(-1) (/root/reference/stac-st/inference.py:54-56,104-107)
+ */
+int stac_log_softmax(const float* logits, int64_t rows, int64_t vocab, float* out,
+                     int32_t* argmax /*[rows] or NULL*/, void* stream);
+
+/* fp32 -> bf16 conversion (weight packing / activation hand-off) */
+int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAC_B200_H_ */

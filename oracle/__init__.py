@@ -1,0 +1,28 @@
+"""CPU oracle for the STAC-ST encoder-side inference hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is product code: only
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
+reference`` legs of ``bench.py`` may import it, and there only as the checker
+(or the timed CPU baseline), never as the thing shipped.
+
+PARITY UNPINNED: the arithmetic of this path lives in SpeechBrain (~v0.5.14,
+``/root/reference/README.md:46-50``), which is neither vendored under
+``/root/reference`` nor installable here, and the reference ships no tests or
+golden vectors.  The restatement in
+``oracle/speechbrain_path.py`` follows the published SpeechBrain source from
+memory of that release; it is cross-checked against independent formulations
+(numpy DFT, hand-written attention, hand-written LayerNorm/conv) in
+``tests/test_oracle.py`` and against the three constants the reference does
+pin (5120-wide CNN output, 25 Hz frame rate, 2500-entry PE table).
+"""
+from .speechbrain_path import (  # noqa: F401
+    Fbank,
+    InputNormalization,
+    ConvolutionFrontEnd,
+    TransformerMultiTask,
+    EncoderWrapper,
+    Linear,
+    build_reference_modules,
+    reference_compute_forward,
+    MODEL_SIZES,
+)

@@ -1,0 +1,85 @@
+// Shared device/host helpers for libstac_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "../../include/stac_b200.h"
+
+#define STAC_LAUNCH_CHECK()                                   \
+  do {                                                        \
+    cudaError_t e__ = cudaPeekAtLastError();                  \
+    if (e__ != cudaSuccess) return (int)cudaGetLastError();   \
+    return STAC_OK;                                           \
+  } while (0)
+
+#define STAC_REQUIRE(cond) \
+  do { if (!(cond)) return STAC_ERR_INVALID_ARGUMENT; } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32); `red` holds >= 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// Order-preserving float <-> uint map so atomicMax works on any finite float.
+__device__ __forceinline__ unsigned int float_to_ordered(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __host__ __forceinline__ float ordered_to_float(unsigned int u) {
+  unsigned int v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(v);
+#else
+  float f; memcpy(&f, &v, 4); return f;
+#endif
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}

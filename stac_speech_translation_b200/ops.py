@@ -1,0 +1,326 @@
+"""Host-side orchestration of the libstac_b200 kernels (one function per stage of the path).
+
+Everything here only allocates torch tensors and enqueues kernels on the current CUDA stream
+through the C ABI; there is no torch arithmetic on the hot path.  Stage numbering follows
+SURVEY.md section 8(a): a2 Fbank, a3 InputNormalization, a4 ConvolutionFrontEnd, a5-a7 encoder,
+a8/a9 CTC head.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_NONE, DT_BF16, DT_F32, check, lib, ptr, stream
+
+N_MELS = 80
+N_FFT = 400
+HOP = 160
+CNN_CH = 256
+F1, F2 = 40, 20
+PRECISIONS = ("fp32", "bf16")
+
+
+def frames_of(n_samples: int):
+    t = 1 + n_samples // HOP
+    t1 = (t - 1) // 2 + 1
+    t2 = (t1 - 1) // 2 + 1
+    return t, t1, t2
+
+
+# --------------------------------------------------------------------------
+# a2 / a3
+# --------------------------------------------------------------------------
+def build_fbank_tables(device) -> torch.Tensor:
+    """Constant block of the Fbank kernel (layout documented in include/stac_b200.h).
+
+    Window and mel weights are computed with the same fp32 torch expressions SpeechBrain's
+    STFT / Filterbank use (hamming_window(400); triangular filters symmetric in Hz with the LEFT
+    band as half-width; 201 linear bins 0..8 kHz), twiddles in float64 then rounded."""
+    window = torch.hamming_window(N_FFT)
+    k = torch.arange(200, dtype=torch.float64)
+    tw200 = torch.stack([torch.cos(2 * math.pi * k / 200), -torch.sin(2 * math.pi * k / 200)], -1)
+    k = torch.arange(25, dtype=torch.float64)
+    tw25 = torch.stack([torch.cos(2 * math.pi * k / 25), -torch.sin(2 * math.pi * k / 25)], -1)
+    k = torch.arange(201, dtype=torch.float64)
+    tw400 = torch.stack([torch.cos(2 * math.pi * k / 400), -torch.sin(2 * math.pi * k / 400)], -1)
+
+    def to_mel(hz):
+        return 2595 * math.log10(1 + hz / 700)
+
+    mel = torch.linspace(to_mel(0), to_mel(8000.0), N_MELS + 2)
+    hz = 700 * (10 ** (mel / 2595) - 1)
+    band = (hz[1:] - hz[:-1])[:-1]
+    f_central = hz[1:-1]
+    all_freqs = torch.linspace(0, 16000 // 2, N_FFT // 2 + 1)
+    slope = (all_freqs[None, :] - f_central[:, None]) / band[:, None]          # [80, 201]
+    fb = torch.max(torch.zeros(1), torch.min(slope + 1.0, -slope + 1.0))        # [80, 201]
+    start = torch.zeros(N_MELS)
+    count = torch.zeros(N_MELS)
+    weights = torch.zeros(N_MELS, 16)
+    for m in range(N_MELS):
+        nz = torch.nonzero(fb[m] > 0).flatten()
+        s, e = int(nz[0]), int(nz[-1]) + 1
+        if e - s > 16:
+            raise ValueError("mel filter wider than 16 taps")
+        start[m], count[m] = s, e - s
+        weights[m, : e - s] = fb[m, s:e]
+    tab = torch.cat([window.float(), tw200.float().flatten(), tw25.float().flatten(),
+                     tw400.float().flatten(), start, count, weights.flatten()])
+    assert tab.numel() == lib().stac_fbank_tables_floats()
+    return tab.to(device=device, dtype=torch.float32).contiguous()
+
+
+def fbank(wavs: torch.Tensor, tables: torch.Tensor, top_db: float = 80.0, per_utterance: bool = True,
+          mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a2 (+a3 when mean/std are given): [B, L] fp32 PCM -> [B, T, 80] fp32 features."""
+    if wavs.dim() != 2:
+        raise _lib.StacB200Error("Fbank expects [batch, samples] waveforms")
+    wavs = wavs.contiguous()
+    b, n = wavs.shape
+    t = 1 + n // HOP
+    db = torch.empty(b, t, N_MELS, device=wavs.device, dtype=torch.float32)
+    umax = torch.zeros(b, device=wavs.device, dtype=torch.int32)
+    check(lib().stac_fbank_logmel(ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tables), ptr(db),
+                                  ptr(umax), stream()), "stac_fbank_logmel")
+    check(lib().stac_fbank_topdb_norm(ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),
+                                      b, t, N_MELS, ptr(db), stream()), "stac_fbank_topdb_norm")
+    return db
+
+
+def input_norm(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(lib().stac_input_norm(ptr(x, torch.float32), ptr(mean, torch.float32), ptr(std, torch.float32),
+                                x.numel() // x.shape[-1], x.shape[-1], ptr(out), stream()), "stac_input_norm")
+    return out
+
+
+# --------------------------------------------------------------------------
+# a4
+# --------------------------------------------------------------------------
+@dataclass
+class FrontendWeights:
+    precision: str
+    w0: torch.Tensor      # [256, 3(freq), 3(time)] fp32
+    b0: torch.Tensor
+    g0: torch.Tensor      # [40*256]
+    be0: torch.Tensor
+    w1: torch.Tensor      # fp32 [256][9][256] (fp32 mode) or bf16 [9][256][256] (bf16 mode); tap = kf*3+kt
+    b1: torch.Tensor
+    g1: torch.Tensor      # [20*256]
+    be1: torch.Tensor
+
+
+def pack_frontend(conv0_w, conv0_b, ln0_w, ln0_b, conv1_w, conv1_b, ln1_w, ln1_b, precision: str) -> FrontendWeights:
+    f = lambda t: t.detach().float().contiguous()
+    w1 = conv1_w.detach().float()                       # [out, in, kf, kt]
+    if precision == "fp32":
+        w1p = w1.permute(0, 2, 3, 1).reshape(CNN_CH, 9, CNN_CH).contiguous()
+    else:
+        w1p = w1.permute(2, 3, 0, 1).reshape(9, CNN_CH, CNN_CH).to(torch.bfloat16).contiguous()
+    return FrontendWeights(precision, f(conv0_w).reshape(CNN_CH, 3, 3), f(conv0_b), f(ln0_w).flatten(),
+                           f(ln0_b).flatten(), w1p, f(conv1_b), f(ln1_w).flatten(), f(ln1_b).flatten())
+
+
+def conv_frontend(feats: torch.Tensor, w: FrontendWeights, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """a4: [B, T, 80] fp32 -> [B, T2, 5120] (fp32, or bf16 when out_dtype=torch.bfloat16)."""
+    feats = feats.contiguous()
+    b, t, nm = feats.shape
+    if nm != N_MELS:
+        raise _lib.StacB200Error("ConvolutionFrontEnd kernel is specialised for 80 mel bins")
+    t1 = (t - 1) // 2 + 1
+    t2 = (t1 - 1) // 2 + 1
+    dev = feats.device
+    pre = torch.empty(b * t2, F2 * CNN_CH, device=dev, dtype=torch.float32)
+    if w.precision == "fp32":
+        x0 = torch.empty(b, t1, F1, CNN_CH, device=dev, dtype=torch.float32)
+        check(lib().stac_conv0_ln_lrelu(ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
+                                        b, t, ptr(x0), DT_F32, stream()), "stac_conv0_ln_lrelu")
+        check(lib().stac_conv1_f32(ptr(x0), ptr(w.w1, torch.float32), ptr(w.b1), b, t1, ptr(pre), stream()),
+              "stac_conv1_f32")
+    else:
+        n_pad = lib().stac_conv0_padded_elems(b, t1)
+        x0 = torch.empty(n_pad, device=dev, dtype=torch.bfloat16)
+        check(lib().stac_conv0_ln_lrelu(ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
+                                        b, t, ptr(x0), DT_BF16, stream()), "stac_conv0_ln_lrelu")
+        check(lib().stac_conv1_bf16(ptr(x0), ptr(w.w1, torch.bfloat16), ptr(w.b1), b, t1, ptr(pre), stream()),
+              "stac_conv1_bf16")
+    out_dtype = out_dtype or torch.float32
+    out = torch.empty(b, t2, F2 * CNN_CH, device=dev, dtype=out_dtype)
+    check(lib().stac_group_ln_lrelu(ptr(pre), b * t2, F2 * CNN_CH, ptr(w.g1), ptr(w.be1), 1e-5, 0.01, ptr(out),
+                                    DT_BF16 if out_dtype == torch.bfloat16 else DT_F32, stream()),
+          "stac_group_ln_lrelu")
+    return out
+
+
+# --------------------------------------------------------------------------
+# a5-a7
+# --------------------------------------------------------------------------
+@dataclass
+class LayerWeights:
+    ln1_g: torch.Tensor
+    ln1_b: torch.Tensor
+    w_qkv: torch.Tensor   # [3d, d]; q rows (and bias) pre-scaled by 1/sqrt(64)
+    b_qkv: torch.Tensor
+    w_o: torch.Tensor
+    b_o: torch.Tensor
+    ln2_g: torch.Tensor
+    ln2_b: torch.Tensor
+    w_1: torch.Tensor
+    b_1: torch.Tensor
+    w_2: torch.Tensor
+    b_2: torch.Tensor
+
+
+@dataclass
+class EncoderWeights:
+    precision: str
+    d_model: int
+    nhead: int
+    w_src: torch.Tensor   # [d, 5120]
+    b_src: torch.Tensor
+    pe: torch.Tensor      # [max_len, d] fp32
+    layers: List[LayerWeights] = field(default_factory=list)
+    lnf_g: torch.Tensor = None
+    lnf_b: torch.Tensor = None
+
+
+def _wcast(t: torch.Tensor, precision: str) -> torch.Tensor:
+    t = t.detach().float()
+    return (t.to(torch.bfloat16) if precision == "bf16" else t).contiguous()
+
+
+def pack_encoder(src_w, src_b, pe, layers, lnf_w, lnf_b, nhead: int, precision: str) -> EncoderWeights:
+    """layers: iterable of dicts with in_proj_weight/in_proj_bias/out_proj_weight/out_proj_bias,
+    ffn1_w/ffn1_b/ffn2_w/ffn2_b, norm1_w/norm1_b/norm2_w/norm2_b (SpeechBrain state_dict tensors)."""
+    f = lambda t: t.detach().float().contiguous()
+    d = src_w.shape[0]
+    if d % nhead != 0 or d // nhead != 64:
+        raise _lib.StacB200Error("attention kernels are specialised for head_dim 64 (all STAC-ST sizes)")
+    ew = EncoderWeights(precision, d, nhead, _wcast(src_w, precision), f(src_b), f(pe).reshape(-1, d))
+    scale = 1.0 / math.sqrt(64.0)   # exact power of two: folding it into W_q/b_q is lossless
+    for L in layers:
+        wq = L["in_proj_weight"].detach().float().clone()
+        bq = L["in_proj_bias"].detach().float().clone()
+        wq[:d] *= scale
+        bq[:d] *= scale
+        ew.layers.append(LayerWeights(
+            f(L["norm1_w"]), f(L["norm1_b"]), _wcast(wq, precision), bq.contiguous(),
+            _wcast(L["out_proj_weight"], precision), f(L["out_proj_bias"]),
+            f(L["norm2_w"]), f(L["norm2_b"]), _wcast(L["ffn1_w"], precision), f(L["ffn1_b"]),
+            _wcast(L["ffn2_w"], precision), f(L["ffn2_b"])))
+    ew.lnf_g, ew.lnf_b = f(lnf_w), f(lnf_b)
+    return ew
+
+
+def kv_lengths(wav_len: Optional[torch.Tensor], batch: int, t2: int, device, train_mask: bool) -> torch.Tensor:
+    """Valid key count per utterance, from the reference's own fp32 expressions:
+    encode(): keep j <= floor(wav_len*T2)   (TransformerMultiTask.py:289-294)
+    forward(): keep j <  round(wav_len*T2)  (TransformerMultiTask.py:225-226)."""
+    if wav_len is None:
+        return torch.full((batch,), t2, device=device, dtype=torch.int32)
+    wl = wav_len.to(device=device, dtype=torch.float32)
+    if train_mask:
+        n = torch.round(wl * t2)
+    else:
+        n = torch.floor(wl * t2) + 1
+    return n.clamp(1, t2).to(torch.int32).contiguous()
+
+
+def _gemm(a, w, bias, c, precision, resid=None, resid_period=0, act=ACT_NONE, vt=None, vt_cols=0, seq_len=0,
+          t_pad=0):
+    m, k = a.shape
+    n = w.shape[0]
+    if precision == "fp32":
+        check(lib().stac_gemm_f32(ptr(a, torch.float32), ptr(w, torch.float32), ptr(bias), ptr(resid), resid_period,
+                                  act, ptr(c, torch.float32), m, n, k, stream()), "stac_gemm_f32")
+    else:
+        check(lib().stac_gemm_bf16(ptr(a, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias), ptr(resid),
+                                   resid_period, act, ptr(c), DT_BF16 if c.dtype == torch.bfloat16 else DT_F32,
+                                   m, n, k, ptr(vt), vt_cols, seq_len, t_pad, stream()), "stac_gemm_bf16")
+    return c
+
+
+def _layernorm(x, g, b, eps, out_f32=None, out_bf16=None):
+    rows, dim = x.shape
+    check(lib().stac_layernorm(ptr(x, torch.float32), rows, dim, ptr(g), ptr(b), eps, ptr(out_f32), ptr(out_bf16),
+                               stream()), "stac_layernorm")
+
+
+def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, want_bf16_copy: bool = False):
+    """a5 (src-linear + PE) and a7 (N pre-LN layers + final LN).
+    src: [B, T2, 5120] fp32 (fp32 mode) or bf16 (bf16 mode).  Returns enc_out fp32 [B, T2, d]
+    (and, if asked, its bf16 copy for the CTC GEMM)."""
+    b, t2, k_in = src.shape
+    d, h, prec = w.d_model, w.nhead, w.precision
+    dev = src.device
+    m = b * t2
+    if t2 > w.pe.shape[0]:
+        raise _lib.StacB200Error(f"sequence of {t2} frames exceeds the positional-encoding table ({w.pe.shape[0]})")
+    act_dt = torch.float32 if prec == "fp32" else torch.bfloat16
+    if src.dtype != act_dt:
+        raise _lib.StacB200Error(f"{prec} encoder expects {act_dt} CNN features")
+    x = torch.empty(m, d, device=dev, dtype=torch.float32)            # residual stream (fp32 in both modes)
+    _gemm(src.reshape(m, k_in), w.w_src, w.b_src, x, prec, resid=w.pe, resid_period=t2)
+    hbuf = torch.empty(m, d, device=dev, dtype=act_dt)
+    qkv = torch.empty(m, 3 * d, device=dev, dtype=act_dt)
+    ctx = torch.empty(m, d, device=dev, dtype=act_dt)
+    d_ffn = w.layers[0].w_1.shape[0] if w.layers else 4 * d
+    ff = torch.empty(m, d_ffn, device=dev, dtype=act_dt)
+    vt = None
+    t_pad = (t2 + 7) // 8 * 8
+    if prec == "bf16":
+        vt = torch.zeros(b * h * 64 * t_pad, device=dev, dtype=torch.bfloat16)   # padding keys stay zero
+    for L in w.layers:
+        if prec == "fp32":
+            _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_f32=hbuf)
+            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec)
+            check(lib().stac_mha_f32(ptr(qkv), ptr(kv_len, torch.int32), b, t2, d, h, ptr(ctx), stream()),
+                  "stac_mha_f32")
+        else:
+            _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_bf16=hbuf)
+            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec, vt=vt, vt_cols=d, seq_len=t2, t_pad=t_pad)
+            check(lib().stac_mha_bf16(ptr(qkv), ptr(vt), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
+                                      stream()), "stac_mha_bf16")
+        _gemm(ctx, L.w_o, L.b_o, x, prec, resid=x)
+        if prec == "fp32":
+            _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_f32=hbuf)
+        else:
+            _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_bf16=hbuf)
+        _gemm(hbuf, L.w_1, L.b_1, ff, prec, act=ACT_GELU_ERF)
+        _gemm(ff, L.w_2, L.b_2, x, prec, resid=x)
+    enc = torch.empty(b, t2, d, device=dev, dtype=torch.float32)
+    enc_bf16 = torch.empty(b, t2, d, device=dev, dtype=torch.bfloat16) if want_bf16_copy else None
+    _layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=enc.view(m, d), out_bf16=None if enc_bf16 is None else enc_bf16.view(m, d))
+    return (enc, enc_bf16) if want_bf16_copy else enc
+
+
+# --------------------------------------------------------------------------
+# a8 / a9
+# --------------------------------------------------------------------------
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str) -> torch.Tensor:
+    """y = x W^T + b over the last dim; fp32 result."""
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1]).contiguous()
+    if precision == "bf16" and x2.dtype != torch.bfloat16:
+        xb = torch.empty_like(x2, dtype=torch.bfloat16)
+        check(lib().stac_cast_bf16(ptr(x2, torch.float32), x2.numel(), ptr(xb), stream()), "stac_cast_bf16")
+        x2 = xb
+    out = torch.empty(x2.shape[0], weight.shape[0], device=x.device, dtype=torch.float32)
+    _gemm(x2, weight, bias, out, precision)
+    return out.view(*shp[:-1], weight.shape[0])
+
+
+def log_softmax(logits: torch.Tensor, want_argmax: bool = False, inplace: bool = False):
+    shp = logits.shape
+    x = logits.reshape(-1, shp[-1]).contiguous()
+    out = x if inplace else torch.empty_like(x)
+    ids = torch.empty(x.shape[0], device=x.device, dtype=torch.int32) if want_argmax else None
+    check(lib().stac_log_softmax(ptr(x, torch.float32), x.shape[0], x.shape[1], ptr(out), ptr(ids), stream()),
+          "stac_log_softmax")
+    out = out.view(shp)
+    return (out, ids.view(shp[:-1])) if want_argmax else out

@@ -1,0 +1,157 @@
+"""The object graph of the reference yaml, and the fused end-to-end call.
+
+``build_modules`` instantiates what transformer_multitask.yaml:173-210,253-254,299-302 builds,
+with the drop-in classes of this package.  ``compute_forward`` is the reference's call sequence
+(/root/reference/stac-st/inference.py:95-107) over those objects, stage by stage, with fp32
+tensors at every boundary.  ``EncoderPipeline`` is the same arithmetic without the fp32 stage
+boundaries (bf16 hand-offs, fused top-dB + normalisation, greedy ids) and is what the benchmark
+and the multi-GPU sharding drive.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import StacB200Error
+from .convolution import ConvolutionFrontEnd
+from .features import Fbank, InputNormalization
+from .linear import Linear, LogSoftmax
+from .transformer import TransformerMultiTask
+
+# (d_model, nhead, num_encoder_layers, d_ffn): /root/reference/run_default.sh:73-76,
+# /root/reference/ablations/run_m_and_l_size.sh:72-99
+MODEL_SIZES = {
+    "S": dict(d_model=256, nhead=4, num_encoder_layers=12, d_ffn=1024),
+    "M": dict(d_model=512, nhead=8, num_encoder_layers=16, d_ffn=2048),
+    "L": dict(d_model=1024, nhead=16, num_encoder_layers=14, d_ffn=4096),
+}
+
+
+@dataclass
+class HParams:
+    """The yaml keys of the hot path (transformer_multitask.yaml:127-170)."""
+    sample_rate: int = 16000
+    n_fft: int = 400
+    n_mels: int = 80
+    d_model: int = 256
+    nhead: int = 4
+    num_encoder_layers: int = 12
+    num_decoder_layers: int = 6
+    d_ffn: int = 1024
+    transformer_dropout: float = 0.1
+    output_neurons: int = 5000
+    blank_index: int = 0
+    turn: int = 7
+    xt: int = 8
+    seed: int = 8886
+
+    @classmethod
+    def for_size(cls, size: str, **kw):
+        return cls(**{**MODEL_SIZES[size], **kw})
+
+
+def build_modules(hp: HParams, precision: str = "bf16", device="cuda") -> Dict[str, nn.Module]:
+    torch.manual_seed(hp.seed)
+    mods = {
+        "compute_features": Fbank(sample_rate=hp.sample_rate, n_fft=hp.n_fft, n_mels=hp.n_mels),
+        "normalize": InputNormalization(norm_type="global", update_until_epoch=4),
+        "CNN": ConvolutionFrontEnd(input_shape=(8, 10, hp.n_mels), num_blocks=2, num_layers_per_block=1,
+                                   out_channels=(256, 256), kernel_sizes=(3, 3), strides=(2, 2),
+                                   residuals=(False, False), precision=precision),
+        "Transformer": TransformerMultiTask(
+            input_size=5120, tgt_vocab=hp.output_neurons, d_model=hp.d_model, nhead=hp.nhead,
+            num_encoder_layers=hp.num_encoder_layers, num_decoder_layers=hp.num_decoder_layers,
+            d_ffn=hp.d_ffn, dropout=hp.transformer_dropout, activation=nn.GELU, encoder_module="transformer",
+            attention_type="regularMHA", normalize_before=True, causal=False, precision=precision),
+        "ctc_lin": Linear(input_size=hp.d_model, n_neurons=hp.output_neurons, precision=precision),
+        "log_softmax": LogSoftmax(dim=-1),
+    }
+    for m in mods.values():
+        m.to(device)
+        m.eval()
+    return mods
+
+
+@torch.no_grad()
+def compute_forward(mods: Dict[str, nn.Module], wavs: torch.Tensor, wav_lens: torch.Tensor, train_mask=False):
+    """The reference's six-call sequence over the drop-in objects; returns every stage boundary."""
+    out = {}
+    feats = mods["compute_features"](wavs)
+    out["fbank"] = feats
+    feats = mods["normalize"](feats, wav_lens)
+    out["feats"] = feats
+    src = mods["CNN"](feats)
+    out["cnn"] = src
+    tr = mods["Transformer"]
+    enc_out = tr.forward_encoder(src, wav_lens) if train_mask else tr.encode(src, wav_lens)
+    out["enc_out"] = enc_out
+    logits = mods["ctc_lin"](enc_out)
+    out["logits"] = logits
+    out["p_ctc"] = mods["log_softmax"](logits)
+    return out
+
+
+class EncoderPipeline:
+    """PCM -> (enc_out, p_ctc[, greedy ids]) in one call, using the modules' packed weights.
+
+    The same kernels as the stage-by-stage drop-ins, minus the fp32 stage boundaries:
+    top-dB clamp and global normalisation are one elementwise pass, the CNN hands bf16 to the
+    encoder in bf16 mode, and the CTC head also emits greedy token ids (the only thing
+    ``append_speaker_turns`` reads, /root/reference/stac-st/inference.py:54-56).
+    """
+
+    def __init__(self, mods: Dict[str, nn.Module], precision: Optional[str] = None, train_mask: bool = False):
+        self.mods = mods
+        self.precision = precision or mods["Transformer"].precision
+        for k in ("CNN", "Transformer", "ctc_lin"):
+            if mods[k].precision != self.precision:
+                raise StacB200Error("all modules of a pipeline must share one precision")
+        self.train_mask = train_mask
+
+    @torch.no_grad()
+    def __call__(self, wavs: torch.Tensor, wav_lens: Optional[torch.Tensor], want_posteriors: bool = True,
+                 want_greedy: bool = True, stop_after: Optional[str] = None):
+        m = self.mods
+        dev = wavs.device
+        fb, norm = m["compute_features"], m["normalize"]
+        mean, std = norm.device_stats(dev, ops.N_MELS)
+        feats = ops.fbank(wavs, fb.tables(dev), fb.top_db, fb.top_db_per_utterance, mean, std)
+        bf16 = self.precision == "bf16"
+        src = ops.conv_frontend(feats, m["CNN"].packed(), torch.bfloat16 if bf16 else torch.float32)
+        if stop_after == "cnn":
+            return {"cnn": src}
+        tr = m["Transformer"]
+        b, t2, _ = src.shape
+        kv_len = ops.kv_lengths(wav_lens, b, t2, dev, self.train_mask)
+        res = {"kv_len": kv_len}
+        if bf16:
+            enc, enc_b = ops.encoder_stack(src, tr.packed(), kv_len, want_bf16_copy=True)
+        else:
+            enc = ops.encoder_stack(src, tr.packed(), kv_len)
+            enc_b = enc
+        res["enc_out"] = enc
+        if want_posteriors or want_greedy:
+            ctc = m["ctc_lin"]
+            bias = None if ctc.w.bias is None else ctc.w.bias.detach().float().contiguous()
+            logits = ops.linear(enc_b, ctc.packed_weight(), bias, self.precision)
+            p, ids = ops.log_softmax(logits, want_argmax=True, inplace=True)
+            res["p_ctc"], res["greedy"] = p, ids
+        return res
+
+
+def ctc_greedy_collapse(ids: torch.Tensor, lengths: Sequence[int], blank: int = 0) -> List[List[int]]:
+    """CTC-greedy token sequences (merge repeats, drop blanks) over the valid frames of each utterance."""
+    ids = ids.cpu()
+    out = []
+    for i, n in enumerate(lengths):
+        seq, prev = [], None
+        for tok in ids[i, : int(n)].tolist():
+            if tok != prev and tok != blank:
+                seq.append(tok)
+            prev = tok
+        out.append(seq)
+    return out

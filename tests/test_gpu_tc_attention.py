@@ -1,0 +1,31 @@
+"""tcgen05 flash attention (stac_mha_bf16) against an fp32 softmax-attention with -inf key padding."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from util import rel_l2  # noqa: E402
+from stac_speech_translation_b200 import ops  # noqa: E402
+
+
+@pytest.mark.parametrize("t,lens,d,h", [(128, [128], 64, 1), (251, [251, 100, 1], 256, 4), (64, [64, 33], 128, 2),
+                                         (130, [129, 130, 5], 256, 4), (751, [751, 400], 256, 4),
+                                         (300, [300, 299], 512, 8)])
+def test_mha_bf16(t, lens, d, h):
+    g = torch.Generator().manual_seed(t + d)
+    b = len(lens)
+    qkv = (torch.randn(b * t, 3 * d, generator=g)).to(torch.bfloat16)
+    kv = torch.tensor(lens, dtype=torch.int32)
+    t_pad = (t + 7) // 8 * 8
+    vt = torch.zeros(b, h, 64, t_pad, dtype=torch.bfloat16)
+    vt[..., :t] = qkv[:, 2 * d:].view(b, t, h, 64).permute(0, 2, 3, 1)
+    ctx = torch.full((b * t, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.check(ops.lib().stac_mha_bf16(ops.ptr(qkv.cuda()), ops.ptr(vt.cuda().contiguous()), ops.ptr(kv.cuda()),
+                                      b, t, t_pad, d, h, ops.ptr(ctx), ops.stream()))
+    q, k, v = (x.float().view(b, t, h, 64).transpose(1, 2) for x in qkv.split(d, dim=-1))
+    mask = torch.arange(t)[None, :] >= kv[:, None]
+    s = (q @ k.transpose(-1, -2)).masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, d)
+    got = ctx.float().cpu()
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)

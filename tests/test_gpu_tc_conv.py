@@ -1,0 +1,41 @@
+"""tcgen05 implicit-GEMM conv1 (stac_conv1_bf16) against torch conv2d on the same bf16-rounded data."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from util import rel_l2  # noqa: E402
+from stac_speech_translation_b200 import ops  # noqa: E402
+
+
+def _pack_padded(x0):
+    """[B, T1, 40, 256] -> reflect-padded parity-split planes (the layout conv0 writes in bf16 mode)."""
+    b, t1 = x0.shape[:2]
+    tp2 = (t1 + 3) // 2
+    pad = torch.nn.functional.pad(x0.permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)
+    full = torch.zeros(b, 2 * tp2, 42, 256)
+    full[:, : t1 + 2] = pad
+    planes = torch.zeros(b, 2, 2, tp2, 21, 256)
+    for pt in range(2):
+        for pf in range(2):
+            planes[:, pt, pf] = full[:, pt::2, pf::2]
+    return planes.to(torch.bfloat16).contiguous()
+
+
+@pytest.mark.parametrize("b,t1", [(1, 12), (2, 13), (3, 126), (2, 501), (1, 7)])
+def test_conv1_bf16(b, t1):
+    g = torch.Generator().manual_seed(t1)
+    x0 = torch.randn(b, t1, 40, 256, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(256, 256, 3, 3, generator=g) / 48).to(torch.bfloat16).float()
+    bias = torch.randn(256, generator=g)
+    xin = torch.nn.functional.pad(x0.permute(0, 3, 2, 1), (1, 1, 1, 1), mode="reflect")   # [B, C, F, T]
+    ref = torch.nn.functional.conv2d(xin, w, bias, stride=2).permute(0, 3, 2, 1)         # [B, T2, 20, 256]
+    t2 = (t1 - 1) // 2 + 1
+    assert ref.shape == (b, t2, 20, 256)
+    wp = w.permute(2, 3, 0, 1).reshape(9, 256, 256).to(torch.bfloat16).contiguous()
+    out = torch.full((b, t2, 20, 256), float("nan"), device="cuda")
+    ops.check(ops.lib().stac_conv1_bf16(ops.ptr(_pack_padded(x0).cuda()), ops.ptr(wp.cuda()), ops.ptr(bias.cuda()),
+                                        b, t1, ops.ptr(out), ops.stream()))
+    got = out.cpu()
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 1e-5, rel_l2(got, ref)

@@ -1,0 +1,81 @@
+"""tcgen05 GEMM (stac_gemm_bf16) against torch fp32 matmul of the same bf16-rounded operands."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from util import rel_l2, rel_max  # noqa: E402
+from stac_speech_translation_b200 import ops  # noqa: E402
+
+
+def _run(m, n, k, bias=True, resid=False, period=0, act=ops.ACT_NONE, out_bf16=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    a = (torch.randn(m, k, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+    b = torch.randn(n, generator=g) if bias else None
+    rows_r = period if period else m
+    r = torch.randn(rows_r, n, generator=g) if resid else None
+    c = torch.full((m, n), float("nan"), device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    ops._gemm(a.cuda(), w.cuda(), None if b is None else b.cuda(), c, "bf16",
+              resid=None if r is None else r.cuda(), resid_period=period, act=act)
+    ref = a.float() @ w.float().T
+    if b is not None:
+        ref = ref + b
+    if act == ops.ACT_GELU_ERF:
+        ref = torch.nn.functional.gelu(ref)
+    if r is not None:
+        ref = ref + (r.repeat(m // period, 1) if period else r)
+    return c.float().cpu(), ref
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (128, 256, 256), (300, 256, 256), (1000, 768, 256),
+                                    (257, 1024, 256), (129, 256, 1024), (515, 5000, 256), (200, 512, 512),
+                                    (4096 + 17, 256, 5120)])
+def test_shapes_block_n_256(m, n, k):
+    got, ref = _run(m, n, k)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 1e-5, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (333, 384, 256), (130, 640, 128)])
+def test_shapes_block_n_128(m, n, k):
+    got, ref = _run(m, n, k)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 1e-5
+
+
+def test_epilogues():
+    got, ref = _run(300, 1024, 256, act=ops.ACT_GELU_ERF, out_bf16=True)
+    assert rel_l2(got, ref) < 4e-3
+    got, ref = _run(300, 256, 1024, resid=True)
+    assert rel_l2(got, ref) < 1e-5
+    got, ref = _run(43 * 6, 256, 512, resid=True, period=43)
+    assert rel_l2(got, ref) < 1e-5
+    got, ref = _run(300, 256, 256, bias=False)
+    assert rel_l2(got, ref) < 1e-5
+
+
+def test_many_tiles_persistent_loop():
+    # more tiles than SMs so every CTA loops, both TMEM accumulator stages and all smem stages wrap
+    got, ref = _run(128 * 200 + 5, 1024, 256, seed=3)
+    assert rel_l2(got, ref) < 1e-5
+    assert rel_max(got, ref) < 1e-4
+
+
+def test_qkv_with_transposed_v():
+    g = torch.Generator().manual_seed(1)
+    b, t, d, h = 3, 77, 256, 4
+    m = b * t
+    a = torch.randn(m, d, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3 * d, d, generator=g) / 16).to(torch.bfloat16)
+    bias = torch.randn(3 * d, generator=g)
+    t_pad = (t + 7) // 8 * 8
+    qkv = torch.zeros(m, 3 * d, device="cuda", dtype=torch.bfloat16)
+    vt = torch.zeros(b * h * 64 * t_pad, device="cuda", dtype=torch.bfloat16)
+    ops._gemm(a.cuda(), w.cuda(), bias.cuda(), qkv, "bf16", vt=vt, vt_cols=d, seq_len=t, t_pad=t_pad)
+    ref = a.float() @ w.float().T + bias
+    assert rel_l2(qkv[:, : 2 * d].float(), ref[:, : 2 * d]) < 4e-3
+    v_ref = ref[:, 2 * d:].view(b, t, h, 64).permute(0, 2, 3, 1)          # [B, H, 64, T]
+    v_got = vt.view(b, h, 64, t_pad).float().cpu()
+    assert rel_l2(v_got[..., :t], v_ref) < 4e-3
+    assert float(v_got[..., t:].abs().max()) == 0.0
