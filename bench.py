@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the STAC-ST encoder-side hot path on B200 (see BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the whole path (PCM -> Fbank -> normalise -> CNN -> encoder -> CTC
+log-posteriors + greedy ids) over one synthetic batch of the workload BASELINE.json's metric is
+quoted on that fits one GPU: configs[1], default ("S") model, 64 x 30 s multi-turn segments, bf16.
+Prints ONE JSON line (rank 0).  `value` is measured with the batch resident in HBM; `e2e` goes
+through the same public call with pinned HOST buffers (H2D of the PCM and D2H of the greedy token
+ids inside the timed region).  `--impl reference` times the CPU oracle (plain-PyTorch restatement
+of the reference's SpeechBrain path, oracle/) on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "encoder audio-sec/sec (RTFx)"
+UNIT = "audio-s/s"
+VOCAB = 5000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", default="S", choices=["S", "M", "L"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--seconds", type=float, default=30.0)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--gather", default="bf16", choices=["ids", "bf16", "fp32"],
+                    help="what travels to rank 0 besides enc_out when N > 1: greedy ids only, bf16 or fp32 posteriors")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="utterances in the CPU-baseline sample")
+    ap.add_argument("--trace-out", default=None, help="write the per-kernel timing table (json) here")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# algorithmic work (SURVEY.md 8d / BASELINE.md section 2)
+# --------------------------------------------------------------------------
+def work_table(size_cfg, batch, n_samples, kv_len_sum_sq_like):
+    d, layers, dffn = size_cfg["d_model"], size_cfg["num_encoder_layers"], size_cfg["d_ffn"]
+    t = 1 + n_samples // 160
+    t1 = (t - 1) // 2 + 1
+    t2 = (t1 - 1) // 2 + 1
+    m = batch * t2
+    w = {
+        "stac_fbank_logmel": ("hbm", batch * (4 * n_samples + 4 * 80 * t), 1),
+        "stac_fbank_topdb_norm": ("hbm", batch * 2 * 4 * 80 * t, 1),
+        "stac_conv0_ln_lrelu": ("hbm", batch * (4 * 80 * t + 2 * 40 * 256 * t1), 1),
+        "stac_conv1_bf16": ("tensor", 2 * 9 * 256 * 256 * 20 * m, 1),
+        "stac_group_ln_lrelu": ("hbm", m * 5120 * (4 + 2), 1),
+        "stac_gemm_bf16:src_linear": ("tensor", 2 * 5120 * d * m, 1),
+        "stac_layernorm": ("hbm", m * d * (4 + 2), 2 * layers + 1),
+        "stac_gemm_bf16:qkv": ("tensor", 2 * d * 3 * d * m, layers),
+        "stac_mha_bf16": ("tensor", 4 * d * kv_len_sum_sq_like, layers),
+        "stac_gemm_bf16:out_proj": ("tensor", 2 * d * d * m, layers),
+        "stac_gemm_bf16:ffn1": ("tensor", 2 * d * dffn * m, layers),
+        "stac_gemm_bf16:ffn2": ("tensor", 2 * d * dffn * m, layers),
+        "stac_gemm_bf16:ctc_lin": ("tensor", 2 * d * VOCAB * m, 1),
+        "stac_log_softmax": ("hbm", m * VOCAB * 4 * 2, 1),
+    }
+    return w
+
+
+def trace_key(name, label):
+    return f"{name}:{label}" if name == "stac_gemm_bf16" else name
+
+
+# --------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (a port of the reference's SpeechBrain path; SpeechBrain itself cannot be
+    installed here) on all host threads, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import oracle
+    from stac_speech_translation_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    omods = oracle.build_reference_modules(args.size)
+    b = max(1, min(args.cpu_batch, args.batch))
+    wavs, wl = synth.fast_synth_batch(b, args.seconds, seed=1234)
+    norm = omods["normalize"]
+    norm.train(); norm(omods["compute_features"](wavs[:, :32000]), wl); norm.eval()
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle.reference_compute_forward(omods, wavs, wl)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.reference_compute_forward(omods, wavs, wl)
+    dt = (time.perf_counter() - t0) / steps
+    val = b * args.seconds / dt
+    sample = f"{b} x {args.seconds:g} s utterances per step ({steps} timed steps) of the {args.batch} x {args.seconds:g} s workload"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[1]: {args.size} model, batch {args.batch} x {args.seconds:g} s, "
+                               f"CPU sample of {b} utterances per step", "precision": "fp32"},
+        "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    import oracle
+    from stac_speech_translation_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    omods = oracle.build_reference_modules(args.size)
+    b = max(1, min(args.cpu_batch, args.batch))
+    wavs, wl = synth.fast_synth_batch(b, args.seconds, seed=1234)
+    norm = omods["normalize"]
+    norm.train(); norm(omods["compute_features"](wavs[:, :32000]), wl); norm.eval()
+    oracle.reference_compute_forward(omods, wavs, wl)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.reference_compute_forward(omods, wavs, wl)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": round(b * args.seconds / dt, 2), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{b} x {args.seconds:g} s utterances, {reps} timed passes after 1 warm-up, torch fp32, "
+                      f"{cores} threads"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import stac_speech_translation_b200 as sb
+    from stac_speech_translation_b200 import ops, synth
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    hp = sb.HParams.for_size(args.size)
+    mods = sb.build_modules(hp, precision=args.precision, device=dev)
+    wavs_cpu, wl_cpu = synth.fast_synth_batch(args.batch, args.seconds, seed=1234 + rank)
+    # normaliser statistics: one SpeechBrain-style statistics step on a calibration slice
+    calib = wavs_cpu[: min(8, args.batch), : 16000 * 4].to(dev)
+    mods["normalize"].calibrate(mods["compute_features"](calib), torch.ones(calib.shape[0], device=dev))
+    pipe = sb.EncoderPipeline(mods)
+    pinned = wavs_cpu.pin_memory()
+    wavs = pinned.to(dev, non_blocking=True)
+    wl = wl_cpu.to(dev)
+    n_samples = wavs.shape[1]
+    audio_s = args.batch * n_samples / 16000.0
+    t2 = ops.frames_of(n_samples)[2]
+
+    gather_bufs = None
+    if world > 1:
+        d = hp.d_model
+        if rank == 0:
+            gather_bufs = {"enc": [torch.empty(args.batch, t2, d, device=dev) for _ in range(world)],
+                           "ids": [torch.empty(args.batch, t2, device=dev, dtype=torch.int32) for _ in range(world)]}
+            if args.gather != "ids":
+                pdt = torch.bfloat16 if args.gather == "bf16" else torch.float32
+                gather_bufs["p"] = [torch.empty(args.batch, t2, VOCAB, device=dev, dtype=pdt) for _ in range(world)]
+
+    def gather(res):
+        if world == 1:
+            return
+        dist.gather(res["enc_out"], gather_bufs["enc"] if rank == 0 else None, dst=0)
+        dist.gather(res["greedy"], gather_bufs["ids"] if rank == 0 else None, dst=0)
+        if args.gather != "ids":
+            p = res["p_ctc"]
+            if args.gather == "bf16":
+                pb = torch.empty(p.shape, device=dev, dtype=torch.bfloat16)
+                ops._call("stac_cast_bf16", ops.ptr(p), p.numel(), ops.ptr(pb), ops.stream())
+                p = pb
+            dist.gather(p, gather_bufs["p"] if rank == 0 else None, dst=0)
+
+    def step(x):
+        res = pipe(x, wl)
+        gather(res)
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    for _ in range(max(args.warmup, 3)):
+        step(wavs)
+    barrier()
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step(wavs)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ops.LAUNCHES - launches0
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms)
+
+    # ---------------- end to end: pinned host PCM in, greedy ids out ----------------
+    copy_stream = torch.cuda.Stream()
+    dev_in = [torch.empty_like(wavs) for _ in range(2)]
+    ids_host = [torch.empty(args.batch, t2, dtype=torch.int32).pin_memory() for _ in range(2)]
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+    out_done = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+
+    def e2e_loop(n):
+        for i in range(n + 1):
+            if i < n:                       # stage PCM of step i (overlaps compute of step i-1)
+                s = i % 2
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(in_free[s])
+                    dev_in[s].copy_(pinned, non_blocking=True)
+                    in_ready[s].record(copy_stream)
+            if i > 0:                       # compute step i-1, ship its greedy ids to the host
+                s = (i - 1) % 2
+                main.wait_event(in_ready[s])
+                res = step(dev_in[s])
+                in_free[s].record(main)
+                ids_host[s].copy_(res["greedy"], non_blocking=True)
+                out_done[s].record(main)
+            if i > 1:                       # the consumer reads step i-2's ids
+                out_done[i % 2].synchronize()
+                _ = int(ids_host[i % 2][0, 0])
+        torch.cuda.synchronize()
+
+    for s in range(2):
+        in_free[s].record(main)
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms)
+
+    if rank != 0:
+        return
+
+    # ---------------- per-kernel table (CUDA events around every launch) + roofline ----------------
+    kv = ops.kv_lengths(wl, args.batch, t2, dev, False).long()
+    attn_pairs = int((kv * t2).sum())                # sum over utterances of T2 * S_valid
+    ops.TRACE = []
+    saved_gather = gather_bufs
+    for _ in range(2):
+        pipe(wavs, wl)
+    torch.cuda.synchronize()
+    trace, ops.TRACE = ops.TRACE, None
+    per = {}
+    for name, label, a, b in trace:
+        k = trace_key(name, label)
+        t, n = per.get(k, (0.0, 0))
+        per[k] = (t + a.elapsed_time(b), n + 1)
+    wt = work_table(sb.MODEL_SIZES[args.size], args.batch, n_samples, attn_pairs)
+    pk = peaks()
+    table = []
+    for k, (t, n) in sorted(per.items(), key=lambda kv_: -kv_[1][0]):
+        bound, work, _ = wt.get(k, ("hbm", 0, 1))
+        avg_ms = t / n
+        ach = work / (avg_ms * 1e-3) / (1e12 if bound == "tensor" else 1e9) if avg_ms > 0 else 0.0
+        peak = pk["tflops_sustained"] if bound == "tensor" else pk["hbm_gbs"]
+        table.append({"kernel": k, "launches_per_step": n // 2, "avg_ms": round(avg_ms, 4),
+                      "ms_per_step": round(t / 2, 4), "bound": bound, "achieved": round(ach, 1),
+                      "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": round(ach / peak, 4)})
+    top = table[0]
+    roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
+                "peak": pk["tflops_sustained"] if top["bound"] == "tensor" else pk["hbm_gbs"],
+                "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                "peak_source": pk["source"] + (" (sustained bf16)" if top["bound"] == "tensor" else " (copy)"),
+                "share_of_step": round(top["ms_per_step"] / sum(r["ms_per_step"] for r in table), 4)}
+    if args.trace_out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.trace_out)), exist_ok=True)
+        json.dump({"table": table, "traced_step_ms": round(sum(r["ms_per_step"] for r in table), 3)},
+                  open(args.trace_out, "w"), indent=1)
+    del saved_gather
+
+    cpu = None if args.no_cpu_baseline else cpu_baseline(args)
+    total_audio = audio_s * world
+    line = {
+        "metric": METRIC, "value": round(total_audio / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"configs[1]: STAC-ST default ({args.size}) encoder + CTC head, batch {args.batch} x "
+                               f"{args.seconds:g} s multi-turn synthetic 16 kHz segments per GPU",
+                   "precision": args.precision, "frames_25hz": t2,
+                   "l2": "per-step working set (~6 GB of activations) >> 126 MB L2, no explicit flush",
+                   "multi_gpu": "whole batches per rank; enc_out + greedy ids"
+                                + ("" if args.gather == "ids" else f" + {args.gather} posteriors")
+                                + " gathered to rank 0 inside the timed region" if world > 1 else "single GPU"},
+        "e2e": {"value": round(total_audio / (e2e_ms * 1e-3), 1), "unit": UNIT,
+                "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(args.batch * t2 * 4),
+                "ms_per_step": round(e2e_ms, 3),
+                "note": "pinned fp32 PCM in (double-buffered on a copy stream), greedy CTC ids out; enc_out and "
+                        "p_ctc stay on the device as in the reference's compute_forward"},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "kernels": table[:8],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

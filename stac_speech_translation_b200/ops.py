@@ -23,6 +23,41 @@ CNN_CH = 256
 F1, F2 = 40, 20
 PRECISIONS = ("fp32", "bf16")
 
+# Optional launch tracing: bench.py sets TRACE to a list to get (kernel, label, start_event, end_event)
+# per launch; LAUNCHES counts kernel launches either way.
+TRACE = None
+LAUNCHES = 0
+_LABEL = ""
+
+
+def _call(name, *args):
+    """Enqueue one libstac_b200 kernel on the current stream (optionally bracketed by CUDA events)."""
+    global LAUNCHES
+    LAUNCHES += 1
+    if TRACE is None:
+        check(getattr(lib(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(getattr(lib(), name)(*args), name)
+    e1.record()
+    TRACE.append((name, _LABEL, e0, e1))
+
+
+class label:
+    """Context manager naming the launches inside it (for the per-kernel timing table)."""
+
+    def __init__(self, text):
+        self.text = text
+
+    def __enter__(self):
+        global _LABEL
+        self.prev, _LABEL = _LABEL, self.text
+
+    def __exit__(self, *exc):
+        global _LABEL
+        _LABEL = self.prev
+
 
 def frames_of(n_samples: int):
     t = 1 + n_samples // HOP
@@ -84,18 +119,18 @@ def fbank(wavs: torch.Tensor, tables: torch.Tensor, top_db: float = 80.0, per_ut
     t = 1 + n // HOP
     db = torch.empty(b, t, N_MELS, device=wavs.device, dtype=torch.float32)
     umax = torch.zeros(b, device=wavs.device, dtype=torch.int32)
-    check(lib().stac_fbank_logmel(ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tables), ptr(db),
-                                  ptr(umax), stream()), "stac_fbank_logmel")
-    check(lib().stac_fbank_topdb_norm(ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),
-                                      b, t, N_MELS, ptr(db), stream()), "stac_fbank_topdb_norm")
+    _call("stac_fbank_logmel", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tables), ptr(db),
+                                  ptr(umax), stream())
+    _call("stac_fbank_topdb_norm", ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),
+                                      b, t, N_MELS, ptr(db), stream())
     return db
 
 
 def input_norm(x: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     out = torch.empty_like(x)
-    check(lib().stac_input_norm(ptr(x, torch.float32), ptr(mean, torch.float32), ptr(std, torch.float32),
-                                x.numel() // x.shape[-1], x.shape[-1], ptr(out), stream()), "stac_input_norm")
+    _call("stac_input_norm", ptr(x, torch.float32), ptr(mean, torch.float32), ptr(std, torch.float32),
+                                x.numel() // x.shape[-1], x.shape[-1], ptr(out), stream())
     return out
 
 
@@ -138,22 +173,19 @@ def conv_frontend(feats: torch.Tensor, w: FrontendWeights, out_dtype: Optional[t
     pre = torch.empty(b * t2, F2 * CNN_CH, device=dev, dtype=torch.float32)
     if w.precision == "fp32":
         x0 = torch.empty(b, t1, F1, CNN_CH, device=dev, dtype=torch.float32)
-        check(lib().stac_conv0_ln_lrelu(ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
-                                        b, t, ptr(x0), DT_F32, stream()), "stac_conv0_ln_lrelu")
-        check(lib().stac_conv1_f32(ptr(x0), ptr(w.w1, torch.float32), ptr(w.b1), b, t1, ptr(pre), stream()),
-              "stac_conv1_f32")
+        _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
+                                        b, t, ptr(x0), DT_F32, stream())
+        _call("stac_conv1_f32", ptr(x0), ptr(w.w1, torch.float32), ptr(w.b1), b, t1, ptr(pre), stream())
     else:
         n_pad = lib().stac_conv0_padded_elems(b, t1)
         x0 = torch.empty(n_pad, device=dev, dtype=torch.bfloat16)
-        check(lib().stac_conv0_ln_lrelu(ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
-                                        b, t, ptr(x0), DT_BF16, stream()), "stac_conv0_ln_lrelu")
-        check(lib().stac_conv1_bf16(ptr(x0), ptr(w.w1, torch.bfloat16), ptr(w.b1), b, t1, ptr(pre), stream()),
-              "stac_conv1_bf16")
+        _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
+                                        b, t, ptr(x0), DT_BF16, stream())
+        _call("stac_conv1_bf16", ptr(x0), ptr(w.w1, torch.bfloat16), ptr(w.b1), b, t1, ptr(pre), stream())
     out_dtype = out_dtype or torch.float32
     out = torch.empty(b, t2, F2 * CNN_CH, device=dev, dtype=out_dtype)
-    check(lib().stac_group_ln_lrelu(ptr(pre), b * t2, F2 * CNN_CH, ptr(w.g1), ptr(w.be1), 1e-5, 0.01, ptr(out),
-                                    DT_BF16 if out_dtype == torch.bfloat16 else DT_F32, stream()),
-          "stac_group_ln_lrelu")
+    _call("stac_group_ln_lrelu", ptr(pre), b * t2, F2 * CNN_CH, ptr(w.g1), ptr(w.be1), 1e-5, 0.01, ptr(out),
+                                    DT_BF16 if out_dtype == torch.bfloat16 else DT_F32, stream())
     return out
 
 
@@ -232,23 +264,32 @@ def kv_lengths(wav_len: Optional[torch.Tensor], batch: int, t2: int, device, tra
 
 
 def _gemm(a, w, bias, c, precision, resid=None, resid_period=0, act=ACT_NONE, vt=None, vt_cols=0, seq_len=0,
-          t_pad=0):
+          t_pad=0, tag=""):
+    global _LABEL
+    prev, _LABEL = _LABEL, tag or _LABEL
+    try:
+        return _gemm_impl(a, w, bias, c, precision, resid, resid_period, act, vt, vt_cols, seq_len, t_pad)
+    finally:
+        _LABEL = prev
+
+
+def _gemm_impl(a, w, bias, c, precision, resid, resid_period, act, vt, vt_cols, seq_len, t_pad):
     m, k = a.shape
     n = w.shape[0]
     if precision == "fp32":
-        check(lib().stac_gemm_f32(ptr(a, torch.float32), ptr(w, torch.float32), ptr(bias), ptr(resid), resid_period,
-                                  act, ptr(c, torch.float32), m, n, k, stream()), "stac_gemm_f32")
+        _call("stac_gemm_f32", ptr(a, torch.float32), ptr(w, torch.float32), ptr(bias), ptr(resid), resid_period,
+                                  act, ptr(c, torch.float32), m, n, k, stream())
     else:
-        check(lib().stac_gemm_bf16(ptr(a, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias), ptr(resid),
+        _call("stac_gemm_bf16", ptr(a, torch.bfloat16), ptr(w, torch.bfloat16), ptr(bias), ptr(resid),
                                    resid_period, act, ptr(c), DT_BF16 if c.dtype == torch.bfloat16 else DT_F32,
-                                   m, n, k, ptr(vt), vt_cols, seq_len, t_pad, stream()), "stac_gemm_bf16")
+                                   m, n, k, ptr(vt), vt_cols, seq_len, t_pad, stream())
     return c
 
 
 def _layernorm(x, g, b, eps, out_f32=None, out_bf16=None):
     rows, dim = x.shape
-    check(lib().stac_layernorm(ptr(x, torch.float32), rows, dim, ptr(g), ptr(b), eps, ptr(out_f32), ptr(out_bf16),
-                               stream()), "stac_layernorm")
+    _call("stac_layernorm", ptr(x, torch.float32), rows, dim, ptr(g), ptr(b), eps, ptr(out_f32), ptr(out_bf16),
+                               stream())
 
 
 def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, want_bf16_copy: bool = False):
@@ -265,7 +306,7 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
     if src.dtype != act_dt:
         raise _lib.StacB200Error(f"{prec} encoder expects {act_dt} CNN features")
     x = torch.empty(m, d, device=dev, dtype=torch.float32)            # residual stream (fp32 in both modes)
-    _gemm(src.reshape(m, k_in), w.w_src, w.b_src, x, prec, resid=w.pe, resid_period=t2)
+    _gemm(src.reshape(m, k_in), w.w_src, w.b_src, x, prec, resid=w.pe, resid_period=t2, tag="src_linear")
     hbuf = torch.empty(m, d, device=dev, dtype=act_dt)
     qkv = torch.empty(m, 3 * d, device=dev, dtype=act_dt)
     ctx = torch.empty(m, d, device=dev, dtype=act_dt)
@@ -278,21 +319,20 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
     for L in w.layers:
         if prec == "fp32":
             _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_f32=hbuf)
-            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec)
-            check(lib().stac_mha_f32(ptr(qkv), ptr(kv_len, torch.int32), b, t2, d, h, ptr(ctx), stream()),
-                  "stac_mha_f32")
+            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec, tag="qkv")
+            _call("stac_mha_f32", ptr(qkv), ptr(kv_len, torch.int32), b, t2, d, h, ptr(ctx), stream())
         else:
             _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_bf16=hbuf)
-            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec, vt=vt, vt_cols=d, seq_len=t2, t_pad=t_pad)
-            check(lib().stac_mha_bf16(ptr(qkv), ptr(vt), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
-                                      stream()), "stac_mha_bf16")
-        _gemm(ctx, L.w_o, L.b_o, x, prec, resid=x)
+            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec, vt=vt, vt_cols=d, seq_len=t2, t_pad=t_pad, tag="qkv")
+            _call("stac_mha_bf16", ptr(qkv), ptr(vt), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
+                                      stream())
+        _gemm(ctx, L.w_o, L.b_o, x, prec, resid=x, tag="out_proj")
         if prec == "fp32":
             _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_f32=hbuf)
         else:
             _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_bf16=hbuf)
-        _gemm(hbuf, L.w_1, L.b_1, ff, prec, act=ACT_GELU_ERF)
-        _gemm(ff, L.w_2, L.b_2, x, prec, resid=x)
+        _gemm(hbuf, L.w_1, L.b_1, ff, prec, act=ACT_GELU_ERF, tag="ffn1")
+        _gemm(ff, L.w_2, L.b_2, x, prec, resid=x, tag="ffn2")
     enc = torch.empty(b, t2, d, device=dev, dtype=torch.float32)
     enc_bf16 = torch.empty(b, t2, d, device=dev, dtype=torch.bfloat16) if want_bf16_copy else None
     _layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=enc.view(m, d), out_bf16=None if enc_bf16 is None else enc_bf16.view(m, d))
@@ -302,16 +342,17 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
 # --------------------------------------------------------------------------
 # a8 / a9
 # --------------------------------------------------------------------------
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str) -> torch.Tensor:
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str,
+           tag: str = "linear") -> torch.Tensor:
     """y = x W^T + b over the last dim; fp32 result."""
     shp = x.shape
     x2 = x.reshape(-1, shp[-1]).contiguous()
     if precision == "bf16" and x2.dtype != torch.bfloat16:
         xb = torch.empty_like(x2, dtype=torch.bfloat16)
-        check(lib().stac_cast_bf16(ptr(x2, torch.float32), x2.numel(), ptr(xb), stream()), "stac_cast_bf16")
+        _call("stac_cast_bf16", ptr(x2, torch.float32), x2.numel(), ptr(xb), stream())
         x2 = xb
     out = torch.empty(x2.shape[0], weight.shape[0], device=x.device, dtype=torch.float32)
-    _gemm(x2, weight, bias, out, precision)
+    _gemm(x2, weight, bias, out, precision, tag=tag)
     return out.view(*shp[:-1], weight.shape[0])
 
 
@@ -320,7 +361,6 @@ def log_softmax(logits: torch.Tensor, want_argmax: bool = False, inplace: bool =
     x = logits.reshape(-1, shp[-1]).contiguous()
     out = x if inplace else torch.empty_like(x)
     ids = torch.empty(x.shape[0], device=x.device, dtype=torch.int32) if want_argmax else None
-    check(lib().stac_log_softmax(ptr(x, torch.float32), x.shape[0], x.shape[1], ptr(out), ptr(ids), stream()),
-          "stac_log_softmax")
+    _call("stac_log_softmax", ptr(x, torch.float32), x.shape[0], x.shape[1], ptr(out), ptr(ids), stream())
     out = out.view(shp)
     return (out, ids.view(shp[:-1])) if want_argmax else out

@@ -137,7 +137,7 @@ class EncoderPipeline:
         if want_posteriors or want_greedy:
             ctc = m["ctc_lin"]
             bias = None if ctc.w.bias is None else ctc.w.bias.detach().float().contiguous()
-            logits = ops.linear(enc_b, ctc.packed_weight(), bias, self.precision)
+            logits = ops.linear(enc_b, ctc.packed_weight(), bias, self.precision, tag="ctc_lin")
             p, ids = ops.log_softmax(logits, want_argmax=True, inplace=True)
             res["p_ctc"], res["greedy"] = p, ids
         return res

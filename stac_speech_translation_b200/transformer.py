@@ -143,8 +143,8 @@ class TransformerMultiTask(nn.Module):
         src = src.contiguous()
         if self.precision == "bf16" and src.dtype != torch.bfloat16:
             srcb = torch.empty_like(src, dtype=torch.bfloat16)
-            ops.check(ops.lib().stac_cast_bf16(ops.ptr(src.float()), src.numel(), ops.ptr(srcb), ops.stream()),
-                      "stac_cast_bf16")
+            src32 = src.float()
+            ops._call("stac_cast_bf16", ops.ptr(src32), src.numel(), ops.ptr(srcb), ops.stream())
             src = srcb
         elif self.precision == "fp32":
             src = src.float()

@@ -1,0 +1,56 @@
+"""world_size-2 (gloo, CPU) test of the sharding + gather-to-rank-0 host logic."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stac_speech_translation_b200 import distributed as sd
+from stac_speech_translation_b200 import synth
+
+
+def _fake_compute(batch):
+    """Deterministic stand-in for the GPU pipeline: ragged outputs that depend on the batch."""
+    idx, t2 = batch
+    base = torch.arange(len(idx) * t2, dtype=torch.float32).view(len(idx), t2, 1) + float(sum(idx))
+    return {"enc_out": base.expand(-1, -1, 4).contiguous(), "greedy": (base[..., 0] % 7).to(torch.int32),
+            "p_ctc": (base.expand(-1, -1, 3) * 0.5).to(torch.bfloat16)}
+
+
+def _worker(rank, world, port, durations, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bucketed, per_rank = sd.plan(durations, world, max_batch_len=60.0, num_buckets=6, max_batch_ex=16)
+        batches = [(b, int(25 * max(durations[i] for i in b)) + 1) for b in bucketed.batches]
+        got = sd.run_sharded(batches, per_rank, _fake_compute, ["enc_out", "greedy", "p_ctc"])
+        if rank == 0:
+            ok = set(got) == set(range(len(batches)))
+            for i, b in enumerate(batches):
+                ref = _fake_compute(b)
+                for k in ref:
+                    ok = ok and got[i][k].dtype == ref[k].dtype and torch.equal(got[i][k], ref[k])
+            ret.put((ok, len(batches), [len(p) for p in per_rank]))
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_and_gather_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    durations = synth.lognormal_durations(96, seed=3).tolist()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, durations, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, n_batches, split = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and n_batches > 4 and min(split) >= 1 and sum(split) == n_batches

@@ -134,7 +134,9 @@ def test_mha_fp32(t, lens):
     qkv = torch.randn(b * t, 3 * d, generator=g)
     kv = torch.tensor(lens, dtype=torch.int32)
     ctx = torch.empty(b * t, d, device="cuda")
-    ops.check(ops.lib().stac_mha_f32(ops.ptr(qkv.cuda()), ops.ptr(kv.cuda()), b, t, d, h, ops.ptr(ctx), ops.stream()))
+    qkv_d, kv_d = qkv.cuda(), kv.cuda()      # keep the device tensors alive across the async launch
+    ops.check(ops.lib().stac_mha_f32(ops.ptr(qkv_d), ops.ptr(kv_d), b, t, d, h, ops.ptr(ctx), ops.stream()))
+    torch.cuda.synchronize()
     q, k, v = (x.view(b, t, h, 64).transpose(1, 2) for x in qkv.split(d, dim=-1))
     mask = torch.arange(t)[None, :] >= kv[:, None]
     s = (q @ k.transpose(-1, -2)).masked_fill(mask[:, None, None, :], float("-inf"))

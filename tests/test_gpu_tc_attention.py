@@ -20,8 +20,10 @@ def test_mha_bf16(t, lens, d, h):
     vt = torch.zeros(b, h, 64, t_pad, dtype=torch.bfloat16)
     vt[..., :t] = qkv[:, 2 * d:].view(b, t, h, 64).permute(0, 2, 3, 1)
     ctx = torch.full((b * t, d), float("nan"), device="cuda", dtype=torch.bfloat16)
-    ops.check(ops.lib().stac_mha_bf16(ops.ptr(qkv.cuda()), ops.ptr(vt.cuda().contiguous()), ops.ptr(kv.cuda()),
+    qkv_d, vt_d, kv_d = qkv.cuda(), vt.cuda().contiguous(), kv.cuda()   # keep alive across the async launch
+    ops.check(ops.lib().stac_mha_bf16(ops.ptr(qkv_d), ops.ptr(vt_d), ops.ptr(kv_d),
                                       b, t, t_pad, d, h, ops.ptr(ctx), ops.stream()))
+    torch.cuda.synchronize()
     q, k, v = (x.float().view(b, t, h, 64).transpose(1, 2) for x in qkv.split(d, dim=-1))
     mask = torch.arange(t)[None, :] >= kv[:, None]
     s = (q @ k.transpose(-1, -2)).masked_fill(mask[:, None, None, :], float("-inf"))

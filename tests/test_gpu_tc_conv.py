@@ -34,8 +34,9 @@ def test_conv1_bf16(b, t1):
     assert ref.shape == (b, t2, 20, 256)
     wp = w.permute(2, 3, 0, 1).reshape(9, 256, 256).to(torch.bfloat16).contiguous()
     out = torch.full((b, t2, 20, 256), float("nan"), device="cuda")
-    ops.check(ops.lib().stac_conv1_bf16(ops.ptr(_pack_padded(x0).cuda()), ops.ptr(wp.cuda()), ops.ptr(bias.cuda()),
-                                        b, t1, ops.ptr(out), ops.stream()))
+    x_d, w_d, b_d = _pack_padded(x0).cuda(), wp.cuda(), bias.cuda()     # keep alive across the async launch
+    ops.check(ops.lib().stac_conv1_bf16(ops.ptr(x_d), ops.ptr(w_d), ops.ptr(b_d), b, t1, ops.ptr(out), ops.stream()))
+    torch.cuda.synchronize()
     got = out.cpu()
     assert not torch.isnan(got).any()
     assert rel_l2(got, ref) < 1e-5, rel_l2(got, ref)

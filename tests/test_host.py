@@ -1,0 +1,176 @@
+"""Host-side logic and the C-ABI boundary, without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import stac_speech_translation_b200 as sb
+from stac_speech_translation_b200 import _lib, ops, synth
+from util import TINY, oracle_modules
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "stac_b200.h")).read()
+    declared = set(re.findall(r"\b(stac_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.exported_symbols())                 # ctypes table mirrors the header
+    handle = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(handle, name), name
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (stac_\w+)", nm))
+    assert exported == declared
+    assert _lib.lib().stac_version() == 100
+    assert b"invalid argument" in _lib.lib().stac_error_string(-1)
+    assert _lib.lib().stac_fbank_tables_floats() == 2692
+    assert _lib.lib().stac_conv0_padded_elems(2, 501) == 2 * 4 * 252 * 21 * 256
+
+
+def test_state_dict_layout_matches_speechbrain_keys():
+    mods = sb.build_modules(sb.HParams(**TINY, output_neurons=64), "bf16", device="cpu")
+    model = torch.nn.ModuleList([mods["CNN"], mods["Transformer"], mods["ctc_lin"], mods["ctc_lin"]])
+    keys = set(model.state_dict())
+    for k in ["0.convblock_0.convs.conv_0.conv.weight", "0.convblock_1.convs.conv_0.conv.bias",
+              "0.convblock_0.convs.norm_0.norm.weight", "0.convblock_1.convs.norm_0.norm.bias",
+              "1.custom_src_module.layers.0.w.weight", "1.custom_src_module.layers.0.w.bias",
+              "1.positional_encoding.pe", "1.encoder.layers.0.self_att.att.in_proj_weight",
+              "1.encoder.layers.1.self_att.att.out_proj.bias", "1.encoder.layers.0.pos_ffn.ffn.0.weight",
+              "1.encoder.layers.0.pos_ffn.ffn.3.bias", "1.encoder.layers.1.norm1.norm.weight",
+              "1.encoder.layers.1.norm2.norm.bias", "1.encoder.norm.norm.weight", "2.w.weight", "3.w.bias"]:
+        assert k in keys, k
+    sd = model.state_dict()
+    assert sd["0.convblock_0.convs.conv_0.conv.weight"].shape == (256, 1, 3, 3)
+    assert sd["0.convblock_1.convs.conv_0.conv.weight"].shape == (256, 256, 3, 3)
+    assert sd["0.convblock_0.convs.norm_0.norm.weight"].shape == (40, 256)
+    assert sd["0.convblock_1.convs.norm_0.norm.weight"].shape == (20, 256)
+    assert sd["1.custom_src_module.layers.0.w.weight"].shape == (128, 5120)
+    assert sd["1.positional_encoding.pe"].shape == (1, 2500, 128)
+    # an oracle (SpeechBrain-layout) checkpoint loads unchanged, and vice versa
+    omods = oracle_modules(TINY, vocab=64)
+    for k in ("CNN", "Transformer", "ctc_lin"):
+        r = mods[k].load_state_dict(omods[k].state_dict(), strict=True)
+        assert not r.missing_keys and not r.unexpected_keys
+        omods[k].load_state_dict(mods[k].state_dict(), strict=True)
+    assert torch.equal(mods["Transformer"].positional_encoding.pe, omods["Transformer"].positional_encoding.pe)
+
+
+def test_weight_packing_follows_checkpoint_updates():
+    mods = sb.build_modules(sb.HParams(**TINY, output_neurons=64), "fp32", device="cpu")
+    tr = mods["Transformer"]
+    p1 = tr.packed()
+    assert tr.packed() is p1                                        # cached while parameters are untouched
+    d = 128
+    att = tr.encoder.layers[0].self_att.att
+    assert torch.allclose(p1.layers[0].w_qkv[:d], att.in_proj_weight[:d] / 8)      # 1/sqrt(64) folded into W_q
+    assert torch.equal(p1.layers[0].w_qkv[d:], att.in_proj_weight[d:].detach())
+    w_src_before = p1.w_src.clone()      # fp32 packs alias the parameters, so keep a copy
+    sd = {k: v * 0.5 if v.is_floating_point() else v for k, v in tr.state_dict().items()}
+    tr.load_state_dict(sd)                                          # e.g. checkpoint averaging, inference.py:228-233
+    p2 = tr.packed()
+    assert p2 is not p1 and torch.allclose(p2.w_src, w_src_before * 0.5)
+    cnn = mods["CNN"]
+    w = cnn.packed()
+    assert w.w1.shape == (256, 9, 256)
+    c1 = cnn.convblock_1.convs.conv_0.conv.weight
+    assert torch.equal(w.w1[5, 2 * 3 + 1, 77], c1[5, 77, 2, 1].detach())           # tap = kf*3 + kt
+    mods16 = sb.build_modules(sb.HParams(**TINY, output_neurons=64), "bf16", device="cpu")
+    wb = mods16["CNN"].packed()
+    assert wb.w1.shape == (9, 256, 256) and wb.w1.dtype == torch.bfloat16
+
+
+def test_no_cpu_fallback_and_clear_errors():
+    mods = sb.build_modules(sb.HParams(**TINY, output_neurons=64), "bf16", device="cpu")
+    with pytest.raises(sb.StacB200Error, match="no CPU fallback"):
+        mods["compute_features"](torch.zeros(1, 16000))
+    with pytest.raises(sb.StacB200Error, match="no CPU fallback"):
+        mods["log_softmax"](torch.zeros(2, 3, 64))
+    mods["Transformer"].train()
+    with pytest.raises(sb.StacB200Error, match="inference-only"):
+        mods["Transformer"].encode(torch.zeros(1, 4, 5120))
+    mods["normalize"].train()
+    with pytest.raises(sb.StacB200Error, match="inference-only"):
+        mods["normalize"](torch.zeros(1, 4, 80), torch.ones(1))
+    mods["normalize"].eval()
+    with pytest.raises(sb.StacB200Error, match="no statistics"):
+        mods["normalize"](torch.zeros(1, 4, 80), torch.ones(1))
+    with pytest.raises(sb.StacB200Error):
+        sb.Fbank(n_mels=40)
+    with pytest.raises(sb.StacB200Error):
+        sb.TransformerMultiTask(5000, 5120, d_model=256, nhead=4, normalize_before=False, activation=torch.nn.GELU)
+    with pytest.raises(sb.StacB200Error, match="decoder"):
+        mods["Transformer"].eval().decode(torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 4, 128))
+
+
+def test_kv_lengths_match_reference_masks():
+    for t2 in (26, 251, 751, 1501):
+        wl = torch.rand(64, generator=torch.Generator().manual_seed(t2)).clamp_min(0.05)
+        wl[0] = 1.0
+        enc = ops.kv_lengths(wl, 64, t2, "cpu", train_mask=False)
+        trn = ops.kv_lengths(wl, 64, t2, "cpu", train_mask=True)
+        keep_e = ~(torch.arange(t2)[None, :].to(wl) > torch.floor(wl * t2)[:, None])          # encode() :289-294
+        keep_t = oracle.speechbrain_path.length_to_mask(torch.round(wl * t2), max_len=t2)     # make_masks :225-226
+        assert torch.equal(enc.long(), keep_e.sum(1))
+        assert torch.equal(trn.long(), keep_t.sum(1).clamp_min(1))
+    assert ops.kv_lengths(None, 3, 10, "cpu", False).tolist() == [10, 10, 10]
+
+
+def test_normalizer_checkpoint_roundtrip(tmp_path):
+    omods = oracle_modules(TINY, vocab=64)
+    n = sb.InputNormalization(norm_type="global", update_until_epoch=4)
+    n._load_statistics_dict(omods["normalize"]._statistics_dict())
+    n._save(tmp_path / "normalizer.ckpt")
+    m = sb.InputNormalization(norm_type="global", update_until_epoch=4)
+    m._load(tmp_path / "normalizer.ckpt")
+    assert torch.equal(m.glob_mean, omods["normalize"].glob_mean) and m.count == omods["normalize"].count
+    # calibrate() is SpeechBrain's first train-mode statistics step
+    wavs, wl = synth.synth_batch([1.0, 0.6], seed=5)
+    feats = omods["compute_features"](wavs)
+    ref = oracle.InputNormalization(norm_type="global")
+    ref.train(); ref(feats.clone(), wl)
+    c = sb.InputNormalization(norm_type="global")
+    c.calibrate(feats, wl)
+    assert torch.allclose(c.glob_mean, ref.glob_mean) and torch.allclose(c.glob_std, ref.glob_std)
+
+
+def test_synthetic_audio_and_bucketing():
+    wavs, wl = synth.synth_batch([2.0, 1.0], seed=1)
+    wavs2, _ = synth.synth_batch([2.0, 1.0], seed=1)
+    assert torch.equal(wavs, wavs2) and wavs.shape == (2, 32000)
+    assert wl.tolist() == [1.0, 0.5] and float(wavs[1, 16000:].abs().max()) == 0.0
+    assert float(wavs.abs().max()) <= 1.0
+    d = synth.lognormal_durations(4096, seed=0)
+    assert d.min() >= 1.0 and d.max() <= 30.0
+    bk = synth.bucket_batches(d, max_batch_len=200.0, num_buckets=50, max_batch_ex=128)
+    seen = sorted(i for b in bk.batches for i in b)
+    assert seen == list(range(4096))                                 # every utterance exactly once
+    for b in bk.batches:
+        assert len(b) <= 128 and len(b) * d[b].max() <= 200.0 + 30.0
+    for world in (2, 4, 8):
+        shards = synth.shard_batches(bk, world)
+        assert sorted(i for s in shards for i in s) == list(range(len(bk.batches)))   # whole batches, once each
+        loads = [sum(synth.batch_cost(d, bk.batches[i]) for i in s) for s in shards]
+        assert max(loads) / (sum(loads) / world) < 1.05             # LPT keeps ranks within 5 %
+
+
+def test_ctc_greedy_collapse():
+    ids = torch.tensor([[0, 7, 7, 0, 7, 8, 8, 0], [5, 5, 5, 0, 0, 3, 9, 9]])
+    assert sb.ctc_greedy_collapse(ids, [8, 6]) == [[7, 7, 8], [5, 3]]
+
+
+def test_fbank_tables_match_oracle_filterbank():
+    # build_fbank_tables needs the library only for its size check
+    tab = ops.build_fbank_tables("cpu")
+    fb = oracle.speechbrain_path.Filterbank(n_mels=80).fbank_matrix()      # [201, 80]
+    assert torch.equal(tab[:400], torch.hamming_window(400))
+    start, count, w = tab[1252:1332].long(), tab[1332:1412].long(), tab[1412:].view(80, 16)
+    dense = torch.zeros(201, 80)
+    for m in range(80):
+        dense[start[m]:start[m] + count[m], m] = w[m, :count[m]]
+    assert torch.equal(dense, fb)                                    # bit-identical sparse copy of the matrix
