@@ -9,9 +9,16 @@
 // Reference behaviour replaced: nn.Linear / nn.Conv2d calls inside SpeechBrain reached from
 //   /root/reference/stac-st/modules/TransformerMultiTask.py:296,304-308 and inference.py:99,106.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2-5 = epilogue (TMEM -> registers -> fused bias/GELU/residual -> global).  Two accumulator
-// stages in TMEM (2 x BLOCK_N columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2.. =
+// epilogue.  Two accumulator stages in TMEM (2 x 256 columns) let the epilogue of tile i overlap
+// the MMAs of tile i+1.
+//   linear mode: 16 epilogue warps (4 per TMEM lane quarter, 64 columns each).  The encoder GEMMs
+//     have K = 256..1024, so a 128x256 tile is only 2-8 k cycles of MMA and the epilogue is the
+//     critical path: results go TMEM -> registers -> fused bias/GELU -> 128B-swizzled staging tile in
+//     shared memory -> one TMA store per 32-row x 128-byte box (full-line writes, bounds clipped by the
+//     tensor map).  An in-place residual (C += ...) is a TMA reduce-add, so the residual stream is never
+//     loaded into the SM.
+//   conv mode: 4 epilogue warps, direct stores (K = 2304: the MMAs hide the epilogue).
 #include <algorithm>
 #include "tc_common.cuh"
 
@@ -19,24 +26,27 @@ namespace {
 
 using namespace tc;
 
-constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16;
 constexpr int kConvRows = 120, kConvT = 6, kConvF = 20;  // conv A tile: 6 time steps x 20 freq bins
+constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 2 * BLOCK_N;
 
-template <int BLOCK_N>
+template <bool kConv>
 struct Cfg {
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : 6;
-  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N;  // 512 or 256 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStages = kConv ? 4 : 3;
+  static constexpr int kEpiWarps = kConv ? 4 : 16;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kStagingBytes = kConv ? 0 : kEpiWarps * 4096;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct EpiParams {
   const float* bias;
-  const float* resid;
+  const float* resid;      // direct-load residual (period > 0 -> row % period), NULL if none / reduce-add
   int64_t resid_period;
+  int reduce_add;          // 1: C += result through TMA reduce-add (in-place residual)
   int act;
   void* c;
   int c_bf16;
@@ -45,19 +55,54 @@ struct EpiParams {
   __nv_bfloat16* vt;
   int64_t vt_cols, seq_len, t_pad;
   // conv mode
-  int conv;           // 0 = linear, 1 = conv1 implicit GEMM
-  int t2_len;         // output time steps per utterance (conv)
+  int t2_len;         // output time steps per utterance
   int tiles_per_utt;  // ceil(T2 / 6)
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+// bf16-mode GELU: x * Phi(x) with Phi(x) - 0.5 = 0.5 erf(x / sqrt 2) ~ xc * Q(xc^2), xc = clamp(x, -4, 4), Q a
+// degree-8 polynomial (least-squares fit on [0, 4], fp32 Horner; max |gelu error| 1.6e-4 over [-8, 8], well under
+// the bf16 rounding of the stored activation).  13 FMA-pipe instructions and no MUFU op per element: the exact
+// erff() or an exp/rcp formulation would make the FFN1 epilogue slower than its MMAs and its HBM traffic.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float xc = fminf(fmaxf(x, -4.0f), 4.0f);
+  const float u = xc * xc;
+  float q = 8.524421446e-11f;
+  q = fmaf(q, u, -7.295211546e-09f);
+  q = fmaf(q, u, 2.791634870e-07f);
+  q = fmaf(q, u, -6.397717698e-06f);
+  q = fmaf(q, u, 9.969574603e-05f);
+  q = fmaf(q, u, -1.137302839e-03f);
+  q = fmaf(q, u, 9.885039181e-03f);
+  q = fmaf(q, u, -6.641801447e-02f);
+  q = fmaf(q, u, 3.989247680e-01f);
+  return x * fmaf(xc, q, 0.5f);
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool kConv>
+__global__ void __launch_bounds__(Cfg<kConv>::kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const EpiParams ep, const int num_m_tiles, const int num_n_tiles, const int num_k_blocks) {
-  using C = Cfg<BLOCK_N>;
+                 const __grid_constant__ CUtensorMap tmap_c, const EpiParams ep, const int num_m_tiles,
+                 const int num_n_tiles, const int num_k_blocks) {
+  using C = Cfg<kConv>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  const uint32_t staging_base = smem_base + C::kStages * kStageBytes;
+  const uint32_t bar_base = staging_base + C::kStagingBytes;
   // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -71,12 +116,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (!kConv) prefetch_tmap(&tmap_c);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), C::kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -92,21 +138,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
-        const int conv_b = ep.conv ? m_tile / ep.tiles_per_utt : 0;
-        const int conv_t0 = ep.conv ? (m_tile - conv_b * ep.tiles_per_utt) * kConvT : 0;
+        const int conv_b = kConv ? m_tile / ep.tiles_per_utt : 0;
+        const int conv_t0 = kConv ? (m_tile - conv_b * ep.tiles_per_utt) * kConvT : 0;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-          const uint32_t b_dst = a_dst + C::kABytes;
-          if (ep.conv) {
-            mbar_arrive_expect_tx(full_bar(stage), kConvRows * BLOCK_K * 2 + C::kBBytes);
+          const uint32_t a_dst = smem_base + stage * kStageBytes;
+          const uint32_t b_dst = a_dst + kABytes;
+          if (kConv) {
+            mbar_arrive_expect_tx(full_bar(stage), kConvRows * BLOCK_K * 2 + kBBytes);
             const int tap = kb >> 2, c0 = (kb & 3) * BLOCK_K;
             const int kf = tap / 3, kt = tap - 3 * kf;
             tma_load_5d(a_dst, &tmap_a, full_bar(stage), c0, kf >> 1, conv_t0 + (kt >> 1),
                         (kt & 1) * 2 + (kf & 1), conv_b);
             tma_load_2d(b_dst, &tmap_b, full_bar(stage), c0, tap * 256 + n_tile * BLOCK_N);
           } else {
-            mbar_arrive_expect_tx(full_bar(stage), C::kStageBytes);
+            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
             tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m_tile * BLOCK_M);
             tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
           }
@@ -114,6 +160,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
@@ -129,9 +176,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+          const uint32_t a_addr = smem_base + stage * kStageBytes;
           const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-          const uint64_t b_desc = make_smem_desc_sw128(a_addr + C::kABytes);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // +32 B per UMMA_K step inside the 128-B swizzle atom (descriptor address unit = 16 B)
@@ -144,100 +191,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    __syncwarp();
+  } else if constexpr (kConv) {
+    // ===================== conv epilogue: 4 warps, direct stores of the pre-LayerNorm output ==========
+    const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+      const int m_tile = tile / num_n_tiles;
       const int r_local = quarter * 32 + lane;
-      int64_t row;
-      bool row_ok;
-      if (ep.conv) {
-        const int conv_b = m_tile / ep.tiles_per_utt;
-        const int t0 = (m_tile - conv_b * ep.tiles_per_utt) * kConvT;
-        row = ((int64_t)conv_b * ep.t2_len + t0) * kConvF + r_local;
-        row_ok = r_local < kConvRows && (t0 + r_local / kConvF) < ep.t2_len;
-      } else {
-        row = (int64_t)m_tile * BLOCK_M + r_local;
-        row_ok = row < ep.m;
-      }
+      const int conv_b = m_tile / ep.tiles_per_utt;
+      const int t0 = (m_tile - conv_b * ep.tiles_per_utt) * kConvT;
+      const int64_t row = ((int64_t)conv_b * ep.t2_len + t0) * kConvF + r_local;
+      const bool row_ok = r_local < kConvRows && (t0 + r_local / kConvF) < ep.t2_len;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
-      const int64_t rrow = (ep.resid && ep.resid_period > 0) ? row % ep.resid_period : row;
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(t_addr + ch * 32, v);
         tmem_ld_wait();
-        const int col0 = n_tile * BLOCK_N + ch * 32;
-        if (!row_ok || col0 >= ep.n) continue;
-        float f[32];
+        if (!row_ok) continue;
+        float* dst = reinterpret_cast<float*>(ep.c) + row * BLOCK_N + ch * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        const bool full = col0 + 32 <= ep.n;
-        if (ep.bias) {
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
-              f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (col0 + i < ep.n) f[i] += __ldg(ep.bias + col0 + i);
-          }
-        }
-        if (ep.act == STAC_ACT_GELU_ERF) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-        }
-        if (ep.resid) {
-          const float* rp = ep.resid + rrow * ep.n + col0;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 rv = *reinterpret_cast<const float4*>(rp + i);
-              f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (col0 + i < ep.n) f[i] += rp[i];
-          }
-        }
-        if (ep.vt != nullptr && col0 >= ep.n - ep.vt_cols) {
-          // V columns of a packed QKV projection -> V^T [B*H][64][t_pad] (keys contiguous)
-          const int64_t b = row / ep.seq_len, t = row - b * ep.seq_len;
-          const int vcol = (int)(col0 - (ep.n - ep.vt_cols));
-          const int64_t heads = ep.vt_cols >> 6;
-          __nv_bfloat16* dst = ep.vt + ((b * heads + (vcol >> 6)) * 64 + (vcol & 63)) * ep.t_pad + t;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) dst[(int64_t)i * ep.t_pad] = __float2bfloat16_rn(f[i]);
-        } else if (ep.c_bf16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.n + col0;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              *reinterpret_cast<uint4*>(dst + i) =
-                  make_uint4(pack_bf16x2(f[i], f[i + 1]), pack_bf16x2(f[i + 2], f[i + 3]),
-                             pack_bf16x2(f[i + 4], f[i + 5]), pack_bf16x2(f[i + 6], f[i + 7]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (col0 + i < ep.n) dst[i] = __float2bfloat16_rn(f[i]);
-          }
-        } else {
-          float* dst = reinterpret_cast<float*>(ep.c) + row * ep.n + col0;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (col0 + i < ep.n) dst[i] = f[i];
-          }
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + ch * 32 + i));
+          *reinterpret_cast<float4*>(dst + i) =
+              make_float4(__uint_as_float(v[i]) + bv.x, __uint_as_float(v[i + 1]) + bv.y,
+                          __uint_as_float(v[i + 2]) + bv.z, __uint_as_float(v[i + 3]) + bv.w);
         }
       }
       tc_fence_before();
@@ -245,13 +227,124 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  } else {
+    // ===================== linear epilogue: 16 warps =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int cgrp = ew >> 2;              // 64-column group of the 256-wide tile
+    const uint32_t stage_buf = staging_base + ew * 4096;
+    const uint32_t my_row = stage_buf + lane * 128;
+    const int sw = lane & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+      const int row0 = m_tile * BLOCK_M + quarter * 32;
+      const int64_t row = (int64_t)row0 + lane;
+      const bool row_ok = row < ep.m;
+      const int colg = n_tile * BLOCK_N + cgrp * 64;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BLOCK_N + cgrp * 64 + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float x[32];
+        {
+          uint32_t v[32];
+          tmem_ld32(t_addr + half * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+        }
+        if (half == 1) {
+          // both halves are in registers / staged: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        const int col0 = colg + half * 32;
+        if (col0 >= ep.n) continue;                    // warp-uniform
+        if (ep.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            // n % 8 == 0, so a 4-column group is either fully inside or fully outside the matrix
+            if (col0 + i < ep.n) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+              x[i] += bv.x; x[i + 1] += bv.y; x[i + 2] += bv.z; x[i + 3] += bv.w;
+            }
+          }
+        }
+        if (ep.act == STAC_ACT_GELU_ERF) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = gelu_fast(x[i]);
+        }
+        if (ep.resid && row_ok) {
+          const int64_t rrow = ep.resid_period > 0 ? row % ep.resid_period : row;
+          const float* rp = ep.resid + rrow * ep.n + col0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            if (col0 + i < ep.n) {
+              const float4 rv = __ldg(reinterpret_cast<const float4*>(rp + i));
+              x[i] += rv.x; x[i + 1] += rv.y; x[i + 2] += rv.z; x[i + 3] += rv.w;
+            }
+          }
+        }
+        if (ep.vt != nullptr && col0 >= ep.n - ep.vt_cols) {
+          // V columns of a packed QKV projection -> V^T [B*H][64][t_pad] (keys contiguous)
+          if (row_ok) {
+            const int64_t b = row / ep.seq_len, t = row - b * ep.seq_len;
+            const int vcol = (int)(col0 - (ep.n - ep.vt_cols));
+            const int64_t heads = ep.vt_cols >> 6;
+            __nv_bfloat16* dst = ep.vt + ((b * heads + (vcol >> 6)) * 64 + (vcol & 63)) * ep.t_pad + t;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[(int64_t)i * ep.t_pad] = __float2bfloat16_rn(x[i]);
+          }
+          continue;
+        }
+        if (ep.c_bf16) {
+          // 64 bf16 columns = one 128-byte staging row; this half fills 16-byte chunks half*4 .. +3
+          if (half == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st_shared_v4(my_row + (((half * 4 + j) ^ sw) << 4), pack_bf16x2(x[8 * j], x[8 * j + 1]),
+                         pack_bf16x2(x[8 * j + 2], x[8 * j + 3]), pack_bf16x2(x[8 * j + 4], x[8 * j + 5]),
+                         pack_bf16x2(x[8 * j + 6], x[8 * j + 7]));
+          }
+          const bool last_half = half == 1 || colg + 32 >= ep.n;
+          if (last_half) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && row0 < ep.m) { tma_store_2d(&tmap_c, stage_buf, colg, row0); bulk_commit(); }
+          }
+        } else {
+          // 32 fp32 columns = one 128-byte staging row
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            st_shared_v4(my_row + ((j ^ sw) << 4), __float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                         __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3]));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < ep.m) {
+            if (ep.reduce_add) tma_reduce_add_2d(&tmap_c, stage_buf, col0, row0);
+            else tma_store_2d(&tmap_c, stage_buf, col0, row0);
+            bulk_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -266,19 +359,19 @@ int num_sms() {
   return n;
 }
 
-template <int BLOCK_N>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiParams& ep, int m_tiles, int n_tiles,
-           int k_blocks, cudaStream_t st) {
-  using C = Cfg<BLOCK_N>;
+template <bool kConv>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const EpiParams& ep, int m_tiles,
+           int n_tiles, int k_blocks, cudaStream_t st) {
+  using C = Cfg<kConv>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<kConv>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
   const int grid = std::min(m_tiles * n_tiles, num_sms());
-  gemm_bf16_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, ep, m_tiles, n_tiles, k_blocks);
+  gemm_bf16_kernel<kConv><<<grid, C::kThreads, C::kSmemBytes, st>>>(ta, tb, tcm, ep, m_tiles, n_tiles, k_blocks);
   STAC_LAUNCH_CHECK();
 }
 
@@ -293,34 +386,44 @@ extern "C" int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float*
   STAC_REQUIRE(c_dtype == STAC_DT_F32 || c_dtype == STAC_DT_BF16);
   if (k % BLOCK_K != 0 || n % 8 != 0 || m >= (1ll << 31) - 256) return STAC_ERR_UNSUPPORTED_SHAPE;
   if (vt_out) {
-    STAC_REQUIRE(vt_cols > 0 && vt_cols % 64 == 0 && vt_cols <= n && (n - vt_cols) % 32 == 0);
+    STAC_REQUIRE(vt_cols > 0 && vt_cols % 64 == 0 && vt_cols <= n && (n - vt_cols) % 64 == 0);
     STAC_REQUIRE(seq_len > 0 && t_pad >= seq_len && t_pad % 8 == 0 && m % seq_len == 0);
   }
-  const int block_n = (n % 256 == 0 || n > 1024) ? 256 : 128;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tcm;
   {
     const uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};
     const uint64_t str[1] = {(uint64_t)k * 2};
     const uint32_t box[2] = {BLOCK_K, BLOCK_M};
-    int r = encode_bf16_map(&ta, a, 2, dims, str, box);
+    int r = encode_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a, 2, dims, str, box);
     if (r != STAC_OK) return r;
   }
   {
     const uint64_t dims[2] = {(uint64_t)k, (uint64_t)n};
     const uint64_t str[1] = {(uint64_t)k * 2};
-    const uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
-    int r = encode_bf16_map(&tb, w, 2, dims, str, box);
+    const uint32_t box[2] = {BLOCK_K, BLOCK_N};
+    int r = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w, 2, dims, str, box);
+    if (r != STAC_OK) return r;
+  }
+  {
+    const bool bf = c_dtype == STAC_DT_BF16;
+    const uint64_t dims[2] = {(uint64_t)n, (uint64_t)m};
+    const uint64_t str[1] = {(uint64_t)n * (bf ? 2 : 4)};
+    const uint32_t box[2] = {bf ? 64u : 32u, 32u};
+    int r = encode_map(&tcm, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, c, 2, dims,
+                       str, box);
     if (r != STAC_OK) return r;
   }
   EpiParams ep{};
-  ep.bias = bias; ep.resid = resid; ep.resid_period = resid_period; ep.act = act;
+  ep.bias = bias; ep.act = act;
+  // an in-place, row-aligned fp32 residual becomes a TMA reduce-add; anything else is loaded directly
+  ep.reduce_add = (resid != nullptr && resid == c && resid_period == 0 && c_dtype == STAC_DT_F32) ? 1 : 0;
+  ep.resid = ep.reduce_add ? nullptr : resid;
+  ep.resid_period = resid_period;
   ep.c = c; ep.c_bf16 = c_dtype == STAC_DT_BF16; ep.m = m; ep.n = n;
   ep.vt = reinterpret_cast<__nv_bfloat16*>(vt_out); ep.vt_cols = vt_cols; ep.seq_len = seq_len; ep.t_pad = t_pad;
-  ep.conv = 0; ep.t2_len = 0; ep.tiles_per_utt = 1;
-  const int m_tiles = (int)ceil_div64(m, BLOCK_M), k_blocks = (int)(k / BLOCK_K);
-  if (block_n == 256)
-    return launch<256>(ta, tb, ep, m_tiles, (int)ceil_div64(n, 256), k_blocks, as_stream(stream));
-  return launch<128>(ta, tb, ep, m_tiles, (int)ceil_div64(n, 128), k_blocks, as_stream(stream));
+  ep.t2_len = 0; ep.tiles_per_utt = 1;
+  return launch<false>(ta, tb, tcm, ep, (int)ceil_div64(m, BLOCK_M), (int)ceil_div64(n, BLOCK_N),
+                       (int)(k / BLOCK_K), as_stream(stream));
 }
 
 extern "C" int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, const float* b1,
@@ -335,18 +438,18 @@ extern "C" int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, 
     const uint64_t dims[5] = {256, 21, (uint64_t)tp2, 4, (uint64_t)batch};
     const uint64_t str[4] = {256 * 2, 21 * 256 * 2, (uint64_t)tp2 * 21 * 256 * 2, (uint64_t)4 * tp2 * 21 * 256 * 2};
     const uint32_t box[5] = {BLOCK_K, kConvF, kConvT, 1, 1};
-    int r = encode_bf16_map(&ta, xpad, 5, dims, str, box);
+    int r = encode_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, xpad, 5, dims, str, box);
     if (r != STAC_OK) return r;
   }
   {
     const uint64_t dims[2] = {256, 9 * 256};
     const uint64_t str[1] = {256 * 2};
     const uint32_t box[2] = {BLOCK_K, 256};
-    int r = encode_bf16_map(&tb, w1_packed, 2, dims, str, box);
+    int r = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w1_packed, 2, dims, str, box);
     if (r != STAC_OK) return r;
   }
   EpiParams ep{};
   ep.bias = b1; ep.c = out; ep.c_bf16 = 0; ep.m = batch * t2 * kConvF; ep.n = 256;
-  ep.conv = 1; ep.t2_len = (int)t2; ep.tiles_per_utt = tiles_per_utt;
-  return launch<256>(ta, tb, ep, (int)(batch * tiles_per_utt), 1, 36, as_stream(stream));
+  ep.t2_len = (int)t2; ep.tiles_per_utt = tiles_per_utt;
+  return launch<true>(ta, tb, tb /*unused*/, ep, (int)(batch * tiles_per_utt), 1, 36, as_stream(stream));
 }

@@ -162,17 +162,17 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor of `rank` dims (dims[0] innermost, contiguous), strides in BYTES for dims 1..rank-1,
-// box dims per dimension, 128-byte swizzle, zero fill out of bounds.
-inline int encode_bf16_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box) {
+// Tensor of `rank` dims (dims[0] innermost, contiguous), strides in BYTES for dims 1..rank-1,
+// box dims per dimension, 128-byte swizzle, zero fill out of bounds (loads) / clipping (stores).
+inline int encode_map(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank,
+                      const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return STAC_ERR_DRIVER_ENTRY;
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+  CUresult r = fn(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
                   bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? STAC_OK : STAC_ERR_TENSOR_MAP;

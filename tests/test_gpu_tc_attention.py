@@ -10,7 +10,8 @@ from stac_speech_translation_b200 import ops  # noqa: E402
 
 @pytest.mark.parametrize("t,lens,d,h", [(128, [128], 64, 1), (251, [251, 100, 1], 256, 4), (64, [64, 33], 128, 2),
                                          (130, [129, 130, 5], 256, 4), (751, [751, 400], 256, 4),
-                                         (300, [300, 299], 512, 8)])
+                                         (300, [300, 299], 512, 8), (300, [300 - 3 * i for i in range(40)], 256, 4),
+                                         (100, [100 - i for i in range(90)], 128, 2), (1501, [1501, 1200], 128, 2)])
 def test_mha_bf16(t, lens, d, h):
     g = torch.Generator().manual_seed(t + d)
     b = len(lens)
