@@ -93,15 +93,18 @@ int stac_conv0_ln_lrelu(const float* feats /*[B,T,80]*/, const float* w0, const 
                         void* out, int out_mode, void* stream);
 
 /* Block 1 convolution only (pre-LayerNorm), fp32 CUDA-core implicit GEMM:
- *   x [B,T1,40,256] fp32, w1 torch layout [256(out),256(in),3(freq),3(time)], out [B,T2,20,256]. */
+ *   x [B,T1,40,256] fp32, w1 packed [256(out)][9 = kf*3+kt][256(in)], out [B,T2,20,256]. */
 int stac_conv1_f32(const float* x, const float* w1, const float* b1, int64_t batch, int64_t t1,
                    float* out, void* stream);
 
-/* Block 1 convolution on tcgen05 tensor cores (bf16 operands, fp32 accumulate):
+/* Block 1 on tcgen05 tensor cores (bf16 operands, fp32 accumulate) with the whole block fused:
+ * conv + bias, LayerNorm over (20,256) eps 1e-5, LeakyReLU(0.01), all in the GEMM epilogue.
  *   xpad: block-0 output in the padded parity-split bf16 layout above;
- *   w1_packed: bf16 [9 = kt*3+kf][256(out)][256(in)];  out fp32 [B,T2,20,256] (pre-LN). */
+ *   w1_packed: bf16 [9 = kf*3+kt][256(out)][256(in)];  ln_g/ln_b [20*256];
+ *   out: bf16 [B,T2,20*256] (what the src-linear GEMM of the encoder consumes). */
 int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, const float* b1,
-                    int64_t batch, int64_t t1, float* out, void* stream);
+                    const float* ln_g, const float* ln_b, int64_t batch, int64_t t1, uint16_t* out,
+                    void* stream);
 
 /* LayerNorm over a whole row of `dim` elements (dim = F*C = 10240 / 5120) + LeakyReLU. */
 int stac_group_ln_lrelu(const float* x, int64_t rows, int64_t dim, const float* gamma,

@@ -29,7 +29,7 @@ _SIGNATURES = {
     "stac_conv0_padded_elems": (c_int64, [c_int64, c_int64]),
     "stac_conv0_ln_lrelu": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, c_int, _P]),
     "stac_conv1_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
-    "stac_conv1_bf16": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
+    "stac_conv1_bf16": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P]),
     "stac_group_ln_lrelu": (c_int, [_P, c_int64, c_int64, _P, _P, c_float, c_float, _P, c_int, _P]),
     "stac_layernorm": (c_int, [_P, c_int64, c_int64, _P, _P, c_float, _P, _P, _P]),
     "stac_gemm_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, _P]),

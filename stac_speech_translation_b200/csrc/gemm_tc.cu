@@ -35,10 +35,12 @@ constexpr int kTmemCols = 2 * BLOCK_N;
 
 template <bool kConv>
 struct Cfg {
-  static constexpr int kStages = kConv ? 4 : 3;
+  static constexpr int kStages = 3;
   static constexpr int kEpiWarps = kConv ? 4 : 16;
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
-  static constexpr int kStagingBytes = kConv ? 0 : kEpiWarps * 4096;
+  // linear: one 4 KB TMA-store staging tile per epilogue warp.
+  // conv:   LayerNorm affine [2][20][256] fp32 (40 KB) | bias (1 KB) | row statistics (1 KB) | 2 x 16 KB output staging
+  static constexpr int kStagingBytes = kConv ? (40960 + 1024 + 1024 + 2 * 16384) : kEpiWarps * 4096;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -57,6 +59,8 @@ struct EpiParams {
   // conv mode
   int t2_len;         // output time steps per utterance
   int tiles_per_utt;  // ceil(T2 / 6)
+  const float* ln_g;  // [20*256] LayerNorm affine of the second block
+  const float* ln_b;
 };
 
 // bf16-mode GELU: x * Phi(x) with Phi(x) - 0.5 = 0.5 erf(x / sqrt 2) ~ xc * Q(xc^2), xc = clamp(x, -4, 4), Q a
@@ -86,6 +90,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -116,7 +126,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    if (!kConv) prefetch_tmap(&tmap_c);
+    prefetch_tmap(&tmap_c);
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), C::kEpiWarps); }
     fence_barrier_init();
@@ -193,40 +203,120 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else if constexpr (kConv) {
-    // ===================== conv epilogue: 4 warps, direct stores of the pre-LayerNorm output ==========
+    // ===================== conv epilogue: 4 warps, fused bias + LayerNorm(20 x 256) + LeakyReLU ==========
+    // Thread = accumulator row (t_local, f2); a time step's LayerNorm group is 20 rows x 256 columns, all inside
+    // this CTA's tile.  Pass 1 reads the tile from TMEM for the row sums, pass 2 re-reads it, normalises and
+    // stages bf16 64-channel slabs (128B-swizzled) that leave through TMA stores into [B, T2, 20*256].
     const int quarter = warp & 3;
+    const int r_local = quarter * 32 + lane;
+    const int tid_e = (warp - 2) * 32 + lane;
+    const int tl = r_local / kConvF, f2 = r_local - tl * kConvF;
+    unsigned char* sgen = smem_raw + (staging_base - smem_u32(smem_raw));
+    float* gam_s = reinterpret_cast<float*>(sgen);
+    float* bet_s = gam_s + kConvF * 256;
+    float* bias_s = bet_s + kConvF * 256;
+    float2* stats_s = reinterpret_cast<float2*>(bias_s + 256);
+    const uint32_t out_stage = staging_base + 40960 + 2048;
+    // affine rows are rotated by 4 floats per freq bin so that lanes (= consecutive bins) hit distinct banks
+    for (int i = tid_e; i < kConvF * 256; i += 128) {
+      const int f = i >> 8, c = i & 255;
+      gam_s[f * 256 + ((c + 4 * f) & 255)] = __ldg(ep.ln_g + i);
+      bet_s[f * 256 + ((c + 4 * f) & 255)] = __ldg(ep.ln_b + i);
+    }
+    for (int i = tid_e; i < 256; i += 128) bias_s[i] = __ldg(ep.bias + i);
+    epi_bar_sync();
+    const float* g_row = gam_s + f2 * 256;
+    const float* b_row = bet_s + f2 * 256;
+    const int rot = 4 * f2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / num_n_tiles;
-      const int r_local = quarter * 32 + lane;
       const int conv_b = m_tile / ep.tiles_per_utt;
       const int t0 = (m_tile - conv_b * ep.tiles_per_utt) * kConvT;
-      const int64_t row = ((int64_t)conv_b * ep.t2_len + t0) * kConvF + r_local;
-      const bool row_ok = r_local < kConvRows && (t0 + r_local / kConvF) < ep.t2_len;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
+      // ---- pass 1: row sum and sum of squares of (acc + bias) ----
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(t_addr + ch * 32, v);
         tmem_ld_wait();
-        if (!row_ok) continue;
-        float* dst = reinterpret_cast<float*>(ep.c) + row * BLOCK_N + ch * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + ch * 32 + i));
-          *reinterpret_cast<float4*>(dst + i) =
-              make_float4(__uint_as_float(v[i]) + bv.x, __uint_as_float(v[i + 1]) + bv.y,
-                          __uint_as_float(v[i + 2]) + bv.z, __uint_as_float(v[i + 3]) + bv.w);
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + ch * 32 + i);
+          const float y0 = __uint_as_float(v[i]) + bv.x, y1 = __uint_as_float(v[i + 1]) + bv.y;
+          const float y2 = __uint_as_float(v[i + 2]) + bv.z, y3 = __uint_as_float(v[i + 3]) + bv.w;
+          s1 += (y0 + y1) + (y2 + y3);
+          s2 = fmaf(y0, y0, s2); s2 = fmaf(y1, y1, s2); s2 = fmaf(y2, y2, s2); s2 = fmaf(y3, y3, s2);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      stats_s[r_local] = make_float2(s1, s2);
+      epi_bar_sync();
+      float mean = 0.f, rstd = 0.f;
+      if (tl < kConvT) {
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int f = 0; f < kConvF; ++f) {
+          const float2 p = stats_s[tl * kConvF + f];
+          a1 += p.x; a2 += p.y;
+        }
+        mean = a1 * (1.0f / (kConvF * 256));
+        const float var = fmaxf(a2 * (1.0f / (kConvF * 256)) - mean * mean, 0.f);
+        rstd = rsqrtf(var + 1e-5f);
+      }
+      // ---- pass 2: normalise, affine, LeakyReLU, bf16, 64-channel slabs through TMA ----
+#pragma unroll 1
+      for (int slab = 0; slab < 4; ++slab) {
+        const uint32_t buf = out_stage + (slab & 1) * 16384;
+        if (tid_e == 0) bulk_wait_read1();     // the store issued two slabs ago has finished reading this buffer
+        epi_bar_sync();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int ch = slab * 2 + half;
+          uint32_t v[32];
+          tmem_ld32(t_addr + ch * 32, v);
+          tmem_ld_wait();
+          if (ch == BLOCK_N / 32 - 1) {
+            // last read of this accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int c = ch * 32 + i;
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + c);
+            const float4 g = *reinterpret_cast<const float4*>(g_row + ((c + rot) & 255));
+            const float4 be = *reinterpret_cast<const float4*>(b_row + ((c + rot) & 255));
+            float y[4] = {__uint_as_float(v[i]) + bv.x, __uint_as_float(v[i + 1]) + bv.y,
+                          __uint_as_float(v[i + 2]) + bv.z, __uint_as_float(v[i + 3]) + bv.w};
+            const float ga[4] = {g.x, g.y, g.z, g.w}, bb[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float a = rstd * ga[q];
+              float o = fmaf(y[q], a, fmaf(-mean, a, bb[q]));
+              y[q] = fmaxf(o, 0.01f * o);        // LeakyReLU(0.01)
+            }
+            pk[i >> 1] = pack_bf16x2(y[0], y[1]);
+            pk[(i >> 1) + 1] = pack_bf16x2(y[2], y[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            st_shared_v4(buf + r_local * 128 + (((half * 4 + j) ^ (r_local & 7)) << 4), pk[4 * j], pk[4 * j + 1],
+                         pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        fence_proxy_async_smem();
+        epi_bar_sync();
+        if (tid_e == 0) { tma_store_3d(&tmap_c, buf, slab * 64, t0 * kConvF, conv_b); bulk_commit(); }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (tid_e == 0) bulk_wait0();
+    __syncwarp();
   } else {
     // ===================== linear epilogue: 16 warps =====================
     const int ew = warp - 2;
@@ -427,12 +517,13 @@ extern "C" int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float*
 }
 
 extern "C" int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, const float* b1,
-                               int64_t batch, int64_t t1, float* out, void* stream) {
-  STAC_REQUIRE(xpad && w1_packed && b1 && out && batch > 0 && t1 >= 2 && t1 < (1 << 30));
+                               const float* ln_g, const float* ln_b, int64_t batch, int64_t t1, uint16_t* out,
+                               void* stream) {
+  STAC_REQUIRE(xpad && w1_packed && b1 && ln_g && ln_b && out && batch > 0 && t1 >= 2 && t1 < (1 << 30));
   const int64_t t2 = (t1 - 1) / 2 + 1, tp2 = (t1 + 3) / 2;
   const int tiles_per_utt = (int)ceil_div64(t2, kConvT);
   if (batch * tiles_per_utt >= (1ll << 31)) return STAC_ERR_UNSUPPORTED_SHAPE;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tcm;
   {
     // [B][4 planes][Tp2][21][256] bf16, innermost first
     const uint64_t dims[5] = {256, 21, (uint64_t)tp2, 4, (uint64_t)batch};
@@ -448,8 +539,16 @@ extern "C" int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, 
     int r = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w1_packed, 2, dims, str, box);
     if (r != STAC_OK) return r;
   }
+  {
+    // output [B][T2*20 rows][256 ch] bf16; rows past an utterance's end are clipped by the map
+    const uint64_t dims[3] = {256, (uint64_t)(t2 * kConvF), (uint64_t)batch};
+    const uint64_t str[2] = {256 * 2, (uint64_t)(t2 * kConvF) * 256 * 2};
+    const uint32_t box[3] = {64, kConvRows, 1};
+    int r = encode_map(&tcm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, out, 3, dims, str, box);
+    if (r != STAC_OK) return r;
+  }
   EpiParams ep{};
-  ep.bias = b1; ep.c = out; ep.c_bf16 = 0; ep.m = batch * t2 * kConvF; ep.n = 256;
-  ep.t2_len = (int)t2; ep.tiles_per_utt = tiles_per_utt;
-  return launch<true>(ta, tb, tb /*unused*/, ep, (int)(batch * tiles_per_utt), 1, 36, as_stream(stream));
+  ep.bias = b1; ep.c = out; ep.c_bf16 = 1; ep.m = batch * t2 * kConvF; ep.n = 256;
+  ep.t2_len = (int)t2; ep.tiles_per_utt = tiles_per_utt; ep.ln_g = ln_g; ep.ln_b = ln_b;
+  return launch<true>(ta, tb, tcm, ep, (int)(batch * tiles_per_utt), 1, 36, as_stream(stream));
 }

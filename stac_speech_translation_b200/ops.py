@@ -170,23 +170,25 @@ def conv_frontend(feats: torch.Tensor, w: FrontendWeights, out_dtype: Optional[t
     t1 = (t - 1) // 2 + 1
     t2 = (t1 - 1) // 2 + 1
     dev = feats.device
-    pre = torch.empty(b * t2, F2 * CNN_CH, device=dev, dtype=torch.float32)
+    out_dtype = out_dtype or torch.float32
     if w.precision == "fp32":
+        pre = torch.empty(b * t2, F2 * CNN_CH, device=dev, dtype=torch.float32)
         x0 = torch.empty(b, t1, F1, CNN_CH, device=dev, dtype=torch.float32)
         _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
-                                        b, t, ptr(x0), DT_F32, stream())
+              b, t, ptr(x0), DT_F32, stream())
         _call("stac_conv1_f32", ptr(x0), ptr(w.w1, torch.float32), ptr(w.b1), b, t1, ptr(pre), stream())
-    else:
-        n_pad = lib().stac_conv0_padded_elems(b, t1)
-        x0 = torch.empty(n_pad, device=dev, dtype=torch.bfloat16)
-        _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
-                                        b, t, ptr(x0), DT_BF16, stream())
-        _call("stac_conv1_bf16", ptr(x0), ptr(w.w1, torch.bfloat16), ptr(w.b1), b, t1, ptr(pre), stream())
-    out_dtype = out_dtype or torch.float32
-    out = torch.empty(b, t2, F2 * CNN_CH, device=dev, dtype=out_dtype)
-    _call("stac_group_ln_lrelu", ptr(pre), b * t2, F2 * CNN_CH, ptr(w.g1), ptr(w.be1), 1e-5, 0.01, ptr(out),
-                                    DT_BF16 if out_dtype == torch.bfloat16 else DT_F32, stream())
-    return out
+        out = torch.empty(b, t2, F2 * CNN_CH, device=dev, dtype=out_dtype)
+        _call("stac_group_ln_lrelu", ptr(pre), b * t2, F2 * CNN_CH, ptr(w.g1), ptr(w.be1), 1e-5, 0.01, ptr(out),
+              DT_BF16 if out_dtype == torch.bfloat16 else DT_F32, stream())
+        return out
+    n_pad = lib().stac_conv0_padded_elems(b, t1)
+    x0 = torch.empty(n_pad, device=dev, dtype=torch.bfloat16)
+    _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
+          b, t, ptr(x0), DT_BF16, stream())
+    out = torch.empty(b, t2, F2 * CNN_CH, device=dev, dtype=torch.bfloat16)
+    _call("stac_conv1_bf16", ptr(x0), ptr(w.w1, torch.bfloat16), ptr(w.b1), ptr(w.g1), ptr(w.be1), b, t1, ptr(out),
+          stream())
+    return out if out_dtype == torch.bfloat16 else out.float()
 
 
 # --------------------------------------------------------------------------

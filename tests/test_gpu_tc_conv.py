@@ -22,21 +22,28 @@ def _pack_padded(x0):
     return planes.to(torch.bfloat16).contiguous()
 
 
-@pytest.mark.parametrize("b,t1", [(1, 12), (2, 13), (3, 126), (2, 501), (1, 7)])
-def test_conv1_bf16(b, t1):
+@pytest.mark.parametrize("b,t1", [(1, 12), (2, 13), (3, 126), (2, 501), (1, 7), (5, 1501)])
+def test_conv1_bf16_fused_block(b, t1):
     g = torch.Generator().manual_seed(t1)
     x0 = torch.randn(b, t1, 40, 256, generator=g).to(torch.bfloat16).float()
     w = (torch.randn(256, 256, 3, 3, generator=g) / 48).to(torch.bfloat16).float()
     bias = torch.randn(256, generator=g)
+    gam = 1.0 + 0.2 * torch.randn(20, 256, generator=g)
+    bet = 0.3 * torch.randn(20, 256, generator=g)
     xin = torch.nn.functional.pad(x0.permute(0, 3, 2, 1), (1, 1, 1, 1), mode="reflect")   # [B, C, F, T]
-    ref = torch.nn.functional.conv2d(xin, w, bias, stride=2).permute(0, 3, 2, 1)         # [B, T2, 20, 256]
+    pre = torch.nn.functional.conv2d(xin, w, bias, stride=2).permute(0, 3, 2, 1)         # [B, T2, 20, 256]
     t2 = (t1 - 1) // 2 + 1
-    assert ref.shape == (b, t2, 20, 256)
+    assert pre.shape == (b, t2, 20, 256)
+    ref = torch.nn.functional.leaky_relu(torch.nn.functional.layer_norm(pre, (20, 256), gam, bet, 1e-5), 0.01)
     wp = w.permute(2, 3, 0, 1).reshape(9, 256, 256).to(torch.bfloat16).contiguous()
-    out = torch.full((b, t2, 20, 256), float("nan"), device="cuda")
+    out = torch.full((b, t2, 20 * 256), float("nan"), device="cuda", dtype=torch.bfloat16)
+    guard = torch.full((4096,), 7.0, device="cuda", dtype=torch.bfloat16)        # allocated right after `out`
     x_d, w_d, b_d = _pack_padded(x0).cuda(), wp.cuda(), bias.cuda()     # keep alive across the async launch
-    ops.check(ops.lib().stac_conv1_bf16(ops.ptr(x_d), ops.ptr(w_d), ops.ptr(b_d), b, t1, ops.ptr(out), ops.stream()))
+    g_d, be_d = gam.flatten().cuda(), bet.flatten().cuda()
+    ops.check(ops.lib().stac_conv1_bf16(ops.ptr(x_d), ops.ptr(w_d), ops.ptr(b_d), ops.ptr(g_d), ops.ptr(be_d), b, t1,
+                                        ops.ptr(out), ops.stream()))
     torch.cuda.synchronize()
-    got = out.cpu()
+    got = out.float().cpu().view(b, t2, 20, 256)
     assert not torch.isnan(got).any()
-    assert rel_l2(got, ref) < 1e-5, rel_l2(got, ref)
+    assert rel_l2(got, ref) < 4e-3, rel_l2(got, ref)          # bf16 rounding of the stored activations
+    assert float((guard.float() - 7.0).abs().max()) == 0.0
