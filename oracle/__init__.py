@@ -14,6 +14,14 @@ memory of that release; it is cross-checked against independent formulations
 (numpy DFT, hand-written attention, hand-written LayerNorm/conv) in
 ``tests/test_oracle.py`` and against the three constants the reference does
 pin (5120-wide CNN output, 25 Hz frame rate, 2500-entry PE table).
+
+What IS pinned by the reference itself: the in-repo glue.  ``tests/golden/make_glue_golden.py``
+imports ``/root/reference/stac-st/modules/TransformerMultiTask.py`` unmodified (its seven
+SpeechBrain imports served by a stub package made of this oracle's classes) and records what the
+reference's own ``encode()`` / ``forward()`` / ``make_masks()`` / ``EncoderWrapper`` return on seeded
+inputs in ``tests/golden/glue_reference.npz``; ``tests/test_oracle.py`` holds the restated
+``TransformerMultiTask`` to those vectors at 1e-6 and ``tests/test_gpu_glue_reference.py`` holds the
+CUDA encoder to them at the north-star tolerances.
 """
 from .speechbrain_path import (  # noqa: F401
     Fbank,

@@ -183,3 +183,34 @@ def test_golden_vectors():
     assert rel_l2(out["cnn"][:, ::7, ::3, ::16], torch.from_numpy(gold["cnn_sample"])) < 1e-5
     assert rel_l2(out_t["enc_out"], torch.from_numpy(gold["enc_out_train_mask"])) < 1e-5
     assert rel_l2(out["enc_out"], out_t["enc_out"]) > 1e-6           # the two mask rules differ on this batch
+
+
+# --------------------------------------------------------------------------
+# Reference-generated fixture: tests/golden/glue_reference.npz was produced by executing the
+# reference's own stac-st/modules/TransformerMultiTask.py (tests/golden/make_glue_golden.py).
+# --------------------------------------------------------------------------
+def _glue_fixture():
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "glue_reference.npz"))
+    state = {k[len("state/"):]: torch.from_numpy(d[k].astype(np.float32)) for k in d.files if k.startswith("state/")}
+    return d, state
+
+
+def test_oracle_glue_against_reference_generated_fixture():
+    d, state = _glue_fixture()
+    d_model = state["encoder.norm.norm.weight"].shape[0]
+    tr = sp.TransformerMultiTask(tgt_vocab=64, input_size=state["custom_src_module.layers.0.w.weight"].shape[1],
+                                 d_model=d_model, nhead=d_model // 64,
+                                 num_encoder_layers=2, d_ffn=state["encoder.layers.0.pos_ffn.ffn.0.weight"].shape[0],
+                                 activation=torch.nn.GELU, normalize_before=True).eval()
+    res = tr.load_state_dict(state, strict=False)
+    assert res.missing_keys == ["positional_encoding.pe"] and not res.unexpected_keys
+    src = torch.from_numpy(d["src"].astype(np.float32))
+    wl = torch.from_numpy(d["wav_lens"])
+    torch.set_num_threads(1)
+    with torch.no_grad():
+        assert rel_l2(tr.encode(src, wl), torch.from_numpy(d["enc_encode"])) < 1e-6
+        assert rel_l2(tr.encode(src.reshape(src.shape[0], src.shape[1], -1)), torch.from_numpy(d["enc_encode_nolen"])) < 1e-6
+        assert rel_l2(tr.forward_encoder(src, wl), torch.from_numpy(d["enc_forward"])) < 1e-6
+        assert rel_l2(sp.EncoderWrapper(tr)(src, wl), torch.from_numpy(d["enc_encode"])) < 1e-6
+    # the two mask rules really differ on this fixture (0.5 * 37 = 18.5: floor+1 = 19 keys vs round = 18)
+    assert rel_l2(torch.from_numpy(d["enc_forward"])[2], torch.from_numpy(d["enc_encode"])[2]) > 1e-4
