@@ -26,15 +26,20 @@ PRECISIONS = ("fp32", "bf16")
 # Optional launch tracing: bench.py sets TRACE to a list to get (kernel, label, start_event, end_event)
 # per launch; LAUNCHES counts kernel launches either way.
 TRACE = None
+TRACE_FILTER = None   # optional set of trace keys ("kernel" or "kernel:label"): only those launches get events
 LAUNCHES = 0
 _LABEL = ""
+
+
+def trace_key(name, label):
+    return f"{name}:{label}" if name == "stac_gemm_bf16" or name == "stac_gemm_f32" else name
 
 
 def _call(name, *args):
     """Enqueue one libstac_b200 kernel on the current stream (optionally bracketed by CUDA events)."""
     global LAUNCHES
     LAUNCHES += 1
-    if TRACE is None:
+    if TRACE is None or (TRACE_FILTER is not None and trace_key(name, _LABEL) not in TRACE_FILTER):
         check(getattr(lib(), name)(*args), name)
         return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
