@@ -1,0 +1,413 @@
+// a4, block 0 of the ConvolutionFrontEnd in bf16 mode, on tcgen05 tensor cores:
+//   reflect-pad 1, Conv2d(1 -> 256, 3x3, stride 2) + bias, LayerNorm over (40, 256) eps 1e-5, LeakyReLU(0.01),
+//   bf16 output in the reflect-padded parity-split layout the tensor-core conv1 reads (include/stac_b200.h).
+// Reference behaviour: SpeechBrain ConvolutionFrontEnd block 0 as configured at
+//   /root/reference/stac-st/hparams/transformer_multitask.yaml:173-180 (call: stac-st/inference.py:99).
+//
+// The stage is bound by its 2 GB output write, so the job of the kernel is to keep the CUDA cores out of the way:
+//   * the 9-tap convolution is one tiny GEMM per tile, D[channel][position] = W[channel][k] . X[position][k], with
+//     near-fp32 accuracy from a bf16 hi/lo split packed along K (x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, the bias and
+//     the LayerNorm shift fill all 32 K slots: two tcgen05.mma K=16 steps per 128-channel half);
+//   * the LayerNorm statistics never touch the 10240 outputs of a time step: sum and sum of squares over
+//     (40 freq x 256 channels) are a linear and a quadratic form of the 40 x 9 input patches (G = W^T W is
+//     built once per CTA), evaluated in fp32 by the producer warps, which then scale the patch rows by rstd and
+//     append -mean*rstd as extra K slots: the accumulator already holds the NORMALISED value;
+//   * with channels on the TMEM lanes each epilogue thread owns ONE channel: its 40 LayerNorm gammas and betas
+//     live in registers for the whole kernel and the epilogue is a single pass
+//     TMEM -> fma(g, u, beta) -> bf16x2 LeakyReLU -> staging smem;
+//   * a time step's two output planes leave the SM as bulk async copies (full 512-byte rows) issued by a
+//     dedicated warp; staging buffers, B tiles and accumulators are all multi-buffered and every hand-off is an
+//     mbarrier, so no role ever waits at a CTA-wide barrier in the steady state.
+// Roles (13 warps): 0-7 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = channel half), 8-10 producers
+// (patch rows + statistics), 11 MMA issuer + TMEM owner, 12 output bulk-copy issuer.
+#include <algorithm>
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kMel = 80, kF1 = 40, kC = 256;
+constexpr float kLnEps = 1e-5f, kSlope = 0.01f;
+constexpr int kTs = 2;                       // time steps per tile
+constexpr int kN = kTs * kF1;                // 80 positions = UMMA N
+constexpr int kStages = 3;                   // B tiles / accumulators in flight
+constexpr int kOutStages = 4;                // staged time steps in flight
+constexpr int kThreads = 13 * 32;
+constexpr int kProducerThreads = 96;
+
+constexpr int kWBytes = 2 * 128 * 128;                 // two 128-channel halves, 128-byte (64 x bf16) rows
+constexpr int kBBytes = kN * 128;                      // 10240
+constexpr int kPlane0Rows = 21, kPlane1Rows = 20;
+constexpr int kOutBytes = (kPlane0Rows + kPlane1Rows) * kC * 2;   // 20992 per time step
+constexpr int kFRow = kMel + 2;
+
+constexpr int kOffW = 0;
+constexpr int kOffB = kOffW + kWBytes;
+constexpr int kOffOut = kOffB + kStages * kBBytes;
+constexpr int kOffWraw = kOffOut + kOutStages * kOutBytes;       // fp32 w0 [256][9] + b0 [256] (setup only)
+constexpr int kOffFeat = kOffWraw + (kC * 9 + kC) * 4;            // float [5][82]
+constexpr int kOffRowStat = kOffFeat + 5 * kFRow * 4;             // float2 [80]
+constexpr int kOffTab = kOffRowStat + kN * 8;                     // float [128]: wsum[9] G[81] bw[9] bsum bb
+constexpr int kOffBar = kOffTab + 128 * 4;
+constexpr int kNumBars = 4 * kStages + 2 * kOutStages;
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) return -i;
+  if (i >= n) return 2 * (n - 1) - i;
+  return i;
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ unsigned short bf16_bits(float x) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float bf16_val(unsigned short b) { return __uint_as_float((uint32_t)b << 16); }
+
+// staging row (512 bytes each) of conv-0 frequency bin f1: plane 0 holds even padded bins fp = f1 + 1
+// (row fp / 2; row 0 mirrors f1 = 1), plane 1 the odd ones.
+__host__ __device__ constexpr int stage_row(int f1) { return (f1 & 1) ? (f1 + 1) / 2 : kPlane0Rows + f1 / 2; }
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, const float* __restrict__ b0,
+                const float* __restrict__ ln_g, const float* __restrict__ ln_b, int frames, int t1_len,
+                int tiles_per_utt, int n_tiles, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bars = sbase + kOffBar;
+  auto b_full = [&](int s) { return bars + 8u * s; };
+  auto b_empty = [&](int s) { return bars + 8u * (kStages + s); };
+  auto acc_full = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto acc_empty = [&](int s) { return bars + 8u * (3 * kStages + s); };
+  auto out_full = [&](int s) { return bars + 8u * (4 * kStages + s); };
+  auto out_empty = [&](int s) { return bars + 8u * (4 * kStages + kOutStages + s); };
+  const uint32_t tmem_slot = bars + 8u * kNumBars;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* wraw = reinterpret_cast<float*>(sptr + kOffWraw);
+  float* tab = reinterpret_cast<float*>(sptr + kOffTab);
+
+  // ---------------- one-time setup: barriers, TMEM, weight tile, statistics tables ----------------
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(b_full(s), 3); mbar_init(b_empty(s), 1); mbar_init(acc_full(s), 1); mbar_init(acc_empty(s), 8);
+    }
+    for (int s = 0; s < kOutStages; ++s) { mbar_init(out_full(s), 8); mbar_init(out_empty(s), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 11) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  for (int i = tid; i < kC * 9; i += kThreads) wraw[i] = __ldg(w0 + i);
+  for (int i = tid; i < kC; i += kThreads) wraw[kC * 9 + i] = __ldg(b0 + i);
+  __syncthreads();
+  if (tid < kC) {
+    // weight row of channel c: [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | b_hi | 1 | 1 | 0 ...] bf16, 128-byte
+    // swizzled row; the patch rows carry [xs_hi | xs_lo | xs_hi | r_hi | r_hi | r_lo | s_hi | s_lo] with
+    // xs = rstd * x, r = rstd, s = -mean * rstd, so the accumulator is (conv + bias - mean) * rstd
+    const int c = tid, r = c & 127;
+    unsigned short kv[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) kv[i] = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float w = wraw[c * 9 + k];
+      const unsigned short hi = bf16_bits(w);
+      kv[k] = hi; kv[9 + k] = hi; kv[18 + k] = bf16_bits(w - bf16_val(hi));
+    }
+    const float bb = wraw[kC * 9 + c];
+    kv[27] = bf16_bits(bb);
+    kv[28] = bf16_bits(bb - bf16_val(kv[27]));
+    kv[29] = kv[27];
+    kv[30] = 0x3f80;
+    kv[31] = 0x3f80;
+    const uint32_t row = sbase + kOffW + (c >> 7) * 16384 + r * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts_v4(row + ((j ^ (r & 7)) << 4), kv[8 * j] | ((uint32_t)kv[8 * j + 1] << 16),
+             kv[8 * j + 2] | ((uint32_t)kv[8 * j + 3] << 16), kv[8 * j + 4] | ((uint32_t)kv[8 * j + 5] << 16),
+             kv[8 * j + 6] | ((uint32_t)kv[8 * j + 7] << 16));
+  } else if (tid < kC + 101) {
+    // tab: [0,9) wsum_k = sum_c w_ck ; [9,90) G_kk' = sum_c w_ck w_ck' ; [90,99) bw_k = sum_c b_c w_ck ;
+    //      [99] bsum = sum_c b_c ; [100] bb = sum_c b_c^2
+    const int i = tid - kC;
+    float acc = 0.f;
+    for (int c = 0; c < kC; ++c) {
+      const float bc = wraw[kC * 9 + c];
+      float v;
+      if (i < 9) v = wraw[c * 9 + i];
+      else if (i < 90) v = wraw[c * 9 + (i - 9) / 9] * wraw[c * 9 + (i - 9) % 9];
+      else if (i < 99) v = bc * wraw[c * 9 + (i - 90)];
+      else if (i == 99) v = bc;
+      else v = bc * bc;
+      acc += v;
+    }
+    tab[i] = acc;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tp2 = (t1_len + 3) >> 1;
+
+  if (warp < 8) {
+    // ============================ epilogue: thread = one output channel ============================
+    const int half = warp >> 2, quarter = warp & 3;
+    const int c = half * 128 + quarter * 32 + lane;
+    float g[kF1], be[kF1];
+#pragma unroll
+    for (int f = 0; f < kF1; ++f) { g[f] = __ldg(ln_g + f * kC + c); be[f] = __ldg(ln_b + f * kC + c); }
+    const uint32_t my_col = sbase + kOffOut + c * 2;
+    const __nv_bfloat162 slope2 = __floats2bfloat162_rn(kSlope, kSlope);
+    int n = 0, as = 0;
+    uint32_t acc_phase = 0;
+    int t1_0 = (blockIdx.x % tiles_per_utt) * kTs;
+    const int t1_step = (gridDim.x % tiles_per_utt) * kTs, t1_wrap = tiles_per_utt * kTs;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      mbar_wait(acc_full(as), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (2 * kN) + half * kN;
+#pragma unroll
+      for (int tl = 0; tl < kTs; ++tl) {
+        const int m = n * kTs + tl, os = m & (kOutStages - 1);
+        const bool valid = t1_0 + tl < t1_len;
+        mbar_wait(out_empty(os), ((m >> 2) & 1) ^ 1);
+        if (valid) {
+          uint32_t va[32], vb[8];
+          tmem_ld32(t_addr + tl * kF1, va);
+          tmem_ld8(t_addr + tl * kF1 + 32, vb);
+          tmem_ld_wait();
+          if (tl == kTs - 1) {
+            // last read of this accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(as));
+          }
+          const uint32_t col = my_col + os * kOutBytes;
+#pragma unroll
+          for (int f = 0; f < kF1; f += 2) {
+            const float u0 = __uint_as_float(f < 32 ? va[f] : vb[f - 32]);
+            const float u1 = __uint_as_float(f + 1 < 32 ? va[f + 1] : vb[f + 1 - 32]);
+            __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(g[f], u0, be[f]), fmaf(g[f + 1], u1, be[f + 1]));
+            y = __hmax2(y, __hmul2(y, slope2));            // LeakyReLU on the packed pair
+            const uint32_t bits = *reinterpret_cast<uint32_t*>(&y);
+            sts_u16(col + stage_row(f) * (kC * 2), (unsigned short)(bits & 0xffffu));
+            sts_u16(col + stage_row(f + 1) * (kC * 2), (unsigned short)(bits >> 16));
+            if (f == 0) sts_u16(col, (unsigned short)(bits >> 16));   // padded bin 0 mirrors f1 = 1
+          }
+        } else if (tl == kTs - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(as));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_full(os));
+      }
+      if (++as == kStages) { as = 0; acc_phase ^= 1; }
+      t1_0 += t1_step;
+      if (t1_0 >= t1_wrap) t1_0 -= t1_wrap;
+    }
+  } else if (warp < 11) {
+    // ============================ producers: LayerNorm statistics + scaled patch rows ============================
+    const int p = tid - 8 * 32;                      // 0..95; rows 0..79 are real positions
+    float* fbuf = reinterpret_cast<float*>(sptr + kOffFeat);
+    float2* rowstat = reinterpret_cast<float2*>(sptr + kOffRowStat);
+    const int tl = p / kF1, f1 = p - tl * kF1;
+    // input rows t = 2*t1_0 - 1 .. 2*t1_0 + 3 (reflected at the batch edges), bins -1..79 (bin -1 mirrors bin 1);
+    // the loads of tile n+1 are issued while tile n is built
+    float ld[5];
+    auto fetch = [&](int tile) {
+      const int b = tile / tiles_per_utt;
+      const int t1_0 = (tile - b * tiles_per_utt) * kTs;
+      const float* frow = feats + (int64_t)b * frames * kMel;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int idx = p + i * kProducerThreads;       // 0 .. 5*81-1
+        ld[i] = 0.f;
+        if (idx < 5 * (kMel + 1)) {
+          const int r = idx / (kMel + 1), fi = idx - r * (kMel + 1);
+          int t = reflect_idx(2 * t1_0 - 1 + r, frames);
+          t = min(max(t, 0), frames - 1);               // rows of an invalid second time step are never used
+          ld[i] = __ldg(frow + (int64_t)t * kMel + (fi == 0 ? 1 : fi - 1));
+        }
+      }
+    };
+    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      named_bar_sync(2, kProducerThreads);              // previous tile's patches have been read from fbuf
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int idx = p + i * kProducerThreads;
+        if (idx < 5 * (kMel + 1)) { const int r = idx / (kMel + 1); fbuf[r * kFRow + (idx - r * (kMel + 1))] = ld[i]; }
+      }
+      named_bar_sync(2, kProducerThreads);
+      if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
+      float x[9];
+      if (p < kN) {
+#pragma unroll
+        for (int kf = 0; kf < 3; ++kf)
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) x[kf * 3 + kt] = fbuf[(2 * tl + kt) * kFRow + 2 * f1 + kf];
+        // row sum and sum of squares over the 256 channels as forms of the 9-tap patch
+        float s1 = tab[99], s2 = tab[100];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          float q = 2.0f * tab[90 + k];
+#pragma unroll
+          for (int k2 = 0; k2 < 9; ++k2) q = fmaf(tab[9 + k * 9 + k2], x[k2], q);
+          s1 = fmaf(tab[k], x[k], s1);
+          s2 = fmaf(q, x[k], s2);
+        }
+        rowstat[p] = make_float2(s1, s2);
+      }
+      named_bar_sync(2, kProducerThreads);
+      mbar_wait(b_empty(s), phase ^ 1);
+      if (p < kN) {
+        // every thread of a time step adds the same 40 row statistics in the same order
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll 8
+        for (int f = 0; f < kF1; ++f) { const float2 r = rowstat[tl * kF1 + f]; a1 += r.x; a2 += r.y; }
+        const float mean = a1 * (1.0f / (kF1 * kC));
+        const float var = fmaxf(a2 * (1.0f / (kF1 * kC)) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + kLnEps);
+        const float shift = -mean * rstd;
+        unsigned short hi[9], lo[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float xs = x[k] * rstd;
+          hi[k] = bf16_bits(xs);
+          lo[k] = bf16_bits(xs - bf16_val(hi[k]));
+        }
+        const unsigned short r_hi = bf16_bits(rstd), r_lo = bf16_bits(rstd - bf16_val(r_hi));
+        const unsigned short s_hi = bf16_bits(shift), s_lo = bf16_bits(shift - bf16_val(s_hi));
+        auto pk = [](unsigned short a, unsigned short bb) { return (uint32_t)a | ((uint32_t)bb << 16); };
+        const uint32_t row = sbase + kOffB + s * kBBytes + p * 128;
+        const int sw = p & 7;
+        sts_v4(row + ((0 ^ sw) << 4), pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]), pk(hi[6], hi[7]));
+        sts_v4(row + ((1 ^ sw) << 4), pk(hi[8], lo[0]), pk(lo[1], lo[2]), pk(lo[3], lo[4]), pk(lo[5], lo[6]));
+        sts_v4(row + ((2 ^ sw) << 4), pk(lo[7], lo[8]), pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]));
+        sts_v4(row + ((3 ^ sw) << 4), pk(hi[6], hi[7]), pk(hi[8], r_hi), pk(r_hi, r_lo), pk(s_hi, s_lo));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_full(s));
+      if (++s == kStages) { s = 0; phase ^= 1; }
+    }
+  } else if (warp == 11) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, kN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(acc_empty(s), ph ^ 1);
+        mbar_wait(b_full(s), ph);
+        tc_fence_after();
+        const uint64_t bd = make_smem_desc_sw128(sbase + kOffB + s * kBBytes);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t ad = make_smem_desc_sw128(sbase + kOffW + half * 16384);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_bf16(tmem_base + s * (2 * kN) + half * kN, ad + 2 * k, bd + 2 * k, idesc, k);
+        }
+        umma_commit(b_empty(s));
+        umma_commit(acc_full(s));
+        if (++s == kStages) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================ output: one bulk copy per plane and padded time index ============================
+    if (lane == 0) {
+      int n = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+        const int b = tile / tiles_per_utt;
+        const int t1_0 = (tile - b * tiles_per_utt) * kTs;
+        for (int tl = 0; tl < kTs; ++tl) {
+          const int m = n * kTs + tl, os = m & (kOutStages - 1);
+          const int t1 = t1_0 + tl;
+          mbar_wait(out_full(os), (m >> 2) & 1);
+          if (t1 < t1_len) {
+            int tps[3];
+            int n_tp = 0;
+            tps[n_tp++] = t1 + 1;
+            if (t1 == 1) tps[n_tp++] = 0;                          // padded time 0 mirrors t1 = 1
+            if (t1 == t1_len - 2) tps[n_tp++] = t1_len + 1;        // padded time T1+1 mirrors t1 = T1-2
+            const uint32_t s0 = sbase + kOffOut + os * kOutBytes;
+            for (int i = 0; i < n_tp; ++i) {
+              const int tp = tps[i];
+              const int64_t plane_t = (int64_t)b * 4 + (tp & 1) * 2;
+              bulk_store(out + ((plane_t + 0) * tp2 + (tp >> 1)) * (21 * kC), s0, kPlane0Rows * kC * 2);
+              bulk_store(out + ((plane_t + 1) * tp2 + (tp >> 1)) * (21 * kC), s0 + kPlane0Rows * kC * 2,
+                         kPlane1Rows * kC * 2);
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // at most 2 groups still reading: the buffer staged two steps ago is free again (the epilogue will
+          // want it two steps from now)
+          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          if (m >= 2) mbar_arrive(out_empty((m - 2) & (kOutStages - 1)));
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 11) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int num_sms_conv0() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+// called by stac_conv0_ln_lrelu (conv_frontend.cu) for out_mode == STAC_DT_BF16
+int stac_conv0_tc_launch(const float* feats, const float* w0, const float* b0, const float* ln_g, const float* ln_b,
+                         int64_t batch, int64_t frames, int t1, uint16_t* out, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int tiles_per_utt = (t1 + kTs - 1) / kTs;
+  const int64_t n_tiles = batch * tiles_per_utt;
+  if (n_tiles >= (1ll << 30)) return STAC_ERR_UNSUPPORTED_SHAPE;
+  const int grid = (int)std::min<int64_t>(n_tiles, num_sms_conv0());
+  conv0_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(feats, w0, b0, ln_g, ln_b, (int)frames, t1, tiles_per_utt,
+                                                      (int)n_tiles, reinterpret_cast<__nv_bfloat16*>(out));
+  STAC_LAUNCH_CHECK();
+}

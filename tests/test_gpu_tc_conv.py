@@ -47,3 +47,48 @@ def test_conv1_bf16_fused_block(b, t1):
     assert not torch.isnan(got).any()
     assert rel_l2(got, ref) < 4e-3, rel_l2(got, ref)          # bf16 rounding of the stored activations
     assert float((guard.float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("b,t", [(1, 3), (2, 4), (1, 5), (3, 37), (2, 300), (1, 1001), (4, 3001)])
+def test_conv0_tc_block_padded_layout(b, t):
+    """Tensor-core block 0 (stac_conv0_ln_lrelu, bf16 mode) against torch: conv + LayerNorm(40,256) + LeakyReLU,
+    every element of the reflect-padded parity-split layout that conv1 reads, ragged / odd / tiny lengths."""
+    g = torch.Generator().manual_seed(1000 + t)
+    feats = torch.randn(b, t, 80, generator=g) * 1.3 + 0.2
+    w = torch.randn(256, 1, 3, 3, generator=g) / 3
+    bias = torch.randn(256, generator=g) * 0.5
+    gam = 1.0 + 0.2 * torch.randn(40, 256, generator=g)
+    bet = 0.3 * torch.randn(40, 256, generator=g)
+    xin = torch.nn.functional.pad(feats.transpose(1, 2).unsqueeze(1), (1, 1, 1, 1), mode="reflect")   # [B,1,F,T]
+    pre = torch.nn.functional.conv2d(xin.double(), w.double(), bias.double(), stride=2).permute(0, 3, 2, 1)
+    t1 = (t - 1) // 2 + 1
+    assert pre.shape == (b, t1, 40, 256)
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.layer_norm(pre, (40, 256), gam.double(), bet.double(), 1e-5), 0.01).float()
+    n = ops.lib().stac_conv0_padded_elems(b, t1)
+    x0 = torch.full((n,), float("nan"), device="cuda", dtype=torch.bfloat16)
+    guard = torch.full((4096,), 7.0, device="cuda", dtype=torch.bfloat16)
+    f_d, w_d, b_d = feats.cuda().contiguous(), w.reshape(256, 3, 3).cuda().contiguous(), bias.cuda()
+    g_d, be_d = gam.flatten().cuda(), bet.flatten().cuda()
+    ops.check(ops.lib().stac_conv0_ln_lrelu(ops.ptr(f_d), ops.ptr(w_d), ops.ptr(b_d), ops.ptr(g_d), ops.ptr(be_d),
+                                            b, t, ops.ptr(x0), ops.DT_BF16, ops.stream()))
+    torch.cuda.synchronize()
+    tp2 = (t1 + 3) // 2
+    planes = x0.view(b, 2, 2, tp2, 21, 256).float().cpu()
+    pad = torch.full((b, 2 * tp2, 42, 256), float("nan"))
+    for pt in range(2):
+        for pf in range(2):
+            pad[:, pt::2, pf::2] = planes[:, pt, pf]
+    want = torch.nn.functional.pad(ref.permute(0, 3, 1, 2), (1, 1, 1, 1), mode="reflect").permute(0, 2, 3, 1)
+    got = pad[:, : t1 + 2, :41]
+    want = want[:, :, :41]
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, want) < 2.5e-3, rel_l2(got, want)      # bf16 rounding of the stored value only
+    # the value before rounding is fp32-accurate: positive outputs are the correctly rounded bf16 almost always;
+    # negative ones go through one more bf16 rounding (LeakyReLU runs on packed bf16 pairs): within 1 ulp (2^-7 rel)
+    wb = want.to(torch.bfloat16).float()
+    pos = want > 0
+    exact = (got[pos] == wb[pos]).float().mean()
+    assert exact > 0.97, float(exact)
+    assert float(((got - want).abs() <= want.abs() * 2.0 ** -7 + 1e-4).float().mean()) > 0.9999
+    assert float((guard.float() - 7.0).abs().max()) == 0.0

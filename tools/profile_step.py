@@ -14,6 +14,7 @@ ap.add_argument("--size", default="S")
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--seconds", type=float, default=30.0)
 ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--stop-after", default=None, choices=[None, "cnn"])
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -24,6 +25,6 @@ calib = wavs[: min(8, args.batch), : 16000 * 4].contiguous()
 mods["normalize"].calibrate(mods["compute_features"](calib), torch.ones(calib.shape[0], device=dev))
 pipe = sb.EncoderPipeline(mods)
 for _ in range(args.steps):
-    res = pipe(wavs, wl)
+    res = pipe(wavs, wl, stop_after=args.stop_after)
 torch.cuda.synchronize()
-print("ok", float(res["enc_out"].abs().mean()))
+print("ok", float(next(iter(res.values())).float().abs().mean()))
