@@ -152,6 +152,17 @@ int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int32_t* kv_le
 int stac_log_softmax(const float* logits, int64_t rows, int64_t vocab, float* out,
                      int32_t* argmax /*[rows] or NULL*/, void* stream);
 
+/* a8 + a9 fused (bf16 mode): log_softmax(enc . W^T + b) and its argmax without ever materialising the logits.
+ * Two passes of the tcgen05 GEMM over the same operands: pass 1 reduces every (row, 64-column group) to
+ * (max, sum exp, argmax) in its epilogue and stores no logits, a small kernel combines the groups into the row's
+ * log-sum-exp and greedy id, pass 2 recomputes the tile and stores logits - lse.  HBM traffic = the fp32
+ * posteriors once (instead of three times) + the 4 % statistics workspace.
+ *   enc bf16 [m, d_model], w bf16 [vocab, d_model], bias fp32 [vocab] or NULL,
+ *   workspace: stac_ctc_head_workspace_floats(m, vocab) floats, log_probs fp32 [m, vocab], argmax int32 [m] or NULL */
+int64_t stac_ctc_head_workspace_floats(int64_t m, int64_t vocab);
+int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const float* bias, int64_t m, int64_t vocab,
+                       int64_t d_model, float* workspace, float* log_probs, int32_t* argmax, void* stream);
+
 /* fp32 -> bf16 conversion (weight packing / activation hand-off) */
 int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);
 

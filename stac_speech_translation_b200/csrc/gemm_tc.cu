@@ -56,6 +56,13 @@ struct EpiParams {
   // V^T side output of a packed QKV projection
   __nv_bfloat16* vt;
   int64_t vt_cols, seq_len, t_pad;
+  // CTC head: pass 1 (stats != NULL) reduces every (row, 64-column group) to (max, sum exp, argmax) and stores nothing
+  // to C; pass 2 (row_sub != NULL) subtracts the row's log-sum-exp
+  float* stats;       // [2][n_groups][m]: max | sum of exp(x - max)
+  int64_t stats_plane;   // n_groups * m
+  const float* row_sub;  // [m] log-sum-exp
+  const float* row_max;  // [m] row maximum (pass 2 finds the greedy id: first column equal to it)
+  int* argmax;           // [m], pre-set to INT_MAX by the reduce kernel
   // conv mode
   int t2_len;         // output time steps per utterance
   int tiles_per_utt;  // ceil(T2 / 6)
@@ -63,23 +70,24 @@ struct EpiParams {
   const float* ln_b;
 };
 
-// bf16-mode GELU: x * Phi(x) with Phi(x) - 0.5 = 0.5 erf(x / sqrt 2) ~ xc * Q(xc^2), xc = clamp(x, -4, 4), Q a
-// degree-8 polynomial (least-squares fit on [0, 4], fp32 Horner; max |gelu error| 1.6e-4 over [-8, 8], well under
-// the bf16 rounding of the stored activation).  13 FMA-pipe instructions and no MUFU op per element: the exact
-// erff() or an exp/rcp formulation would make the FFN1 epilogue slower than its MMAs and its HBM traffic.
+// bf16-mode GELU: x * Phi(x) with Phi(x) = 0.5 (1 + erf(x / sqrt 2)) ~ 0.5 (1 + tanh(x (a + b x^2 + c x^4))); a, b, c are a
+// minimax fit to the exact-erf GELU (max |error| 2.5e-5 over [-8, 8] before the 2^-11 relative error of tanh.approx,
+// well under the bf16 rounding of the stored activation).  6 FMA-pipe instructions + 1 MUFU per element: the exact
+// erff() (or a long polynomial) makes the FFN1 epilogue issue-bound - slower than its MMAs and its HBM traffic.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float xc = fminf(fmaxf(x, -4.0f), 4.0f);
-  const float u = xc * xc;
-  float q = 8.524421446e-11f;
-  q = fmaf(q, u, -7.295211546e-09f);
-  q = fmaf(q, u, 2.791634870e-07f);
-  q = fmaf(q, u, -6.397717698e-06f);
-  q = fmaf(q, u, 9.969574603e-05f);
-  q = fmaf(q, u, -1.137302839e-03f);
-  q = fmaf(q, u, 9.885039181e-03f);
-  q = fmaf(q, u, -6.641801447e-02f);
-  q = fmaf(q, u, 3.989247680e-01f);
-  return x * fmaf(xc, q, 0.5f);
+  const float u = fminf(x * x, 64.0f);      // the fit is for |x| <= 8; beyond it tanh is saturated anyway
+  float p = fmaf(-3.51516785e-04f, u, 3.70056460e-02f);
+  p = fmaf(p, u, 7.97507884e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
@@ -336,6 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + cgrp * 64 + ((uint32_t)(quarter * 32) << 16);
+      float st_m = -INFINITY, st_s = 0.f;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         float x[32];
@@ -368,6 +377,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (ep.act == STAC_ACT_GELU_ERF) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = gelu_fast(x[i]);
+        }
+        if (ep.stats != nullptr) {
+          // CTC pass 1: online (max, sum exp) of this thread's row over its 64-column group
+          constexpr float kL2e = 1.4426950408889634f;
+          if (col0 + 32 > ep.n) {                        // warp-uniform: only the ragged last group masks columns
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i >= ep.n) x[i] = -INFINITY;
+          }
+          float hm0 = fmaxf(x[0], x[1]), hm1 = fmaxf(x[2], x[3]);
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) { hm0 = fmaxf(hm0, fmaxf(x[i], x[i + 1])); hm1 = fmaxf(hm1, fmaxf(x[i + 2], x[i + 3])); }
+          const float hm = fmaxf(hm0, hm1);
+          if (hm > st_m) { st_s *= ex2_approx((st_m - hm) * kL2e); st_m = hm; }
+          const float ms = st_m * kL2e;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            s0 += ex2_approx(fmaf(x[i], kL2e, -ms));
+            s1 += ex2_approx(fmaf(x[i + 1], kL2e, -ms));
+          }
+          st_s += s0 + s1;
+          if ((half == 1 || col0 + 32 >= ep.n) && row_ok) {
+            const int64_t g = (int64_t)(colg >> 6) * ep.m + row;
+            ep.stats[g] = st_m;
+            ep.stats[ep.stats_plane + g] = st_s;
+          }
+          continue;
+        }
+        if (ep.row_sub != nullptr) {
+          // CTC pass 2: log-probabilities; the greedy id is the first column holding the row maximum
+          const float l = row_ok ? __ldg(ep.row_sub + row) : 0.f;
+          const float rmax = row_ok ? __ldg(ep.row_max + row) : INFINITY;
+          if (col0 + 32 > ep.n) {                        // ragged last group (its stores are clipped by the map)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i >= ep.n) x[i] = -INFINITY;
+          }
+          float h0 = fmaxf(x[0], x[1]), h1 = fmaxf(x[2], x[3]);
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) { h0 = fmaxf(h0, fmaxf(x[i], x[i + 1])); h1 = fmaxf(h1, fmaxf(x[i + 2], x[i + 3])); }
+          if (fmaxf(h0, h1) == rmax && ep.argmax != nullptr) {      // rare: this chunk holds the row maximum
+            int first = 0x7fffffff;
+#pragma unroll
+            for (int i = 31; i >= 0; --i)
+              if (x[i] == rmax && col0 + i < ep.n) first = col0 + i;
+            if (first != 0x7fffffff) atomicMin(ep.argmax + row, first);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] -= l;
         }
         if (ep.resid && row_ok) {
           const int64_t rrow = ep.resid_period > 0 ? row % ep.resid_period : row;
@@ -467,18 +526,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
 
 }  // namespace
 
-extern "C" int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float* bias, const float* resid,
-                              int64_t resid_period, int act, void* c, int c_dtype, int64_t m, int64_t n,
-                              int64_t k, uint16_t* vt_out, int64_t vt_cols, int64_t seq_len, int64_t t_pad,
-                              void* stream) {
-  STAC_REQUIRE(a && w && c && m > 0 && n > 0 && k > 0 && resid_period >= 0);
-  STAC_REQUIRE(act == STAC_ACT_NONE || act == STAC_ACT_GELU_ERF);
-  STAC_REQUIRE(c_dtype == STAC_DT_F32 || c_dtype == STAC_DT_BF16);
+// tensor maps + launch of the linear-mode kernel; `ep` carries the epilogue options (c/m/n are filled in here)
+static int launch_linear(const uint16_t* a, const uint16_t* w, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
+                         EpiParams ep, void* stream) {
   if (k % BLOCK_K != 0 || n % 8 != 0 || m >= (1ll << 31) - 256) return STAC_ERR_UNSUPPORTED_SHAPE;
-  if (vt_out) {
-    STAC_REQUIRE(vt_cols > 0 && vt_cols % 64 == 0 && vt_cols <= n && (n - vt_cols) % 64 == 0);
-    STAC_REQUIRE(seq_len > 0 && t_pad >= seq_len && t_pad % 8 == 0 && m % seq_len == 0);
-  }
   CUtensorMap ta, tb, tcm;
   {
     const uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};
@@ -503,17 +554,80 @@ extern "C" int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float*
                        str, box);
     if (r != STAC_OK) return r;
   }
+  ep.c = c; ep.c_bf16 = c_dtype == STAC_DT_BF16; ep.m = m; ep.n = n;
+  ep.t2_len = 0; ep.tiles_per_utt = 1;
+  return launch<false>(ta, tb, tcm, ep, (int)ceil_div64(m, BLOCK_M), (int)ceil_div64(n, BLOCK_N),
+                       (int)(k / BLOCK_K), as_stream(stream));
+}
+
+extern "C" int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float* bias, const float* resid,
+                              int64_t resid_period, int act, void* c, int c_dtype, int64_t m, int64_t n,
+                              int64_t k, uint16_t* vt_out, int64_t vt_cols, int64_t seq_len, int64_t t_pad,
+                              void* stream) {
+  STAC_REQUIRE(a && w && c && m > 0 && n > 0 && k > 0 && resid_period >= 0);
+  STAC_REQUIRE(act == STAC_ACT_NONE || act == STAC_ACT_GELU_ERF);
+  STAC_REQUIRE(c_dtype == STAC_DT_F32 || c_dtype == STAC_DT_BF16);
+  if (vt_out) {
+    STAC_REQUIRE(vt_cols > 0 && vt_cols % 64 == 0 && vt_cols <= n && (n - vt_cols) % 64 == 0);
+    STAC_REQUIRE(seq_len > 0 && t_pad >= seq_len && t_pad % 8 == 0 && m % seq_len == 0);
+  }
   EpiParams ep{};
   ep.bias = bias; ep.act = act;
   // an in-place, row-aligned fp32 residual becomes a TMA reduce-add; anything else is loaded directly
   ep.reduce_add = (resid != nullptr && resid == c && resid_period == 0 && c_dtype == STAC_DT_F32) ? 1 : 0;
   ep.resid = ep.reduce_add ? nullptr : resid;
   ep.resid_period = resid_period;
-  ep.c = c; ep.c_bf16 = c_dtype == STAC_DT_BF16; ep.m = m; ep.n = n;
   ep.vt = reinterpret_cast<__nv_bfloat16*>(vt_out); ep.vt_cols = vt_cols; ep.seq_len = seq_len; ep.t_pad = t_pad;
-  ep.t2_len = 0; ep.tiles_per_utt = 1;
-  return launch<false>(ta, tb, tcm, ep, (int)ceil_div64(m, BLOCK_M), (int)ceil_div64(n, BLOCK_N),
-                       (int)(k / BLOCK_K), as_stream(stream));
+  return launch_linear(a, w, c, c_dtype, m, n, k, ep, stream);
+}
+
+namespace {
+// CTC head, between the two GEMM passes: combine the per-group statistics of every row
+__global__ void __launch_bounds__(256)
+ctc_reduce_kernel(const float* __restrict__ stats, int64_t plane, int n_groups, int64_t m, float* __restrict__ lse,
+                  float* __restrict__ row_max, int* __restrict__ argmax) {
+  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (row >= m) return;
+  float mx = -INFINITY, sum = 0.f;
+  for (int g = 0; g < n_groups; ++g) {
+    const float gm = stats[(int64_t)g * m + row];
+    const float gs = stats[plane + (int64_t)g * m + row];
+    if (gm > mx) {
+      sum = sum * expf(mx - gm) + gs;
+      mx = gm;
+    } else {
+      sum += gs * expf(gm - mx);
+    }
+  }
+  lse[row] = mx + logf(sum);
+  row_max[row] = mx;
+  if (argmax) argmax[row] = 0x7fffffff;
+}
+}  // namespace
+
+extern "C" int64_t stac_ctc_head_workspace_floats(int64_t m, int64_t vocab) {
+  return 2 * ceil_div64(vocab, 64) * m + 2 * m;
+}
+
+extern "C" int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const float* bias, int64_t m, int64_t vocab,
+                                  int64_t d_model, float* workspace, float* log_probs, int32_t* argmax, void* stream) {
+  STAC_REQUIRE(enc && w && workspace && log_probs && m > 0 && vocab > 0 && d_model > 0);
+  const int64_t n_groups = ceil_div64(vocab, 64);
+  const int64_t plane = n_groups * m;
+  float* lse = workspace + 2 * plane;
+  float* row_max = lse + m;
+  EpiParams ep{};
+  ep.bias = bias;
+  ep.stats = workspace; ep.stats_plane = plane;
+  int r = launch_linear(enc, w, log_probs, STAC_DT_F32, m, vocab, d_model, ep, stream);   // pass 1: statistics only
+  if (r != STAC_OK) return r;
+  ctc_reduce_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, as_stream(stream)>>>(workspace, plane, (int)n_groups, m,
+                                                                                lse, row_max, argmax);
+  if (cudaPeekAtLastError() != cudaSuccess) return (int)cudaGetLastError();
+  EpiParams ep2{};
+  ep2.bias = bias;
+  ep2.row_sub = lse; ep2.row_max = row_max; ep2.argmax = argmax;
+  return launch_linear(enc, w, log_probs, STAC_DT_F32, m, vocab, d_model, ep2, stream);  // pass 2: logits - lse
 }
 
 extern "C" int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, const float* b1,

@@ -363,6 +363,26 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     return out.view(*shp[:-1], weight.shape[0])
 
 
+def ctc_head_bf16(enc_bf16: torch.Tensor, weight_bf16: torch.Tensor, bias: Optional[torch.Tensor]):
+    """a8 + a9 fused (bf16 mode): log_softmax(enc W^T + b) fp32 [.., V] and greedy ids int32 [..], logits never
+    materialised (two GEMM passes, see include/stac_b200.h)."""
+    shp = enc_bf16.shape
+    x2 = enc_bf16.reshape(-1, shp[-1]).contiguous()
+    m, d = x2.shape
+    v = weight_bf16.shape[0]
+    global _LABEL
+    ws = torch.empty(lib().stac_ctc_head_workspace_floats(m, v), device=x2.device, dtype=torch.float32)
+    out = torch.empty(m, v, device=x2.device, dtype=torch.float32)
+    ids = torch.empty(m, device=x2.device, dtype=torch.int32)
+    prev, _LABEL = _LABEL, "ctc_head"
+    try:
+        _call("stac_ctc_head_bf16", ptr(x2, torch.bfloat16), ptr(weight_bf16, torch.bfloat16), ptr(bias), m, v, d,
+              ptr(ws), ptr(out), ptr(ids), stream())
+    finally:
+        _LABEL = prev
+    return out.view(*shp[:-1], v), ids.view(shp[:-1])
+
+
 def log_softmax(logits: torch.Tensor, want_argmax: bool = False, inplace: bool = False):
     shp = logits.shape
     x = logits.reshape(-1, shp[-1]).contiguous()

@@ -137,8 +137,11 @@ class EncoderPipeline:
         if want_posteriors or want_greedy:
             ctc = m["ctc_lin"]
             bias = None if ctc.w.bias is None else ctc.w.bias.detach().float().contiguous()
-            logits = ops.linear(enc_b, ctc.packed_weight(), bias, self.precision, tag="ctc_lin")
-            p, ids = ops.log_softmax(logits, want_argmax=True, inplace=True)
+            if bf16:
+                p, ids = ops.ctc_head_bf16(enc_b, ctc.packed_weight(), bias)
+            else:
+                logits = ops.linear(enc_b, ctc.packed_weight(), bias, self.precision, tag="ctc_lin")
+                p, ids = ops.log_softmax(logits, want_argmax=True, inplace=True)
             res["p_ctc"], res["greedy"] = p, ids
         return res
 

@@ -79,3 +79,24 @@ def test_qkv_with_transposed_v():
     v_got = vt.view(b, h, 64, t_pad).float().cpu()
     assert rel_l2(v_got[..., :t], v_ref) < 4e-3
     assert float(v_got[..., t:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("m,v,d", [(300, 5000, 256), (77, 64, 128), (1000, 5000, 512), (129, 5000, 1024), (5, 136, 256)])
+def test_fused_ctc_head(m, v, d):
+    """stac_ctc_head_bf16 (two-pass GEMM + log-softmax + argmax) against torch on the same bf16-rounded operands."""
+    g = torch.Generator().manual_seed(m + v)
+    x = torch.randn(m, d, generator=g).to(torch.bfloat16)
+    w = (torch.randn(v, d, generator=g) / d ** 0.5 * 3).to(torch.bfloat16)
+    b = torch.randn(v, generator=g)
+    logits = x.float() @ w.float().t() + b
+    ref = torch.log_softmax(logits, -1)
+    got, ids = ops.ctc_head_bf16(x.cuda(), w.cuda(), b.cuda())
+    torch.cuda.synchronize()
+    assert got.shape == (m, v) and ids.shape == (m,)
+    assert float((got.cpu() - ref).abs().max()) < 2e-4
+    assert float((got.cpu().exp().sum(-1) - 1).abs().max()) < 1e-4        # posteriors sum to one
+    # greedy ids: equal to torch's argmax except on near ties (fp32 summation order differs)
+    top2 = logits.topk(2, -1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4
+    assert bool((ids.cpu().long()[clear] == logits.argmax(-1)[clear]).all())
+    assert bool((logits.gather(1, ids.cpu().long()[:, None])[:, 0] >= top2[:, 0] - 1e-4).all())
