@@ -158,10 +158,12 @@ int stac_log_softmax(const float* logits, int64_t rows, int64_t vocab, float* ou
  * log-sum-exp and greedy id, pass 2 recomputes the tile and stores logits - lse.  HBM traffic = the fp32
  * posteriors once (instead of three times) + the 4 % statistics workspace.
  *   enc bf16 [m, d_model], w bf16 [vocab, d_model], bias fp32 [vocab] or NULL,
- *   workspace: stac_ctc_head_workspace_floats(m, vocab) floats, log_probs fp32 [m, vocab], argmax int32 [m] or NULL */
+ *   workspace: stac_ctc_head_workspace_floats(m, vocab) floats, log_probs [m, vocab] fp32 (STAC_DT_F32, the
+ *   reference's contract) or bf16 (STAC_DT_BF16: what non-root ranks ship to rank 0), argmax int32 [m] or NULL */
 int64_t stac_ctc_head_workspace_floats(int64_t m, int64_t vocab);
 int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const float* bias, int64_t m, int64_t vocab,
-                       int64_t d_model, float* workspace, float* log_probs, int32_t* argmax, void* stream);
+                       int64_t d_model, float* workspace, void* log_probs, int out_dtype, int32_t* argmax,
+                       void* stream);
 
 /* fp32 -> bf16 conversion (weight packing / activation hand-off) */
 int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);

@@ -610,8 +610,10 @@ extern "C" int64_t stac_ctc_head_workspace_floats(int64_t m, int64_t vocab) {
 }
 
 extern "C" int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const float* bias, int64_t m, int64_t vocab,
-                                  int64_t d_model, float* workspace, float* log_probs, int32_t* argmax, void* stream) {
+                                  int64_t d_model, float* workspace, void* log_probs, int out_dtype, int32_t* argmax,
+                                  void* stream) {
   STAC_REQUIRE(enc && w && workspace && log_probs && m > 0 && vocab > 0 && d_model > 0);
+  STAC_REQUIRE(out_dtype == STAC_DT_F32 || out_dtype == STAC_DT_BF16);
   const int64_t n_groups = ceil_div64(vocab, 64);
   const int64_t plane = n_groups * m;
   float* lse = workspace + 2 * plane;
@@ -619,7 +621,7 @@ extern "C" int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const 
   EpiParams ep{};
   ep.bias = bias;
   ep.stats = workspace; ep.stats_plane = plane;
-  int r = launch_linear(enc, w, log_probs, STAC_DT_F32, m, vocab, d_model, ep, stream);   // pass 1: statistics only
+  int r = launch_linear(enc, w, log_probs, out_dtype, m, vocab, d_model, ep, stream);   // pass 1: statistics only
   if (r != STAC_OK) return r;
   ctc_reduce_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, as_stream(stream)>>>(workspace, plane, (int)n_groups, m,
                                                                                 lse, row_max, argmax);
@@ -627,7 +629,7 @@ extern "C" int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const 
   EpiParams ep2{};
   ep2.bias = bias;
   ep2.row_sub = lse; ep2.row_max = row_max; ep2.argmax = argmax;
-  return launch_linear(enc, w, log_probs, STAC_DT_F32, m, vocab, d_model, ep2, stream);  // pass 2: logits - lse
+  return launch_linear(enc, w, log_probs, out_dtype, m, vocab, d_model, ep2, stream);  // pass 2: logits - lse
 }
 
 extern "C" int stac_conv1_bf16(const uint16_t* xpad, const uint16_t* w1_packed, const float* b1,

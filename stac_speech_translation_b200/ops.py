@@ -319,10 +319,7 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
     ctx = torch.empty(m, d, device=dev, dtype=act_dt)
     d_ffn = w.layers[0].w_1.shape[0] if w.layers else 4 * d
     ff = torch.empty(m, d_ffn, device=dev, dtype=act_dt)
-    vt = None
     t_pad = (t2 + 7) // 8 * 8
-    if prec == "bf16":
-        vt = torch.zeros(b * h * 64 * t_pad, device=dev, dtype=torch.bfloat16)   # padding keys stay zero
     for L in w.layers:
         if prec == "fp32":
             _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_f32=hbuf)
@@ -330,8 +327,9 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
             _call("stac_mha_f32", ptr(qkv), ptr(kv_len, torch.int32), b, t2, d, h, ptr(ctx), stream())
         else:
             _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_bf16=hbuf)
-            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec, vt=vt, vt_cols=d, seq_len=t2, t_pad=t_pad, tag="qkv")
-            _call("stac_mha_bf16", ptr(qkv), ptr(vt), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
+            _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec, tag="qkv")
+            # V is read straight from the packed projection (MN-major B operand): no transposed copy
+            _call("stac_mha_bf16", ptr(qkv), ptr(None), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
                                       stream())
         _gemm(ctx, L.w_o, L.b_o, x, prec, resid=x, tag="out_proj")
         if prec == "fp32":
@@ -363,7 +361,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     return out.view(*shp[:-1], weight.shape[0])
 
 
-def ctc_head_bf16(enc_bf16: torch.Tensor, weight_bf16: torch.Tensor, bias: Optional[torch.Tensor]):
+def ctc_head_bf16(enc_bf16: torch.Tensor, weight_bf16: torch.Tensor, bias: Optional[torch.Tensor],
+                  out_dtype: torch.dtype = torch.float32):
     """a8 + a9 fused (bf16 mode): log_softmax(enc W^T + b) fp32 [.., V] and greedy ids int32 [..], logits never
     materialised (two GEMM passes, see include/stac_b200.h)."""
     shp = enc_bf16.shape
@@ -372,12 +371,12 @@ def ctc_head_bf16(enc_bf16: torch.Tensor, weight_bf16: torch.Tensor, bias: Optio
     v = weight_bf16.shape[0]
     global _LABEL
     ws = torch.empty(lib().stac_ctc_head_workspace_floats(m, v), device=x2.device, dtype=torch.float32)
-    out = torch.empty(m, v, device=x2.device, dtype=torch.float32)
+    out = torch.empty(m, v, device=x2.device, dtype=out_dtype)
     ids = torch.empty(m, device=x2.device, dtype=torch.int32)
     prev, _LABEL = _LABEL, "ctc_head"
     try:
         _call("stac_ctc_head_bf16", ptr(x2, torch.bfloat16), ptr(weight_bf16, torch.bfloat16), ptr(bias), m, v, d,
-              ptr(ws), ptr(out), ptr(ids), stream())
+              ptr(ws), ptr(out), DT_BF16 if out_dtype == torch.bfloat16 else DT_F32, ptr(ids), stream())
     finally:
         _LABEL = prev
     return out.view(*shp[:-1], v), ids.view(shp[:-1])

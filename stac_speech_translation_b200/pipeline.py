@@ -104,8 +104,10 @@ class EncoderPipeline:
     ``append_speaker_turns`` reads, /root/reference/stac-st/inference.py:54-56).
     """
 
-    def __init__(self, mods: Dict[str, nn.Module], precision: Optional[str] = None, train_mask: bool = False):
+    def __init__(self, mods: Dict[str, nn.Module], precision: Optional[str] = None, train_mask: bool = False,
+                 posterior_dtype: torch.dtype = torch.float32):
         self.mods = mods
+        self.posterior_dtype = posterior_dtype      # bf16 only for ranks that ship posteriors to rank 0
         self.precision = precision or mods["Transformer"].precision
         for k in ("CNN", "Transformer", "ctc_lin"):
             if mods[k].precision != self.precision:
@@ -138,7 +140,7 @@ class EncoderPipeline:
             ctc = m["ctc_lin"]
             bias = None if ctc.w.bias is None else ctc.w.bias.detach().float().contiguous()
             if bf16:
-                p, ids = ops.ctc_head_bf16(enc_b, ctc.packed_weight(), bias)
+                p, ids = ops.ctc_head_bf16(enc_b, ctc.packed_weight(), bias, self.posterior_dtype)
             else:
                 logits = ops.linear(enc_b, ctc.packed_weight(), bias, self.precision, tag="ctc_lin")
                 p, ids = ops.log_softmax(logits, want_argmax=True, inplace=True)

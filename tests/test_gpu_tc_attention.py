@@ -12,7 +12,8 @@ from stac_speech_translation_b200 import ops  # noqa: E402
                                          (130, [129, 130, 5], 256, 4), (751, [751, 400], 256, 4),
                                          (300, [300, 299], 512, 8), (300, [300 - 3 * i for i in range(40)], 256, 4),
                                          (100, [100 - i for i in range(90)], 128, 2), (1501, [1501, 1200], 128, 2)])
-def test_mha_bf16(t, lens, d, h):
+@pytest.mark.parametrize("use_vt", [False, True])
+def test_mha_bf16(t, lens, d, h, use_vt):
     g = torch.Generator().manual_seed(t + d)
     b = len(lens)
     qkv = (torch.randn(b * t, 3 * d, generator=g)).to(torch.bfloat16)
@@ -22,7 +23,7 @@ def test_mha_bf16(t, lens, d, h):
     vt[..., :t] = qkv[:, 2 * d:].view(b, t, h, 64).permute(0, 2, 3, 1)
     ctx = torch.full((b * t, d), float("nan"), device="cuda", dtype=torch.bfloat16)
     qkv_d, vt_d, kv_d = qkv.cuda(), vt.cuda().contiguous(), kv.cuda()   # keep alive across the async launch
-    ops.check(ops.lib().stac_mha_bf16(ops.ptr(qkv_d), ops.ptr(vt_d), ops.ptr(kv_d),
+    ops.check(ops.lib().stac_mha_bf16(ops.ptr(qkv_d), ops.ptr(vt_d if use_vt else None), ops.ptr(kv_d),
                                       b, t, t_pad, d, h, ops.ptr(ctx), ops.stream()))
     torch.cuda.synchronize()
     q, k, v = (x.float().view(b, t, h, 64).transpose(1, 2) for x in qkv.split(d, dim=-1))
