@@ -7,11 +7,13 @@
 //
 // head_dim 64 makes this kernel MUFU-bound (one ex2 per score against 4 MMA flops per score per 64-wide d), so the
 // design goal is to keep the exponential pipe of every SM sub-partition busy, not the tensor core:
-//   * persistent, warp-specialised, one CTA per SM, 320 threads:
-//       warps 0-3  softmax group 0 (query tile 0: 128 rows, thread = row)
-//       warps 4-7  softmax group 1 (query tile 1)
-//       warp  8    TMA producer (Q tiles double-buffered per work item, K / V tiles in a 5-stage ring)
-//       warps 9-10 MMA issuers (one thread per softmax group)
+//   * persistent, warp-specialised, one CTA per SM, 608 threads:
+//       warps 0-7   softmax group 0 (query tile 0: 128 rows; warp & 3 = 32-row quarter, (warp >> 2) & 1 = which 32 of
+//                   the 64 key columns: two threads per row, so every SM sub-partition holds FOUR softmax warps whose
+//                   max / exp / pack / store phases interleave and keep its exp unit fed)
+//       warps 8-15  softmax group 1 (query tile 1)
+//       warps 16-17 MMA issuers (one thread per softmax group)
+//       warp  18    TMA producer (Q tiles double-buffered per work item, K / V tiles in a 5-stage ring)
 //   * work item = (utterance, head, block of 256 queries); the two query tiles share every K / V tile;
 //   * key tiles are 64 wide and every group owns TWO score buffers in TMEM: S(j+1) = Q K_{j+1}^T is issued as soon
 //     as the softmax warps have pulled S(j-1) into registers, i.e. it is already there when they finish tile j, and
@@ -30,20 +32,30 @@ using namespace tc;
 
 constexpr int kHd = 64, kQTile = 128, kKTile = 64;
 constexpr int kKvStages = 5;
-constexpr int kThreads = 352;
+constexpr int kThreads = 608;
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int kOffQ = 0;                         // [2 bufs][2 groups] x 16 KB
 constexpr int kOffP = 65536;                     // [2 groups][2 bufs] x 16 KB (128 rows x 64 keys bf16, K-major)
 constexpr int kOffKV = 131072;                   // [stages] x (K 8 KB + V 8 KB)
-constexpr int kOffBar = kOffKV + kKvStages * 16384;
+constexpr int kOffX = kOffKV + kKvStages * 16384;      // float [2 groups][2 bufs][2 halves][128 rows]: row-max exchange
+constexpr int kOffLen = kOffX + 2 * 2 * 2 * 128 * 4;   // int [kLenCache]
+constexpr int kOffBar = kOffLen + 128 * 4;
 constexpr int kNumBars = 8 + 2 * kKvStages + 18;
+#ifdef MHA_TRACE
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024 + 5 * 64 * 8 * 4;
+#else
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+#endif
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef MHA_NOEXP      // timing experiment only (tools/bench_mha.py): results are wrong
+  return x;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 // tcgen05.st: 32 lanes x 32 consecutive fp32 columns (thread i writes TMEM lane base_lane + i)
@@ -60,26 +72,48 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 3-input max (one instruction on sm_100)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+#ifdef MHA_TRACE     // timing experiment only (tools/trace_mha.py): CTA 0 logs clock32 per (role, step, event) in smem
+__device__ unsigned int* g_trace = nullptr;
+#define TRACE(role, ev, step)                                                                        \
+  do {                                                                                               \
+    if (blockIdx.x == 0 && (step) < 64) trace_s[((role) * 64 + (step)) * 8 + (ev)] = (unsigned int)clock64(); \
+  } while (0)
+#else
+#define TRACE(role, ev, step) do {} while (0)
+#endif
+
 struct Item {
   int b, h, q0, n_keys, n_kt;
   bool active1;      // the second query tile of the block exists
 };
 
-__device__ __forceinline__ Item decode_item(int item, int n_qblk, int n_head, int seq_len,
-                                            const int* __restrict__ kv_len) {
+constexpr int kLenCache = 128;     // key counts of the first work items of a CTA, staged in smem at kernel start
+
+__device__ __forceinline__ Item decode_item(int item, int ordinal, const int* len_cache, int n_qblk, int n_head,
+                                            int seq_len, const int* __restrict__ kv_len) {
   Item it;
   const int qb = item % n_qblk;
   const int bh = item / n_qblk;
   it.h = bh % n_head;
   it.b = bh / n_head;
   it.q0 = qb * 2 * kQTile;
-  it.n_keys = min(max(__ldg(kv_len + it.b), 1), seq_len);
+  // (a global load here would sit on the critical path of every role at every item boundary)
+  it.n_keys = min(max(ordinal < kLenCache ? len_cache[ordinal] : __ldg(kv_len + it.b), 1), seq_len);
   it.n_kt = (it.n_keys + kKTile - 1) / kKTile;
   it.active1 = it.q0 + kQTile < seq_len;
   return it;
 }
 
-// 11 warps = 3 on three of the four SM sub-partitions, whose 16 K-register files cap the kernel at 168 regs/thread
 template <bool kVT>
 __global__ void __launch_bounds__(kThreads, 1)
 mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -102,8 +136,16 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto p_free = [&](int w, int i) { return gb + 8u * (w * 9 + 6 + i); };
   auto o_free = [&](int w) { return gb + 8u * (w * 9 + 8); };
   const uint32_t tmem_slot = bars + 8u * kNumBars;
+#ifdef MHA_TRACE
+  unsigned int* trace_s = reinterpret_cast<unsigned int*>(sptr + kOffBar + kNumBars * 8 + 16);
+#endif
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* len_cache = reinterpret_cast<int*>(sptr + kOffLen);
+  for (int n = tid; n < kLenCache; n += kThreads) {
+    const long long item = (long long)blockIdx.x + (long long)n * gridDim.x;
+    if (item < n_items) len_cache[n] = __ldg(kv_len + (int)(item / n_qblk) / n_head);
+  }
 
   if (tid == 0) {
     prefetch_tmap(&tmap_q);
@@ -113,20 +155,20 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int s = 0; s < kKvStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }
     for (int w = 0; w < 2; ++w) {
       for (int i = 0; i < 2; ++i) {
-        mbar_init(s_full(w, i), 1); mbar_init(s_free(w, i), 4); mbar_init(p_full(w, i), 4); mbar_init(p_free(w, i), 1);
+        mbar_init(s_full(w, i), 1); mbar_init(s_free(w, i), 8); mbar_init(p_full(w, i), 8); mbar_init(p_free(w, i), 1);
       }
-      mbar_init(o_free(w), 4);
+      mbar_init(o_free(w), 8);
     }
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 16) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 8) {
+  if (warp == 18) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
@@ -134,7 +176,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       int n_done = 0;
       uint32_t q_uses[2][2] = {{0, 0}, {0, 0}};   // fills of Q buffer (buf, w): parity source
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
-        const Item it = decode_item(item, n_qblk, n_head, seq_len, kv_len);
+        const Item it = decode_item(item, n_done, len_cache, n_qblk, n_head, seq_len, kv_len);
         const int buf = n_done & 1;
         const int row_base = it.b * seq_len;
         for (int w = 0; w < 2; ++w) {
@@ -147,6 +189,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         for (int j = 0; j < it.n_kt; ++j) {
           mbar_wait(kv_empty(stage), kv_phase ^ 1);
+          TRACE(0, 0, (n_done * it.n_kt + j));
           const uint32_t kdst = sbase + kOffKV + stage * 16384;
           mbar_arrive_expect_tx(kv_full(stage), 16384);
           tma_load_2d(kdst, &tmap_kv, kv_full(stage), d_model + it.h * kHd, row_base + j * kKTile);
@@ -157,13 +200,15 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp >= 9) {
-    // ============================ MMA issuers: warp 9 -> group 0, warp 10 -> group 1 ============================
+  } else if (warp >= 16) {
+    // ============================ MMA issuers: warp 16 -> group 0, warp 17 -> group 1 ============================
     // Per group the order is fixed: S(0) S(1) | P.V(0) S(2) | P.V(1) S(3) | ...  (the scores run two tiles ahead of
     // the softmax; s_free(g) always arrives before p_full(g), so blocking waits in this order never stall a ready
     // operation).  The two groups are independent instruction streams on different sub-partitions.
-    if (lane == 0) {
-      const int w = warp - 9;
+    {
+      // every lane runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions, which lets
+      // ptxas keep descriptors in uniform registers instead of wrapping each MMA in a broadcast loop
+      const int w = warp - 16;
       constexpr uint32_t idesc_s = make_idesc_bf16(128, kKTile);
       // P.V: N = head_dim; V straight from the QKV projection is an MN-major B operand (bit 16)
       constexpr uint32_t idesc_o = make_idesc_bf16(128, kHd) | (kVT ? 0u : (1u << 16));
@@ -176,7 +221,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       };
       auto load_item = [&](Cursor& c) {
         c.valid = c.item < n_items;
-        if (c.valid) { const Item it = decode_item(c.item, n_qblk, n_head, seq_len, kv_len); c.n_kt = it.n_kt; c.active1 = it.active1; }
+        if (c.valid) { const Item it = decode_item(c.item, c.n_done, len_cache, n_qblk, n_head, seq_len, kv_len); c.n_kt = it.n_kt; c.active1 = it.active1; }
       };
       auto skip_inactive = [&](Cursor& c) {
         // group 1 has no query tile in some items: its cursor jumps over them (and over their ring stages)
@@ -212,39 +257,50 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         while (sc.valid && g_s < g_p + 2) {
           // ---- S(g_s) = Q K^T into score buffer g_s & 1 ----
           const int i = g_s & 1, buf = sc.n_done & 1;
+          TRACE(1 + w, 0, g_s);
           mbar_wait(kv_full(sc.stage), sc.phase);
+          TRACE(1 + w, 1, g_s);
           mbar_wait(s_free(w, i), ((uint32_t)(g_s >> 1) & 1) ^ 1);
+          TRACE(1 + w, 2, g_s);
           if (sc.j == 0) mbar_wait(q_full(buf, w), (buf ? q_fill1 : q_fill0) & 1);
           tc_fence_after();
-          const uint64_t qd = make_smem_desc_sw128(q_base + buf * 32768);
-          const uint64_t kd = make_smem_desc_sw128(sbase + kOffKV + sc.stage * 16384);
+          const bool last_of_item = sc.j == sc.n_kt - 1;
+          if (elect_one()) {
+            const uint64_t qd = make_smem_desc_sw128(q_base + buf * 32768);
+            const uint64_t kd = make_smem_desc_sw128(sbase + kOffKV + sc.stage * 16384);
 #pragma unroll
-          for (int k = 0; k < kHd / 16; ++k) umma_bf16(s_tmem + i * kKTile, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full(w, i));
-          if (sc.j == sc.n_kt - 1) {
-            umma_commit(q_empty(buf, w));
-            if (buf) ++q_fill1; else ++q_fill0;
+            for (int k = 0; k < kHd / 16; ++k) umma_bf16(s_tmem + i * kKTile, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+            umma_commit(s_full(w, i));
+            if (last_of_item) umma_commit(q_empty(buf, w));
           }
+          __syncwarp();
+          if (last_of_item) { if (buf) ++q_fill1; else ++q_fill0; }
+          TRACE(1 + w, 3, g_s);
           ++g_s;
           advance(sc);
         }
         // ---- O += P(g_p) V ----
         {
           const int i = g_p & 1;
+          TRACE(1 + w, 4, g_p);
           mbar_wait(p_full(w, i), (uint32_t)(g_p >> 1) & 1);
+          TRACE(1 + w, 5, g_p);
           if (pc.j == 0) { mbar_wait(o_free(w), (items_started & 1) ^ 1); ++items_started; }
           tc_fence_after();
-          const uint64_t pd = make_smem_desc_sw128(sbase + kOffP + (w * 2 + i) * 16384);
-          const uint32_t vaddr = sbase + kOffKV + pc.stage * 16384 + 8192;
-          const uint64_t vd = make_smem_desc_sw128(vaddr);
+          if (elect_one()) {
+            const uint64_t pd = make_smem_desc_sw128(sbase + kOffP + (w * 2 + i) * 16384);
+            const uint64_t vd = make_smem_desc_sw128(sbase + kOffKV + pc.stage * 16384 + 8192);
 #pragma unroll
-          for (int k = 0; k < kKTile / 16; ++k) {
-            // K-major V^T: 16 keys = 32 bytes inside the swizzled row (+2); MN-major V: 16 keys = 16 rows of 128 bytes (+128)
-            umma_bf16(o_tmem, pd + 2 * k, vd + (kVT ? 2 * k : 128 * k), idesc_o, (k | pc.j) != 0);
+            for (int k = 0; k < kKTile / 16; ++k) {
+              // K-major V^T: 16 keys = 32 bytes inside the swizzled row (+2); MN-major V: 16 keys = 16 rows of 128 bytes (+128)
+              umma_bf16(o_tmem, pd + 2 * k, vd + (kVT ? 2 * k : 128 * k), idesc_o, (k | pc.j) != 0);
+            }
+            umma_commit(p_free(w, i));
+            umma_commit(kv_empty(pc.stage));                 // second arrival comes from the other group's issuer ...
+            if (w == 0 && !pc.active1) mbar_arrive(kv_empty(pc.stage));   // ... or from here when it has no tile in this item
           }
-          umma_commit(p_free(w, i));
-          umma_commit(kv_empty(pc.stage));                 // second arrival comes from the other group's issuer ...
-          if (w == 0 && !pc.active1) mbar_arrive(kv_empty(pc.stage));   // ... or from here when it has no tile in this item
+          __syncwarp();
+          TRACE(1 + w, 6, g_p);
           ++g_p;
           advance(pc);
         }
@@ -253,77 +309,88 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     __syncwarp();
   } else {
     // ============================ softmax groups ============================
-    const int w = warp >> 2;                       // group / query tile
-    const int r = tid & 127;                       // row inside the tile
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tmem_o = tmem_base + 256 + w * kHd + lane_off;
+    const int w = warp >> 3;                       // group / query tile
+    const int quarter = warp & 3, ch = (warp >> 2) & 1;   // 32-row quarter (= TMEM lane quarter), column half
+    const int r = quarter * 32 + lane;             // row inside the tile
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tmem_o = tmem_base + 256 + w * kHd + ch * 32 + lane_off;
     const int sw = r & 7;
+    const int pair_bar = 1 + w * 4 + quarter;      // named barrier of the two warps that share these 32 rows
+    float* xch = reinterpret_cast<float*>(sptr + kOffX) + w * 512;
     int g = 0;                                     // per-group step index
-    uint32_t n_items_done = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const Item it = decode_item(item, n_qblk, n_head, seq_len, kv_len);
+    int ordinal = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
+      const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
       if (w == 1 && !it.active1) continue;
       // m_ref: the maximum the exponents are taken against.  It is only raised (and O / l rescaled) when the
-      // running maximum exceeds it by more than 8 in the log2 domain, so P <= 2^8 and the O accumulator in
-      // TMEM is touched by the CUDA cores only on those rare steps and once at the end.
+      // running maximum exceeds it by more than 2^kRaise: P <= 2^kRaise stays far inside bf16 / fp32 range, and the
+      // O accumulator in TMEM is touched by the CUDA cores only on those rare steps and once at the end.
+      constexpr float kRaise = 40.0f;
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < it.n_kt; ++j, ++g) {
         const int i = g & 1;
         const uint32_t u = (uint32_t)(g >> 1) & 1;
+        if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 0, g);
         mbar_wait(s_full(w, i), u);
+        if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 1, g);
         tc_fence_after();
-        uint32_t v[64];
-        {
-          uint32_t va[32], vb[32];
-          const uint32_t tmem_s = tmem_base + (w * 2 + i) * kKTile + lane_off;
-          tmem_ld32(tmem_s, va);
-          tmem_ld32(tmem_s + 32, vb);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) { v[c] = va[c]; v[32 + c] = vb[c]; }
-        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (w * 2 + i) * kKTile + ch * 32 + lane_off, v);
+        tmem_ld_wait();
         // the scores are in registers: the MMA warp may overwrite this buffer with S(g + 2)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free(w, i));
-        // P buffer i was last read by P.V(g - 2); once that has retired, O holds every step up to g - 2
-        mbar_wait(p_free(w, i), u ^ 1);
-        const int valid = it.n_keys - j * kKTile;    // columns < valid are real keys
+        if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 2, g);
+        const int valid = it.n_keys - j * kKTile - ch * 32;    // my columns < valid are real keys
         float tm0 = -INFINITY, tm1 = -INFINITY;
-        if (valid >= kKTile) {
+#ifdef MHA_NOMAX
+        tm0 = tm1 = 0.f;
+        if (true) {
+        } else
+#endif
+        if (valid >= 32) {
 #pragma unroll
-          for (int c = 0; c < 64; c += 2) {
-            tm0 = fmaxf(tm0, __uint_as_float(v[c]));
-            tm1 = fmaxf(tm1, __uint_as_float(v[c + 1]));
+          for (int c = 0; c < 32; c += 4) {
+            tm0 = max3(tm0, __uint_as_float(v[c]), __uint_as_float(v[c + 1]));
+            tm1 = max3(tm1, __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
+          for (int c = 0; c < 32; ++c) {
             if (c >= valid) v[c] = 0xff800000u;        // -inf: exp2 gives exactly 0
             tm0 = fmaxf(tm0, __uint_as_float(v[c]));
           }
         }
-        const float tile_max = fmaxf(tm0, tm1);
+        // row maximum over both column halves (the partner warp holds the other 32 columns of these rows)
+        float* xrow = xch + i * 256 + r;
+#ifdef MHA_NOMAX
+        const float tile_max = 0.f;
+#else
+        xrow[ch * 128] = fmaxf(tm0, tm1);
+        named_bar_sync(pair_bar, 64);
+        const float tile_max = fmaxf(fmaxf(tm0, tm1), xrow[(ch ^ 1) * 128]);
+#endif
+        // P buffer i was last read by P.V(g - 2); once that has retired, O holds every step up to g - 2
+        mbar_wait(p_free(w, i), u ^ 1);
+        if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 3, g);
         if (j == 0) {
           m_ref = tile_max;                          // O is overwritten by the first P.V of the item
         } else {
-          const bool raise = (tile_max - m_ref) * kLog2e > 8.0f;
+          const bool raise = (tile_max - m_ref) * kLog2e > kRaise;
           if (__any_sync(0xffffffffu, raise)) {
             const float factor = raise ? ex2_approx((m_ref - tile_max) * kLog2e) : 1.0f;
             if (raise) m_ref = tile_max;
             l_run *= factor;
             mbar_wait(p_free(w, i ^ 1), (uint32_t)((g - 1) >> 1) & 1);   // P.V of the previous step has landed in TMEM
             tc_fence_after();
-#pragma unroll 1
-            for (int ch = 0; ch < 2; ++ch) {
-              uint32_t o[32];
-              tmem_ld32(tmem_o + ch * 32, o);
-              tmem_ld_wait();
+            uint32_t o[32];
+            tmem_ld32(tmem_o, o);
+            tmem_ld_wait();
 #pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
-              tmem_st32(tmem_o + ch * 32, o);
-              tmem_st_wait();
-            }
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
+            tmem_st32(tmem_o, o);
+            tmem_st_wait();
             tc_fence_before();
           }
         }
@@ -331,7 +398,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         unsigned char* prow = sptr + kOffP + (w * 2 + i) * 16384 + r * 128;
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -341,28 +408,36 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             l1 += p1;
             pk[e] = pack_bf16x2(p0, p1);
           }
-          *reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#ifdef MHA_NOPSTORE
+          if (pk[0] == 0x12345678u && pk[3] == 0x9abcdef0u)
+#endif
+          *reinterpret_cast<uint4*>(prow + (((ch * 4 + q) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         l_run += l0 + l1;
+        if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 4, g);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(w, i));
+        if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 5, g);
       }
-      // epilogue of the item: O (TMEM) / l -> ctx
+      // epilogue of the item: O (TMEM) / l -> ctx; the row sum is the total over both column halves
+      float* xrow = xch + (g & 1) * 256 + r;
+      xrow[ch * 128] = l_run;
+      named_bar_sync(pair_bar, 64);
+      const float inv = 1.0f / (l_run + xrow[(ch ^ 1) * 128]);
+      named_bar_sync(pair_bar, 64);                  // the exchange slot is reused by the next item's first steps
       mbar_wait(p_free(w, (g - 1) & 1), (uint32_t)((g - 1) >> 1) & 1);   // the last P.V of the item has retired
       tc_fence_after();
       const int q = it.q0 + w * kQTile + r;
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = ctx + ((int64_t)it.b * seq_len + q) * d_model + it.h * kHd;
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      __nv_bfloat16* dst = ctx + ((int64_t)it.b * seq_len + q) * d_model + it.h * kHd + ch * 32;
+      {
         uint32_t o[32];
-        tmem_ld32(tmem_o + ch * 32, o);
+        tmem_ld32(tmem_o, o);
         tmem_ld_wait();
         if (q < seq_len) {
 #pragma unroll
           for (int c = 0; c < 32; c += 8) {
-            *reinterpret_cast<uint4*>(dst + ch * 32 + c) = make_uint4(
+            *reinterpret_cast<uint4*>(dst + c) = make_uint4(
                 pack_bf16x2(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv),
                 pack_bf16x2(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv),
                 pack_bf16x2(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv),
@@ -373,14 +448,16 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free(w));         // the next item's first P.V may overwrite O_w
-      ++n_items_done;
     }
-    (void)n_items_done;
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+#ifdef MHA_TRACE
+  if (blockIdx.x == 0 && g_trace != nullptr)
+    for (int k = tid; k < 5 * 64 * 8; k += kThreads) g_trace[k] = trace_s[k];
+#endif
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 int num_sms_attn() {
@@ -410,6 +487,13 @@ int launch_mha(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap&
 }
 
 }  // namespace
+
+#ifdef MHA_TRACE
+extern "C" int stac_mha_trace(unsigned int* buf) {
+  cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+  return 0;
+}
+#endif
 
 extern "C" int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int32_t* kv_len, int64_t batch,
                              int64_t seq_len, int64_t t_pad, int64_t d_model, int64_t n_head, uint16_t* ctx,
