@@ -53,8 +53,8 @@ const char* stac_error_string(int code);
  *
  * tables: constant block built once by the host (layout: stac_fbank_tables_floats()
  *         floats: window[400] | mel_start[80] | mel_count[80] | mel_weight[80][16]).
- * utt_max_ordered: uint32[B], order-preserving encoding of the fp32 maximum; the
- *         caller zero-fills it before the call (0 encodes "below every float").
+ * utt_max_ordered: uint32[B], order-preserving encoding of the fp32 maximum (zeroed by the
+ *         call itself with a stream-ordered memset; 0 encodes "below every float").
  */
 int stac_fbank_tables_floats(void);
 int stac_fbank_logmel(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_row_stride,
@@ -136,9 +136,18 @@ int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float* bias, cons
                    int64_t k, uint16_t* vt_out, int64_t vt_cols, int64_t seq_len, int64_t t_pad,
                    void* stream);
 
+/* Valid key count per utterance, int32 [B], from the relative lengths the reference passes around
+ * (wav_lens = len / Lmax, fp32) with the reference's own fp32 arithmetic:
+ *   round_rule 0: encode()  keeps j <= floor(wav_len * T2)   -> floor(.) + 1   (TransformerMultiTask.py:289-294)
+ *   round_rule 1: forward() keeps j <  round(wav_len * T2)   (round half to even, make_masks :225-226)
+ * clamped to [1, T2]; wav_len NULL -> T2 for every utterance. */
+int stac_kv_lengths(const float* wav_len, int64_t batch, int64_t t2, int round_rule, int32_t* out, void* stream);
+
 /* Multi-head self-attention with key-padding by valid length (head_dim 64):
  *   qkv [B*T, 3*d] packed [q|k|v] with bias already added and q pre-scaled by 1/8,
- *   kv_len int32[B] (keys j < kv_len[b] are attended), ctx [B*T, d].                  */
+ *   kv_len int32[B] (keys j < kv_len[b] are attended), ctx [B*T, d].
+ * stac_mha_bf16: v_t = NULL reads V straight from qkv (MN-major tensor-core operand, the normal path);
+ *   v_t != NULL is a K-major transposed copy bf16 [B*H][64][t_pad] (t_pad % 8 == 0, zero padded).      */
 int stac_mha_f32(const float* qkv, const int32_t* kv_len, int64_t batch, int64_t seq_len,
                  int64_t d_model, int64_t n_head, float* ctx, void* stream);
 int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int32_t* kv_len, int64_t batch,

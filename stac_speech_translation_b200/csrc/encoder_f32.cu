@@ -155,6 +155,19 @@ log_softmax_kernel(const float* __restrict__ logits, int vocab, float* __restric
   if (argmax && threadIdx.x == 0) argmax[r] = bi;
 }
 
+// valid key count per utterance from the reference's own fp32 expressions (see include/stac_b200.h)
+__global__ void kv_lengths_kernel(const float* __restrict__ wav_len, int batch, int t2, int round_rule,
+                                  int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  int n = t2;
+  if (wav_len != nullptr) {
+    const float x = __fmul_rn(wav_len[i], (float)t2);
+    n = round_rule ? (int)rintf(x) : (int)floorf(x) + 1;      // torch.round is round-half-to-even
+  }
+  out[i] = min(max(n, 1), t2);
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ out) {
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
        i += (int64_t)gridDim.x * blockDim.x * 4) {
@@ -212,6 +225,14 @@ extern "C" int stac_log_softmax(const float* logits, int64_t rows, int64_t vocab
                                 int32_t* argmax, void* stream) {
   STAC_REQUIRE(logits && out && rows > 0 && rows < (1ll << 31) && vocab > 0 && vocab < (1 << 30));
   log_softmax_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(logits, (int)vocab, out, argmax);
+  STAC_LAUNCH_CHECK();
+}
+
+extern "C" int stac_kv_lengths(const float* wav_len, int64_t batch, int64_t t2, int round_rule, int32_t* out,
+                               void* stream) {
+  STAC_REQUIRE(out && batch > 0 && batch < (1 << 30) && t2 > 0 && t2 < (1 << 24));
+  kv_lengths_kernel<<<(unsigned)ceil_div64(batch, 128), 128, 0, as_stream(stream)>>>(wav_len, (int)batch, (int)t2,
+                                                                                    round_rule, out);
   STAC_LAUNCH_CHECK();
 }
 

@@ -241,6 +241,8 @@ extern "C" int stac_fbank_logmel(const float* pcm, int64_t batch, int64_t n_samp
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  cudaError_t me = cudaMemsetAsync(utt_max_ordered, 0, (size_t)batch * sizeof(uint32_t), as_stream(stream));
+  if (me != cudaSuccess) return (int)me;
   dim3 grid((unsigned)ceil_div64(n_frames, kFrames), (unsigned)batch);
   fbank_logmel_kernel<<<grid, kThreads, sizeof(Smem), as_stream(stream)>>>(
       pcm, n_samples, pcm_row_stride, n_frames, tables, logmel_db, utt_max_ordered);

@@ -123,7 +123,7 @@ def fbank(wavs: torch.Tensor, tables: torch.Tensor, top_db: float = 80.0, per_ut
     b, n = wavs.shape
     t = 1 + n // HOP
     db = torch.empty(b, t, N_MELS, device=wavs.device, dtype=torch.float32)
-    umax = torch.zeros(b, device=wavs.device, dtype=torch.int32)
+    umax = torch.empty(b, device=wavs.device, dtype=torch.int32)      # zeroed by the call (stream-ordered memset)
     _call("stac_fbank_logmel", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tables), ptr(db),
                                   ptr(umax), stream())
     _call("stac_fbank_topdb_norm", ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),
@@ -260,6 +260,12 @@ def kv_lengths(wav_len: Optional[torch.Tensor], batch: int, t2: int, device, tra
     """Valid key count per utterance, from the reference's own fp32 expressions:
     encode(): keep j <= floor(wav_len*T2)   (TransformerMultiTask.py:289-294)
     forward(): keep j <  round(wav_len*T2)  (TransformerMultiTask.py:225-226)."""
+    if torch.device(device).type == "cuda":
+        out = torch.empty(batch, device=device, dtype=torch.int32)
+        wl = None if wav_len is None else wav_len.to(device=device, dtype=torch.float32).contiguous()
+        _call("stac_kv_lengths", ptr(wl), batch, t2, int(train_mask), ptr(out), stream())
+        return out
+    # host-side twin of the kernel (index math on CPU tensors; used by the CPU tests of the mask rules)
     if wav_len is None:
         return torch.full((batch,), t2, device=device, dtype=torch.int32)
     wl = wav_len.to(device=device, dtype=torch.float32)
