@@ -151,7 +151,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // (the whole warp runs the loop; one elected lane issues: warp-uniform operands stay in uniform registers)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -162,26 +163,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * kStageBytes;
           const uint32_t b_dst = a_dst + kABytes;
-          if (kConv) {
-            mbar_arrive_expect_tx(full_bar(stage), kConvRows * BLOCK_K * 2 + kBBytes);
-            const int tap = kb >> 2, c0 = (kb & 3) * BLOCK_K;
-            const int kf = tap / 3, kt = tap - 3 * kf;
-            tma_load_5d(a_dst, &tmap_a, full_bar(stage), c0, kf >> 1, conv_t0 + (kt >> 1),
-                        (kt & 1) * 2 + (kf & 1), conv_b);
-            tma_load_2d(b_dst, &tmap_b, full_bar(stage), c0, tap * 256 + n_tile * BLOCK_N);
-          } else {
-            mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-            tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m_tile * BLOCK_M);
-            tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+          if (elect_one()) {
+            if (kConv) {
+              mbar_arrive_expect_tx(full_bar(stage), kConvRows * BLOCK_K * 2 + kBBytes);
+              const int tap = kb >> 2, c0 = (kb & 3) * BLOCK_K;
+              const int kf = tap / 3, kt = tap - 3 * kf;
+              tma_load_5d(a_dst, &tmap_a, full_bar(stage), c0, kf >> 1, conv_t0 + (kt >> 1),
+                          (kt & 1) * 2 + (kf & 1), conv_b);
+              tma_load_2d(b_dst, &tmap_b, full_bar(stage), c0, tap * 256 + n_tile * BLOCK_N);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+              tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * BLOCK_K, m_tile * BLOCK_M);
+              tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+            }
           }
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -194,22 +197,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * kStageBytes;
-          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-          const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * kStageBytes;
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+            const uint64_t b_desc = make_smem_desc_sw128(a_addr + kABytes);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // +32 B per UMMA_K step inside the 128-B swizzle atom (descriptor address unit = 16 B)
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // +32 B per UMMA_K step inside the 128-B swizzle atom (descriptor address unit = 16 B)
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
+            if (kb == num_k_blocks - 1) umma_commit(tfull_bar(acc));
           }
-          umma_commit(empty_bar(stage));   // frees the smem slot when these MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(tfull_bar(acc));
+          __syncwarp();
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if constexpr (kConv) {
     // ===================== conv epilogue: 4 warps, fused bias + LayerNorm(20 x 256) + LeakyReLU ==========
     // Thread = accumulator row (t_local, f2); a time step's LayerNorm group is 20 rows x 256 columns, all inside
@@ -453,7 +458,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if (ep.c_bf16) {
           // 64 bf16 columns = one 128-byte staging row; this half fills 16-byte chunks half*4 .. +3
-          if (half == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+          if (half == 0) { bulk_wait_read0(); __syncwarp(); }     // (every lane: the elected issuer is one of them)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             st_shared_v4(my_row + (((half * 4 + j) ^ sw) << 4), pack_bf16x2(x[8 * j], x[8 * j + 1]),
@@ -464,11 +469,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (last_half) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && row0 < ep.m) { tma_store_2d(&tmap_c, stage_buf, colg, row0); bulk_commit(); }
+            if (row0 < ep.m && elect_one()) { tma_store_2d(&tmap_c, stage_buf, colg, row0); bulk_commit(); }
           }
         } else {
           // 32 fp32 columns = one 128-byte staging row
-          if (lane == 0) bulk_wait_read0();
+          bulk_wait_read0();
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -477,7 +482,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && row0 < ep.m) {
+          if (row0 < ep.m && elect_one()) {
             if (ep.reduce_add) tma_reduce_add_2d(&tmap_c, stage_buf, col0, row0);
             else tma_store_2d(&tmap_c, stage_buf, col0, row0);
             bulk_commit();
@@ -485,7 +490,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-    if (lane == 0) bulk_wait0();
+    bulk_wait0();
     __syncwarp();
   }
 
