@@ -118,6 +118,7 @@ def work_table(size_cfg, batch, n_samples, kv_len_sum_sq_like):
         "stac_gemm_bf16:out_proj": ("tensor", 2 * d * d * m, layers),
         "stac_gemm_bf16:ffn1": ("tensor", 2 * d * dffn * m, layers),
         "stac_gemm_bf16:ffn2": ("tensor", 2 * d * dffn * m, layers),
+        "stac_ffn_fused_bf16": ("tensor", 4 * d * dffn * m, layers),
         "stac_gemm_bf16:ctc_lin": ("tensor", 2 * d * VOCAB * m, 1),
         "stac_log_softmax": ("hbm", m * VOCAB * 4 * 2, 1),
         # fused CTC head: the fp32 posteriors are written once (bf16 states in); its two GEMM passes are 2x the FLOPs

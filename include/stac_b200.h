@@ -136,6 +136,14 @@ int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float* bias, cons
                    int64_t k, uint16_t* vt_out, int64_t vt_cols, int64_t seq_len, int64_t t_pad,
                    void* stream);
 
+/* Position-wise feed-forward block of one encoder layer in ONE kernel (bf16 mode, d_model = 256):
+ *   x += W2 . GELU(W1 . h + b1) + b2      h bf16 [m, 256] (= LayerNorm2(x)), x fp32 [m, 256] in place,
+ *   w1 bf16 [d_ffn, 256], w2 bf16 [256, d_ffn], d_ffn a multiple of 128 (<= 4096).
+ * The hidden activation lives only in tensor / shared memory.  Other widths: STAC_ERR_UNSUPPORTED_SHAPE
+ * (callers fall back to two stac_gemm_bf16 calls). */
+int stac_ffn_fused_bf16(const uint16_t* h, const uint16_t* w1, const float* b1, const uint16_t* w2, const float* b2,
+                        float* x, int64_t m, int64_t d_model, int64_t d_ffn, void* stream);
+
 /* Valid key count per utterance, int32 [B], from the relative lengths the reference passes around
  * (wav_lens = len / Lmax, fp32) with the reference's own fp32 arithmetic:
  *   round_rule 0: encode()  keeps j <= floor(wav_len * T2)   -> floor(.) + 1   (TransformerMultiTask.py:289-294)

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "stac_gemm_f32": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_int64, c_int64, c_int64, _P]),
     "stac_gemm_bf16": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, c_int, c_int64, c_int64, c_int64,
                                _P, c_int64, c_int64, c_int64, _P]),
+    "stac_ffn_fused_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, _P]),
     "stac_kv_lengths": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
     "stac_mha_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P]),
     "stac_mha_bf16": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P]),

@@ -22,6 +22,7 @@ HOP = 160
 CNN_CH = 256
 F1, F2 = 40, 20
 PRECISIONS = ("fp32", "bf16")
+FUSED_FFN = True       # tests flip this to compare against the two-GEMM path
 
 # Optional launch tracing: bench.py sets TRACE to a list to get (kernel, label, start_event, end_event)
 # per launch; LAUNCHES counts kernel launches either way.
@@ -324,7 +325,9 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
     qkv = torch.empty(m, 3 * d, device=dev, dtype=act_dt)
     ctx = torch.empty(m, d, device=dev, dtype=act_dt)
     d_ffn = w.layers[0].w_1.shape[0] if w.layers else 4 * d
-    ff = torch.empty(m, d_ffn, device=dev, dtype=act_dt)
+    # S model in bf16 mode: the whole feed-forward block is one kernel and the hidden activation never reaches HBM
+    fused_ffn = prec == "bf16" and d == 256 and d_ffn % 128 == 0 and 128 <= d_ffn <= 4096 and FUSED_FFN
+    ff = None if fused_ffn else torch.empty(m, d_ffn, device=dev, dtype=act_dt)
     t_pad = (t2 + 7) // 8 * 8
     for L in w.layers:
         if prec == "fp32":
@@ -342,8 +345,12 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
             _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_f32=hbuf)
         else:
             _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_bf16=hbuf)
-        _gemm(hbuf, L.w_1, L.b_1, ff, prec, act=ACT_GELU_ERF, tag="ffn1")
-        _gemm(ff, L.w_2, L.b_2, x, prec, resid=x, tag="ffn2")
+        if fused_ffn:
+            _call("stac_ffn_fused_bf16", ptr(hbuf), ptr(L.w_1, torch.bfloat16), ptr(L.b_1), ptr(L.w_2, torch.bfloat16),
+                  ptr(L.b_2), ptr(x), m, d, d_ffn, stream())
+        else:
+            _gemm(hbuf, L.w_1, L.b_1, ff, prec, act=ACT_GELU_ERF, tag="ffn1")
+            _gemm(ff, L.w_2, L.b_2, x, prec, resid=x, tag="ffn2")
     enc = torch.empty(b, t2, d, device=dev, dtype=torch.float32)
     enc_bf16 = torch.empty(b, t2, d, device=dev, dtype=torch.bfloat16) if want_bf16_copy else None
     _layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=enc.view(m, d), out_bf16=None if enc_bf16 is None else enc_bf16.view(m, d))

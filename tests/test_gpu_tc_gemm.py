@@ -100,3 +100,29 @@ def test_fused_ctc_head(m, v, d):
     clear = (top2[:, 0] - top2[:, 1]) > 1e-4
     assert bool((ids.cpu().long()[clear] == logits.argmax(-1)[clear]).all())
     assert bool((logits.gather(1, ids.cpu().long()[:, None])[:, 0] >= top2[:, 0] - 1e-4).all())
+
+
+@pytest.mark.parametrize("m,dffn", [(128, 1024), (300, 1024), (1000, 1024), (77, 128), (20000, 1024), (513, 256), (129, 384)])
+def test_fused_ffn_block(m, dffn):
+    """stac_ffn_fused_bf16: x += W2 GELU(W1 h + b1) + b2 in one kernel against torch (exact-erf GELU) on the same
+    bf16-rounded operands, and against the two-GEMM path it replaces."""
+    g = torch.Generator().manual_seed(m + dffn)
+    h = torch.randn(m, 256, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(dffn, 256, generator=g) / 16).to(torch.bfloat16)
+    w2 = (torch.randn(256, dffn, generator=g) / dffn ** 0.5).to(torch.bfloat16)
+    b1, b2 = torch.randn(dffn, generator=g) * 0.3, torch.randn(256, generator=g) * 0.3
+    x0 = torch.randn(m, 256, generator=g)
+    hid = torch.nn.functional.gelu(h.float() @ w1.float().t() + b1).to(torch.bfloat16).float()
+    ref = x0 + hid @ w2.float().t() + b2
+    x = x0.cuda().clone()
+    guard = torch.full((4096,), 7.0, device="cuda")
+    h_d, w1_d, w2_d, b1_d, b2_d = h.cuda(), w1.cuda(), w2.cuda(), b1.cuda(), b2.cuda()
+    ops.check(ops.lib().stac_ffn_fused_bf16(ops.ptr(h_d), ops.ptr(w1_d), ops.ptr(b1_d), ops.ptr(w2_d), ops.ptr(b2_d),
+                                            ops.ptr(x), m, 256, dffn, ops.stream()))
+    torch.cuda.synchronize()
+    assert rel_l2(x, ref) < 2e-3, rel_l2(x, ref)
+    assert rel_max(x, ref) < 1e-2
+    assert float((guard - 7.0).abs().max()) == 0.0
+    # unsupported widths are refused, not mis-computed
+    assert ops.lib().stac_ffn_fused_bf16(ops.ptr(h_d), ops.ptr(w1_d), ops.ptr(b1_d), ops.ptr(w2_d), ops.ptr(b2_d),
+                                         ops.ptr(x), m, 512, dffn, ops.stream()) == -2
