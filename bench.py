@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gather", default="bf16", choices=["ids", "bf16", "fp32"],
                     help="what travels to rank 0 besides enc_out when N > 1: greedy ids only, bf16 or fp32 posteriors")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="SMs left free for the NCCL transfer kernels when N > 1 (default 0: measured no gain at N=8, "
+                         "the gather is bound by NCCL's per-peer point-to-point bandwidth, not by SM contention)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances in the CPU-baseline sample")
     ap.add_argument("--trace-out", default=None, help="write the per-kernel timing table (json) here")
@@ -251,6 +254,10 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if world > 1:
+        # the gather's NCCL send/recv kernels hold whole SMs for the length of the transfer: persistent kernels must not
+        # count on them (a CTA that waits for a held SM costs a full kernel duration)
+        ops.check(ops.lib().stac_set_reserved_sms(max(0, args.reserve_sms)), "stac_set_reserved_sms")
     hp = sb.HParams.for_size(args.size)
     mods = sb.build_modules(hp, precision=args.precision, device=dev)
     wavs_cpu, wl_cpu = synth.fast_synth_batch(args.batch, args.seconds, seed=1234 + rank)

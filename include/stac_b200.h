@@ -43,6 +43,9 @@ extern "C" {
 #define STAC_DT_BF16 1
 
 int stac_version(void);
+/* Persistent kernels launch at most (SM count - n) CTAs from now on (default 0).  Use when a communication kernel
+ * (NCCL send/recv of the multi-GPU gather) runs beside the path and holds SMs. */
+int stac_set_reserved_sms(int n);
 const char* stac_error_string(int code);
 
 /* ---------------------------------------------------------------------------

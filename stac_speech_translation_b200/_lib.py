@@ -22,6 +22,7 @@ _P = c_void_p
 _SIGNATURES = {
     "stac_version": (c_int, []),
     "stac_error_string": (c_char_p, [c_int]),
+    "stac_set_reserved_sms": (c_int, [c_int]),
     "stac_fbank_tables_floats": (c_int, []),
     "stac_fbank_logmel": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "stac_fbank_topdb_norm": (c_int, [_P, _P, c_int, c_float, _P, _P, c_int64, c_int64, c_int64, _P, _P]),

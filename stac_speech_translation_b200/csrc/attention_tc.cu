@@ -460,16 +460,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-int num_sms_attn() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms_attn() { return stac_grid_limit(); }
 
 template <bool kVT>
 int launch_mha(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tv, const int32_t* kv_len,

@@ -16,6 +16,8 @@
 #define STAC_REQUIRE(cond) \
   do { if (!(cond)) return STAC_ERR_INVALID_ARGUMENT; } while (0)
 
+int stac_grid_limit();   // api.cu: SM count minus the SMs reserved for a concurrent communication kernel
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -381,16 +381,7 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
   if (warp == 11) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-int num_sms_conv0() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms_conv0() { return stac_grid_limit(); }
 
 }  // namespace
 

@@ -311,16 +311,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
   if (warp == 17) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-int num_sms_ffn() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms_ffn() { return stac_grid_limit(); }
 
 }  // namespace
 

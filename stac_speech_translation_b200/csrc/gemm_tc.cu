@@ -502,16 +502,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms() { return stac_grid_limit(); }
 
 template <bool kConv>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const EpiParams& ep, int m_tiles,
