@@ -10,11 +10,11 @@ from .convolution import ConvolutionFrontEnd  # noqa: F401
 from .transformer import TransformerMultiTask, EncoderWrapper  # noqa: F401
 from .linear import Linear, LogSoftmax  # noqa: F401
 from .pipeline import (  # noqa: F401
-    HParams, MODEL_SIZES, build_modules, compute_forward, EncoderPipeline, ctc_greedy_collapse,
+    HParams, MODEL_SIZES, build_modules, compute_forward, EncoderPipeline, GraphedPipeline, ctc_greedy_collapse,
 )
 
 __all__ = [
     "Fbank", "InputNormalization", "ConvolutionFrontEnd", "TransformerMultiTask", "EncoderWrapper",
     "Linear", "LogSoftmax", "HParams", "MODEL_SIZES", "build_modules", "compute_forward",
-    "EncoderPipeline", "ctc_greedy_collapse", "StacB200Error",
+    "EncoderPipeline", "GraphedPipeline", "ctc_greedy_collapse", "StacB200Error",
 ]

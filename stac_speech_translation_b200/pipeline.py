@@ -148,6 +148,36 @@ class EncoderPipeline:
         return res
 
 
+class GraphedPipeline:
+    """One CUDA graph of the whole path for a fixed batch shape: PCM buffer -> (enc_out, p_ctc, greedy ids).
+
+    Every kernel of the path takes plain device pointers and a stream, so the ~80 launches of a step capture into
+    one graph; a replay costs the host a few microseconds instead of a few milliseconds of Python/ctypes launch
+    work, which is what the end-to-end rate depends on when the host is slow or shared.  The input lives in
+    ``self.wavs`` (copy new audio there, on any stream ordered before the replay); the results are the same
+    static tensors on every replay."""
+
+    def __init__(self, pipe: "EncoderPipeline", wavs: torch.Tensor, wav_lens: Optional[torch.Tensor], warmup: int = 2,
+                 **call_kwargs):
+        self.wavs = wavs
+        self.wav_lens = wav_lens
+        side = torch.cuda.Stream(device=wavs.device)
+        side.wait_stream(torch.cuda.current_stream(wavs.device))
+        with torch.cuda.stream(side):                 # first calls set kernel attributes / pack weights: not capturable
+            for _ in range(max(1, warmup)):
+                pipe(self.wavs, self.wav_lens, **call_kwargs)
+        torch.cuda.current_stream(wavs.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = pipe(self.wavs, self.wav_lens, **call_kwargs)
+
+    def __call__(self, wavs: Optional[torch.Tensor] = None):
+        if wavs is not None and wavs.data_ptr() != self.wavs.data_ptr():
+            self.wavs.copy_(wavs, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def ctc_greedy_collapse(ids: torch.Tensor, lengths: Sequence[int], blank: int = 0) -> List[List[int]]:
     """CTC-greedy token sequences (merge repeats, drop blanks) over the valid frames of each utterance."""
     ids = ids.cpu()

@@ -124,3 +124,22 @@ def test_ctc_greedy_agreement_bf16_vs_oracle():
                "median_top2_margin": float(margin[valid].median())},
               open(os.path.join(OUT, "ctc_greedy_agreement.json"), "w"), indent=1)
     assert frame_agree > 0.9
+
+
+def test_graphed_pipeline_replays_the_same_results():
+    """sb.GraphedPipeline (one CUDA graph of the whole path) against the eager pipeline, on new audio per replay."""
+    omods = oracle_modules("S", num_encoder_layers=2)
+    mods = product_from_oracle(omods, "bf16")
+    pipe = sb.EncoderPipeline(mods)
+    wavs, wl = synth.synth_batch([2.0, 1.5, 1.1], seed=8)
+    wavs2, _ = synth.synth_batch([2.0, 1.5, 1.1], seed=9)
+    buf = wavs.cuda().clone()
+    graphed = sb.GraphedPipeline(pipe, buf, wl.cuda())
+    for w in (wavs, wavs2, wavs):
+        got = graphed(w.cuda())
+        torch.cuda.synchronize()
+        want = pipe(w.cuda(), wl.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(got["greedy"], want["greedy"])
+        assert torch.equal(got["enc_out"], want["enc_out"])
+        assert torch.equal(got["p_ctc"], want["p_ctc"])
