@@ -14,6 +14,8 @@
 //       warps 8-15  softmax group 1 (query tile 1)
 //       warps 16-17 MMA issuers (one thread per softmax group)
 //       warp  18    TMA producer (Q tiles double-buffered per work item, K / V tiles in a 5-stage ring)
+//       warp  19    output: one TMA store per (item, group) of the normalised O tile, staged in the item's dead Q
+//                   buffer (row-per-thread global stores cost ~2800 cycles per item on the softmax critical path)
 //   * work item = (utterance, head, block of 256 queries); the two query tiles share every K / V tile;
 //   * key tiles are 64 wide and every group owns TWO score buffers in TMEM: S(j+1) = Q K_{j+1}^T is issued as soon
 //     as the softmax warps have pulled S(j-1) into registers, i.e. it is already there when they finish tile j, and
@@ -32,7 +34,7 @@ using namespace tc;
 
 constexpr int kHd = 64, kQTile = 128, kKTile = 64;
 constexpr int kKvStages = 5;
-constexpr int kThreads = 608;
+constexpr int kThreads = 640;
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int kOffQ = 0;                         // [2 bufs][2 groups] x 16 KB
 constexpr int kOffP = 65536;                     // [2 groups][2 bufs] x 16 KB (128 rows x 64 keys bf16, K-major)
@@ -40,7 +42,7 @@ constexpr int kOffKV = 131072;                   // [stages] x (K 8 KB + V 8 KB)
 constexpr int kOffX = kOffKV + kKvStages * 16384;      // float [2 groups][2 bufs][2 halves][128 rows]: row-max exchange
 constexpr int kOffLen = kOffX + 2 * 2 * 2 * 128 * 4;   // int [kLenCache]
 constexpr int kOffBar = kOffLen + 128 * 4;
-constexpr int kNumBars = 8 + 2 * kKvStages + 18;
+constexpr int kNumBars = 8 + 2 * kKvStages + 20;
 #ifdef MHA_TRACE
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024 + 5 * 64 * 8 * 4;
 #else
@@ -117,8 +119,8 @@ __device__ __forceinline__ Item decode_item(int item, int ordinal, const int* le
 template <bool kVT>
 __global__ void __launch_bounds__(kThreads, 1)
 mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                const __grid_constant__ CUtensorMap tmap_vt, const int* __restrict__ kv_len, int seq_len,
-                int d_model, int n_head, int n_qblk, int n_items, __nv_bfloat16* __restrict__ ctx) {
+                const __grid_constant__ CUtensorMap tmap_vt, const __grid_constant__ CUtensorMap tmap_ctx,
+                const int* __restrict__ kv_len, int seq_len, int d_model, int n_head, int n_qblk, int n_items) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* sptr = smem_raw + (sbase - smem_u32(smem_raw));
@@ -135,6 +137,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto p_full = [&](int w, int i) { return gb + 8u * (w * 9 + 4 + i); };
   auto p_free = [&](int w, int i) { return gb + 8u * (w * 9 + 6 + i); };
   auto o_free = [&](int w) { return gb + 8u * (w * 9 + 8); };
+  auto o_staged = [&](int w) { return gb + 8u * (18 + w); };     // the group's O tile is staged in smem for the store warp
   const uint32_t tmem_slot = bars + 8u * kNumBars;
 #ifdef MHA_TRACE
   unsigned int* trace_s = reinterpret_cast<unsigned int*>(sptr + kOffBar + kNumBars * 8 + 16);
@@ -151,13 +154,16 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_kv);
     if (kVT) prefetch_tmap(&tmap_vt);
-    for (int i = 0; i < 4; ++i) { mbar_init(q_full(i >> 1, i & 1), 1); mbar_init(q_empty(i >> 1, i & 1), 1); }
+    prefetch_tmap(&tmap_ctx);
+    // q_empty: the last S of the item has retired (commit) AND the item's output tile, staged in the same buffer, has
+    // been read by its TMA store (store warp)
+    for (int i = 0; i < 4; ++i) { mbar_init(q_full(i >> 1, i & 1), 1); mbar_init(q_empty(i >> 1, i & 1), 2); }
     for (int s = 0; s < kKvStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }
     for (int w = 0; w < 2; ++w) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(s_full(w, i), 1); mbar_init(s_free(w, i), 8); mbar_init(p_full(w, i), 8); mbar_init(p_free(w, i), 1);
       }
-      mbar_init(o_free(w), 8);
+      mbar_init(o_free(w), 8); mbar_init(o_staged(w), 8);
     }
     fence_barrier_init();
   }
@@ -200,6 +206,29 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     __syncwarp();
+  } else if (warp == 19) {
+    // ============================ output store warp ============================
+    uint32_t cnt[2] = {0, 0};
+    int n_done = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+      const Item it = decode_item(item, n_done, len_cache, n_qblk, n_head, seq_len, kv_len);
+      const int buf = n_done & 1;
+      for (int w = 0; w < 2; ++w) {
+        if (w == 1 && !it.active1) continue;
+        mbar_wait(o_staged(w), cnt[w]++ & 1);
+        if (elect_one()) {
+          // rows past the end of the utterance are clipped by the 3-D map
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_ctx)), "r"(sbase + kOffQ + (buf * 2 + w) * 16384),
+                         "r"(it.h * kHd), "r"(it.q0 + w * kQTile), "r"(it.b) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(q_empty(buf, w));               // the Q buffer may be refilled
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp >= 16) {
     // ============================ MMA issuers: warp 16 -> group 0, warp 17 -> group 1 ============================
     // Per group the order is fixed: S(0) S(1) | P.V(0) S(2) | P.V(1) S(3) | ...  (the scores run two tiles ahead of
@@ -327,6 +356,14 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // O accumulator in TMEM is touched by the CUDA cores only on those rare steps and once at the end.
       constexpr float kRaise = 40.0f;
       float m_ref = -INFINITY, l_run = 0.f;
+#ifndef MHA_STAGGER_NS
+#define MHA_STAGGER_NS 350
+#endif
+#if MHA_STAGGER_NS > 0
+      // the two groups share every sub-partition's exp unit: start group 1 half a tile late so that its exp phase
+      // falls into group 0's max / barrier phase instead of on top of its exp phase
+      if (w == 1) __nanosleep(MHA_STAGGER_NS);
+#endif
       for (int j = 0; j < it.n_kt; ++j, ++g) {
         const int i = g & 1;
         const uint32_t u = (uint32_t)(g >> 1) & 1;
@@ -427,27 +464,31 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float inv = 1.0f / (l_run + xrow[(ch ^ 1) * 128]);
       named_bar_sync(pair_bar, 64);                  // the exchange slot is reused by the next item's first steps
       mbar_wait(p_free(w, (g - 1) & 1), (uint32_t)((g - 1) >> 1) & 1);   // the last P.V of the item has retired
+      if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 6, g - 1);
       tc_fence_after();
-      const int q = it.q0 + w * kQTile + r;
-      __nv_bfloat16* dst = ctx + ((int64_t)it.b * seq_len + q) * d_model + it.h * kHd + ch * 32;
       {
         uint32_t o[32];
         tmem_ld32(tmem_o, o);
         tmem_ld_wait();
-        if (q < seq_len) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free(w));       // the next item's first P.V may overwrite O_w
+        // stage my 32 columns of row r in the item's Q buffer (dead since the last S), 128-byte swizzled rows
+        const uint32_t srow = sbase + kOffQ + ((ordinal & 1) * 2 + w) * 16384 + r * 128;
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            *reinterpret_cast<uint4*>(dst + c) = make_uint4(
-                pack_bf16x2(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv),
-                pack_bf16x2(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv),
-                pack_bf16x2(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv),
-                pack_bf16x2(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv));
-          }
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t a0 = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+          const uint32_t a1 = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+          const uint32_t a2 = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+          const uint32_t a3 = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(srow + (((ch * 4 + c) ^ sw) << 4)), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_staged(w));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free(w));         // the next item's first P.V may overwrite O_w
+      if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 7, g - 1);
     }
   }
 
@@ -463,8 +504,8 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 int num_sms_attn() { return stac_grid_limit(); }
 
 template <bool kVT>
-int launch_mha(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tv, const int32_t* kv_len,
-               int seq_len, int d_model, int n_head, int n_qblk, int n_items, uint16_t* ctx, cudaStream_t st) {
+int launch_mha(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& tv, const CUtensorMap& tctx,
+               const int32_t* kv_len, int seq_len, int d_model, int n_head, int n_qblk, int n_items, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(mha_bf16_kernel<kVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -472,8 +513,8 @@ int launch_mha(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap&
     attr = true;
   }
   const int grid = std::min(n_items, num_sms_attn());
-  mha_bf16_kernel<kVT><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tv, kv_len, seq_len, d_model, n_head, n_qblk,
-                                                          n_items, reinterpret_cast<__nv_bfloat16*>(ctx));
+  mha_bf16_kernel<kVT><<<grid, kThreads, kSmemBytes, st>>>(tq, tkv, tv, tctx, kv_len, seq_len, d_model, n_head, n_qblk,
+                                                          n_items);
   STAC_LAUNCH_CHECK();
 }
 
@@ -508,6 +549,15 @@ extern "C" int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int
     int r = encode_map(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 2, dims, str, box);
     if (r != STAC_OK) return r;
   }
+  CUtensorMap tctx;
+  {
+    // ctx [B][T][d_model]: a tile that runs past the end of its utterance is clipped in the T dimension
+    const uint64_t cdims[3] = {(uint64_t)d_model, (uint64_t)seq_len, (uint64_t)batch};
+    const uint64_t cstr[2] = {(uint64_t)d_model * 2, (uint64_t)seq_len * d_model * 2};
+    const uint32_t cbox[3] = {kHd, kQTile, 1};
+    int r = encode_map(&tctx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ctx, 3, cdims, cstr, cbox);
+    if (r != STAC_OK) return r;
+  }
   tv = tkv;
   if (v_t) {
     // V^T [B*H][64][t_pad], innermost = keys
@@ -516,9 +566,9 @@ extern "C" int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int
     const uint32_t vbox[3] = {kKTile, kHd, 1};
     int r = encode_map(&tv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, v_t, 3, vdims, vstr, vbox);
     if (r != STAC_OK) return r;
-    return launch_mha<true>(tq, tkv, tv, kv_len, (int)seq_len, (int)d_model, (int)n_head, (int)n_qblk, (int)n_items,
-                            ctx, as_stream(stream));
+    return launch_mha<true>(tq, tkv, tv, tctx, kv_len, (int)seq_len, (int)d_model, (int)n_head, (int)n_qblk,
+                            (int)n_items, as_stream(stream));
   }
-  return launch_mha<false>(tq, tkv, tv, kv_len, (int)seq_len, (int)d_model, (int)n_head, (int)n_qblk, (int)n_items,
-                           ctx, as_stream(stream));
+  return launch_mha<false>(tq, tkv, tv, tctx, kv_len, (int)seq_len, (int)d_model, (int)n_head, (int)n_qblk,
+                           (int)n_items, as_stream(stream));
 }

@@ -21,9 +21,11 @@ tr = (buf.cpu().long() & 0xffffffff).view(5, 64, 8)
 t0 = int(tr[tr > 0].min())
 names = {0: "producer: kv_empty passed", 1: "mma0: 0 S-start 1 kv_full 2 s_free 3 S-issued 4 PV-start 5 p_full 6 PV-issued",
          3: "softmax0: 0 start 1 s_full 2 ld+s_free 3 p_free 4 exp/store done 5 p_full arrived"}
-for role in (0, 1, 3):
+names[4] = 'softmax1 (same events)'
+names[2] = 'mma1 (same events)'
+for role in (1, 3):
     print(names[role])
-    for step in range(14, 28):
+    for step in range(20, 28):
         row = tr[role, step]
         base = int(tr[1, 14, 0])
-        print(f"{step:3d} " + " ".join(f"{(int(x) - base) & 0xffffffff:7d}" for x in row[:7]))
+        print(f"{step:3d} " + " ".join(f"{(int(x) - base) & 0xffffffff:7d}" for x in row[:8]))
