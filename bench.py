@@ -110,6 +110,7 @@ def work_table(size_cfg, batch, n_samples, kv_len_sum_sq_like):
     m = batch * t2
     w = {
         "stac_fbank_logmel": ("hbm", batch * (4 * n_samples + 4 * 80 * t), 1),
+        "stac_fbank_logmel_tc": ("hbm", batch * (4 * n_samples + 4 * 80 * t), 1),
         "stac_fbank_topdb_norm": ("hbm", batch * 2 * 4 * 80 * t, 1),
         "stac_conv0_ln_lrelu": ("hbm", batch * (4 * 80 * t + 2 * 40 * 256 * t1), 1),
         "stac_conv1_bf16": ("tensor", 2 * 9 * 256 * 256 * 20 * m, 1),

@@ -64,6 +64,17 @@ int stac_fbank_logmel(const float* pcm, int64_t batch, int64_t n_samples, int64_
                       const float* tables, float* logmel_db /*[B,T,80]*/,
                       uint32_t* utt_max_ordered /*[B]*/, void* stream);
 
+/* a2 on tensor cores (bf16 mode): the windowed 400-point DFT of 128 frames per tile is a tcgen05 GEMM against fp16
+ * cos / sin matrices after folding the frame on its symmetry (K = 201 + 199 instead of 400 + 400), fused with power, mel,
+ * dB and the per-utterance maximum.  Same outputs as stac_fbank_logmel (log-mel within 4e-4 relative).
+ *   tables:   stac_fbank_tc_tables_floats() floats: window[400] | per-bin mel weights [208][2]
+ *   twiddles: stac_fbank_tc_twiddle_halfs() fp16: [cos | sin][208 bins][256 columns], see ops.build_fbank_tc_tables */
+int stac_fbank_tc_tables_floats(void);
+int stac_fbank_tc_twiddle_halfs(void);
+int stac_fbank_logmel_tc(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_row_stride,
+                         const float* tables, const uint16_t* twiddles, float* logmel_db /*[B,T,80]*/,
+                         uint32_t* utt_max_ordered /*[B]*/, void* stream);
+
 /* top-dB clamp (+ optional global mean/std normalisation, a3) in one elementwise pass:
  *   y = max(x, max_b - top_db);  if (mean) y = (y - mean[m]) / std[m]
  * per_utterance != 0: max_b is utterance b's maximum, else the maximum over the batch.

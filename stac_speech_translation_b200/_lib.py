@@ -25,6 +25,9 @@ _SIGNATURES = {
     "stac_set_reserved_sms": (c_int, [c_int]),
     "stac_fbank_tables_floats": (c_int, []),
     "stac_fbank_logmel": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
+    "stac_fbank_tc_tables_floats": (c_int, []),
+    "stac_fbank_tc_twiddle_halfs": (c_int, []),
+    "stac_fbank_logmel_tc": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "stac_fbank_topdb_norm": (c_int, [_P, _P, c_int, c_float, _P, _P, c_int64, c_int64, c_int64, _P, _P]),
     "stac_input_norm": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "stac_conv0_padded_elems": (c_int64, [c_int64, c_int64]),

@@ -44,6 +44,12 @@ class Fbank(nn.Module):
             self._tables = ops.build_fbank_tables(device)
         return self._tables
 
+    def tc_tables(self, device):
+        """Constants of the tensor-core STFT kernel (used by the fused bf16 pipeline)."""
+        if getattr(self, "_tc_tables", None) is None or self._tc_tables[0].device != device:
+            self._tc_tables = ops.build_fbank_tc_tables(device)
+        return self._tc_tables
+
     @torch.no_grad()
     def forward(self, wav):
         return ops.fbank(wav.float(), self.tables(wav.device), self.top_db, self.top_db_per_utterance)

@@ -75,6 +75,21 @@ def frames_of(n_samples: int):
 # --------------------------------------------------------------------------
 # a2 / a3
 # --------------------------------------------------------------------------
+def mel_filter_matrix() -> torch.Tensor:
+    """[80, 201] triangular mel filterbank with the same fp32 torch expressions SpeechBrain's Filterbank uses
+    (filters symmetric in Hz with the LEFT band as half-width; 201 linear bins 0..8 kHz)."""
+    def to_mel(hz):
+        return 2595 * math.log10(1 + hz / 700)
+
+    mel = torch.linspace(to_mel(0), to_mel(8000.0), N_MELS + 2)
+    hz = 700 * (10 ** (mel / 2595) - 1)
+    band = (hz[1:] - hz[:-1])[:-1]
+    f_central = hz[1:-1]
+    all_freqs = torch.linspace(0, 16000 // 2, N_FFT // 2 + 1)
+    slope = (all_freqs[None, :] - f_central[:, None]) / band[:, None]          # [80, 201]
+    return torch.max(torch.zeros(1), torch.min(slope + 1.0, -slope + 1.0))       # [80, 201]
+
+
 def build_fbank_tables(device) -> torch.Tensor:
     """Constant block of the Fbank kernel (layout documented in include/stac_b200.h).
 
@@ -89,16 +104,7 @@ def build_fbank_tables(device) -> torch.Tensor:
     k = torch.arange(201, dtype=torch.float64)
     tw400 = torch.stack([torch.cos(2 * math.pi * k / 400), -torch.sin(2 * math.pi * k / 400)], -1)
 
-    def to_mel(hz):
-        return 2595 * math.log10(1 + hz / 700)
-
-    mel = torch.linspace(to_mel(0), to_mel(8000.0), N_MELS + 2)
-    hz = 700 * (10 ** (mel / 2595) - 1)
-    band = (hz[1:] - hz[:-1])[:-1]
-    f_central = hz[1:-1]
-    all_freqs = torch.linspace(0, 16000 // 2, N_FFT // 2 + 1)
-    slope = (all_freqs[None, :] - f_central[:, None]) / band[:, None]          # [80, 201]
-    fb = torch.max(torch.zeros(1), torch.min(slope + 1.0, -slope + 1.0))        # [80, 201]
+    fb = mel_filter_matrix()
     start = torch.zeros(N_MELS)
     count = torch.zeros(N_MELS)
     weights = torch.zeros(N_MELS, 16)
@@ -113,6 +119,60 @@ def build_fbank_tables(device) -> torch.Tensor:
                      tw400.float().flatten(), start, count, weights.flatten()])
     assert tab.numel() == lib().stac_fbank_tables_floats()
     return tab.to(device=device, dtype=torch.float32).contiguous()
+
+
+_FFT_TABLES = {}
+
+
+def build_fbank_tc_tables(device):
+    """Constants of the tensor-core Fbank kernel (layouts in include/stac_b200.h): (tables fp32, twiddles fp16).
+    Window and mel weights come from the same fp32 torch expressions SpeechBrain uses; the per-bin mel layout must
+    have the sparsity structure baked into csrc/fbank_mel_structure.h (checked here); twiddles are computed in
+    float64 and rounded to fp16 once."""
+    window = torch.hamming_window(N_FFT)
+    fb = mel_filter_matrix()                                   # [80, 201]
+    wbin = torch.zeros(208, 2)
+    for k in range(201):
+        nz = torch.nonzero(fb[:, k] > 0).flatten().tolist()
+        if len(nz) > 2 or (len(nz) == 2 and nz[1] != nz[0] + 1):
+            raise ValueError("mel filterbank structure differs from csrc/fbank_mel_structure.h")
+        for j, m in enumerate(nz):
+            wbin[k, j] = fb[m, k]
+    tab = torch.cat([window.float(), wbin.flatten()])
+    assert tab.numel() == lib().stac_fbank_tc_tables_floats()
+    kk = torch.arange(201, dtype=torch.float64)[:, None]
+    tw = torch.zeros(2, 208, 256, dtype=torch.float64)
+    n_cos = torch.arange(201, dtype=torch.float64)[None, :]
+    tw[0, :201, :201] = torch.cos(2 * math.pi * kk * n_cos / 400)
+    n_sin = torch.arange(1, 200, dtype=torch.float64)[None, :]
+    tw[1, :201, :199] = -torch.sin(2 * math.pi * kk * n_sin / 400)
+    tw = tw.to(torch.float16).reshape(2 * 208, 256).contiguous()
+    assert tw.numel() == lib().stac_fbank_tc_twiddle_halfs()
+    return tab.to(device=device, dtype=torch.float32).contiguous(), tw.to(device)
+
+
+def fbank_tc(wavs: torch.Tensor, tc_tables, top_db: float = 80.0, per_utterance: bool = True,
+             mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a2 (+a3) with the STFT on tensor cores (bf16 mode): [B, L] fp32 PCM -> [B, T, 80] fp32 features."""
+    if wavs.dim() != 2:
+        raise _lib.StacB200Error("Fbank expects [batch, samples] waveforms")
+    wavs = wavs.contiguous()
+    tab, tw = tc_tables
+    b, n = wavs.shape
+    if n % 4 != 0 or wavs.data_ptr() % 16 != 0:
+        # the tensor-core kernel moves PCM tiles with 16-byte bulk copies; odd lengths take the exact FFT kernel
+        key = str(wavs.device)
+        if key not in _FFT_TABLES:
+            _FFT_TABLES[key] = build_fbank_tables(wavs.device)
+        return fbank(wavs, _FFT_TABLES[key], top_db, per_utterance, mean, std)
+    t = 1 + n // HOP
+    db = torch.empty(b, t, N_MELS, device=wavs.device, dtype=torch.float32)
+    umax = torch.empty(b, device=wavs.device, dtype=torch.int32)      # zeroed by the call (stream-ordered memset)
+    _call("stac_fbank_logmel_tc", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tab), ptr(tw, torch.float16),
+          ptr(db), ptr(umax), stream())
+    _call("stac_fbank_topdb_norm", ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),
+          b, t, N_MELS, ptr(db), stream())
+    return db
 
 
 def fbank(wavs: torch.Tensor, tables: torch.Tensor, top_db: float = 80.0, per_utterance: bool = True,

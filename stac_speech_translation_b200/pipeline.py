@@ -121,8 +121,11 @@ class EncoderPipeline:
         dev = wavs.device
         fb, norm = m["compute_features"], m["normalize"]
         mean, std = norm.device_stats(dev, ops.N_MELS)
-        feats = ops.fbank(wavs, fb.tables(dev), fb.top_db, fb.top_db_per_utterance, mean, std)
         bf16 = self.precision == "bf16"
+        if bf16:      # STFT as a tensor-core GEMM (fp16 operands, fp32 accumulation); fp32 mode keeps the exact FFT kernel
+            feats = ops.fbank_tc(wavs, fb.tc_tables(dev), fb.top_db, fb.top_db_per_utterance, mean, std)
+        else:
+            feats = ops.fbank(wavs, fb.tables(dev), fb.top_db, fb.top_db_per_utterance, mean, std)
         src = ops.conv_frontend(feats, m["CNN"].packed(), torch.bfloat16 if bf16 else torch.float32)
         if stop_after == "cnn":
             return {"cnn": src}
