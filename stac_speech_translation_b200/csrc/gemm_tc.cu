@@ -584,18 +584,20 @@ ctc_reduce_kernel(const float* __restrict__ stats, int64_t plane, int n_groups, 
                   float* __restrict__ row_max, int* __restrict__ argmax) {
   const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (row >= m) return;
-  float mx = -INFINITY, sum = 0.f;
-  for (int g = 0; g < n_groups; ++g) {
-    const float gm = stats[(int64_t)g * m + row];
-    const float gs = stats[plane + (int64_t)g * m + row];
-    if (gm > mx) {
-      sum = sum * expf(mx - gm) + gs;
-      mx = gm;
-    } else {
-      sum += gs * expf(gm - mx);
-    }
+  // two passes of independent, coalesced loads (a single online pass is one long dependent chain per row)
+  const float* pm = stats + row;
+  float mx = -INFINITY;
+#pragma unroll 8
+  for (int g = 0; g < n_groups; ++g) mx = fmaxf(mx, __ldg(pm + (int64_t)g * m));
+  float s0 = 0.f, s1 = 0.f;
+  int g = 0;
+#pragma unroll 4
+  for (; g + 1 < n_groups; g += 2) {
+    s0 = fmaf(__ldg(pm + plane + (int64_t)g * m), __expf(__ldg(pm + (int64_t)g * m) - mx), s0);
+    s1 = fmaf(__ldg(pm + plane + (int64_t)(g + 1) * m), __expf(__ldg(pm + (int64_t)(g + 1) * m) - mx), s1);
   }
-  lse[row] = mx + logf(sum);
+  if (g < n_groups) s0 = fmaf(__ldg(pm + plane + (int64_t)g * m), __expf(__ldg(pm + (int64_t)g * m) - mx), s0);
+  lse[row] = mx + logf(s0 + s1);
   row_max[row] = mx;
   if (argmax) argmax[row] = 0x7fffffff;
 }
