@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gather", default="bf16", choices=["ids", "bf16", "fp32"],
                     help="what travels to rank 0 besides enc_out when N > 1: greedy ids only, bf16 or fp32 posteriors")
+    ap.add_argument("--gather-transport", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: rank 0 pulls results over peer memory with the copy engines (default), or NCCL send/recv")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="SMs left free for the NCCL transfer kernels when N > 1 (default 0: measured no gain at N=8, "
                          "the gather is bound by NCCL's per-peer point-to-point bandwidth, not by SM contention)")
@@ -140,7 +142,10 @@ def workload_config(args, t2, world):
             "l2": "per-step working set (~6 GB of activations) >> 126 MB L2, no explicit flush",
             "multi_gpu": ("whole batches per rank; enc_out + greedy ids"
                           + ("" if args.gather == "ids" else f" + {args.gather} posteriors")
-                          + " gathered to rank 0 (NCCL) inside the timed region") if world > 1 else "single GPU"}
+                          + (" pulled by rank 0 over NVLink peer memory (copy engines; torch.distributed gloo control "
+                             "messages, NCCL barrier)" if getattr(args, "gather_transport", "peer") == "peer"
+                             else " sent to rank 0 with NCCL point-to-point")
+                          + " inside the timed region") if world > 1 else "single GPU"}
 
 
 def run_reference(args, rank, world):
@@ -266,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
     calib = wavs_cpu[: min(8, args.batch), : 16000 * 4].to(dev)
     mods["normalize"].calibrate(mods["compute_features"](calib), torch.ones(calib.shape[0], device=dev))
     # non-root ranks produce the posteriors directly in the dtype that travels to rank 0
-    ship_bf16 = world > 1 and args.gather == "bf16" and args.precision == "bf16"
+    ship_bf16 = world > 1 and args.gather == "bf16" and args.precision == "bf16"   # wire dtype of the posteriors
     pipe = sb.EncoderPipeline(mods, posterior_dtype=torch.bfloat16 if (ship_bf16 and rank != 0) else torch.float32)
     pinned = wavs_cpu.pin_memory()
     wavs = pinned.to(dev, non_blocking=True)
@@ -275,30 +280,40 @@ def run_ours(args, rank, world, local_rank):
     audio_s = args.batch * n_samples / 16000.0
     t2 = ops.frames_of(n_samples)[2]
 
-    gather_bufs = None
+    # ---- multi-GPU: results of every rank to rank 0 ----
+    gather_bufs, peer = None, None
     if world > 1:
         d = hp.d_model
-        if rank == 0:
+        pdt = torch.bfloat16 if (args.gather == "bf16" and args.precision == "bf16") else torch.float32
+        if args.gather_transport == "peer":
+            from stac_speech_translation_b200.distributed import PeerGather
+            specs = {"enc_out": ((args.batch, t2, d), torch.float32), "greedy": ((args.batch, t2), torch.int32)}
+            if args.gather != "ids":
+                specs["p_ctc"] = ((args.batch, t2, VOCAB), pdt)
+            peer = PeerGather(specs, dev)
+        elif rank == 0:
             gather_bufs = {"enc": [torch.empty(args.batch, t2, d, device=dev) for _ in range(world)],
                            "ids": [torch.empty(args.batch, t2, device=dev, dtype=torch.int32) for _ in range(world)]}
             if args.gather != "ids":
-                pdt = torch.bfloat16 if args.gather == "bf16" else torch.float32
                 gather_bufs["p"] = [torch.empty(args.batch, t2, VOCAB, device=dev, dtype=pdt) for _ in range(world)]
 
-    pending = []          # gathers in flight: (works, tensors kept alive); at most one step behind the compute
+    pending = []          # NCCL transport: gathers in flight (works, tensors kept alive); at most one step behind
+    gstep = [0]           # steps issued so far (selects the result slot of the peer transport)
 
     def drain(keep=0):
+        if peer is not None:
+            if keep == 0:
+                peer.finish()
+            return
         while len(pending) > keep:
             works, _ = pending.pop(0)
             for w in works:
                 w.wait()
 
-    def gather(res):
+    def gather_nccl(res):
         """enc_out, greedy ids (and posteriors) of this step to rank 0 over NCCL point-to-point, asynchronously:
         the transfer of step i overlaps the compute of step i+1 (the references keep the buffers alive); rank 0's
         own results stay where they are."""
-        if world == 1:
-            return
         keys = ["enc", "ids"] + ([] if args.gather == "ids" else ["p"])
         if rank == 0:
             ops_ = [dist.P2POp(dist.irecv, gather_bufs[k][r], r) for r in range(1, world) for k in keys]
@@ -318,9 +333,21 @@ def run_ours(args, rank, world, local_rank):
         pending.append((dist.batch_isend_irecv(ops_), keep))
         drain(keep=1)
 
-    def step(x):
-        res = pipe(x, wl)
-        gather(res)
+    def step(x, graphs=None):
+        """One step of this rank: the path over one batch + shipping its results to rank 0.  `graphs`: per-slot CUDA
+        graphs of the path (the end-to-end loop); eager launches otherwise."""
+        i = gstep[0]
+        gstep[0] += 1
+        if peer is not None and rank != 0:
+            peer.begin_write(i)               # rank 0 has pulled the step that used this slot last
+            res = graphs[i % 2]() if graphs else pipe(x, wl, outputs=peer.slot(i))
+            peer.end_write(i)
+            return res
+        res = graphs[i % 2]() if graphs else pipe(x, wl)
+        if peer is not None:
+            peer.collect(i)                   # copy-engine pull of every peer's step i, on a side stream
+        elif world > 1:
+            gather_nccl(res)
         return res
 
     def barrier():
@@ -379,7 +406,9 @@ def run_ours(args, rank, world, local_rank):
     dev_in = [torch.empty_like(wavs) for _ in range(2)]
     for d_ in dev_in:
         d_.copy_(wavs)
-    graphed = [sb.GraphedPipeline(pipe, dev_in[s], wl) for s in range(2)]
+    graphed = [sb.GraphedPipeline(pipe, dev_in[s], wl,
+                                  **({"outputs": peer.slot(s)} if (peer is not None and rank != 0) else {}))
+               for s in range(2)]
     ids_host = [torch.empty(args.batch, t2, dtype=torch.int32).pin_memory() for _ in range(2)]
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
@@ -387,24 +416,24 @@ def run_ours(args, rank, world, local_rank):
     main = torch.cuda.current_stream()
 
     def e2e_loop(n):
+        k0 = gstep[0]                       # input / graph / result slot of a step = its global index & 1
         for i in range(n + 1):
             if i < n:                       # stage PCM of step i (overlaps compute of step i-1)
-                s = i % 2
+                s = (k0 + i) % 2
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(in_free[s])
                     dev_in[s].copy_(pinned, non_blocking=True)
                     in_ready[s].record(copy_stream)
             if i > 0:                       # compute step i-1, ship its greedy ids to the host
-                s = (i - 1) % 2
+                s = (k0 + i - 1) % 2
                 main.wait_event(in_ready[s])
-                res = graphed[s]()
-                gather(res)
+                res = step(None, graphs=graphed)
                 in_free[s].record(main)
                 ids_host[s].copy_(res["greedy"], non_blocking=True)
                 out_done[s].record(main)
             if i > 1:                       # the consumer reads step i-2's ids
-                out_done[i % 2].synchronize()
-                _ = int(ids_host[i % 2][0, 0])
+                out_done[(k0 + i) % 2].synchronize()
+                _ = int(ids_host[(k0 + i) % 2][0, 0])
         drain()
         torch.cuda.synchronize()
 
@@ -424,6 +453,25 @@ def run_ours(args, rank, world, local_rank):
     e2e_loop(args.steps)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    # ---- multi-GPU: what rank 0 holds must be what the ranks produced (checked on the last step) ----
+    gather_check = None
+    if peer is not None:
+        last = gstep[0] - 1
+        barrier()
+        mine = None
+        if rank != 0:
+            sl = peer.slot(last)
+            mine = {k: float(v.double().sum()) for k, v in sl.items()}
+        sums = [None] * world
+        dist.all_gather_object(sums, mine)
+        if rank == 0:
+            for r in range(1, world):
+                for k, want in sums[r].items():
+                    got = float(peer.gathered[r][k].double().sum())
+                    if abs(got - want) > 1e-6 * max(1.0, abs(want)):
+                        raise RuntimeError(f"peer gather mismatch: rank {r} {k}: {got} != {want}")
+            gather_check = "checksums of every rank's last step match what rank 0 pulled"
 
     if rank != 0:
         return
@@ -455,6 +503,7 @@ def run_ours(args, rank, world, local_rank):
                         "(GraphedPipeline) per step, greedy CTC ids out; enc_out and p_ctc stay on the device as in "
                         "the reference's compute_forward"},
         "gpu_launches": launches,
+        **({"gather_check": gather_check} if gather_check else {}),
         "clocks": clocks.summary(),
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -464,6 +513,8 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()
     args = parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -366,7 +366,8 @@ def _layernorm(x, g, b, eps, out_f32=None, out_bf16=None):
                                stream())
 
 
-def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, want_bf16_copy: bool = False):
+def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, want_bf16_copy: bool = False,
+                  enc_out: Optional[torch.Tensor] = None):
     """a5 (src-linear + PE) and a7 (N pre-LN layers + final LN).
     src: [B, T2, 5120] fp32 (fp32 mode) or bf16 (bf16 mode).  Returns enc_out fp32 [B, T2, d]
     (and, if asked, its bf16 copy for the CTC GEMM)."""
@@ -411,7 +412,10 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
         else:
             _gemm(hbuf, L.w_1, L.b_1, ff, prec, act=ACT_GELU_ERF, tag="ffn1")
             _gemm(ff, L.w_2, L.b_2, x, prec, resid=x, tag="ffn2")
-    enc = torch.empty(b, t2, d, device=dev, dtype=torch.float32)
+    # (enc_out: caller-provided result buffer, e.g. the slot rank 0 pulls from in the multi-GPU gather)
+    enc = enc_out if enc_out is not None else torch.empty(b, t2, d, device=dev, dtype=torch.float32)
+    if enc.shape != (b, t2, d) or enc.dtype != torch.float32:
+        raise _lib.StacB200Error("enc_out buffer must be fp32 [batch, frames, d_model]")
     enc_bf16 = torch.empty(b, t2, d, device=dev, dtype=torch.bfloat16) if want_bf16_copy else None
     _layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=enc.view(m, d), out_bf16=None if enc_bf16 is None else enc_bf16.view(m, d))
     return (enc, enc_bf16) if want_bf16_copy else enc
@@ -435,7 +439,8 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 def ctc_head_bf16(enc_bf16: torch.Tensor, weight_bf16: torch.Tensor, bias: Optional[torch.Tensor],
-                  out_dtype: torch.dtype = torch.float32):
+                  out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None,
+                  ids_out: Optional[torch.Tensor] = None):
     """a8 + a9 fused (bf16 mode): log_softmax(enc W^T + b) fp32 [.., V] and greedy ids int32 [..], logits never
     materialised (two GEMM passes, see include/stac_b200.h)."""
     shp = enc_bf16.shape
@@ -444,8 +449,18 @@ def ctc_head_bf16(enc_bf16: torch.Tensor, weight_bf16: torch.Tensor, bias: Optio
     v = weight_bf16.shape[0]
     global _LABEL
     ws = torch.empty(lib().stac_ctc_head_workspace_floats(m, v), device=x2.device, dtype=torch.float32)
-    out = torch.empty(m, v, device=x2.device, dtype=out_dtype)
-    ids = torch.empty(m, device=x2.device, dtype=torch.int32)
+    if out is not None:
+        if out.numel() != m * v or out.dtype != out_dtype or not out.is_contiguous():
+            raise _lib.StacB200Error("posterior buffer must be contiguous [rows, vocab] of the requested dtype")
+        out = out.view(m, v)
+    else:
+        out = torch.empty(m, v, device=x2.device, dtype=out_dtype)
+    if ids_out is not None:
+        if ids_out.numel() != m or ids_out.dtype != torch.int32 or not ids_out.is_contiguous():
+            raise _lib.StacB200Error("greedy-id buffer must be contiguous int32 [rows]")
+        ids = ids_out.view(m)
+    else:
+        ids = torch.empty(m, device=x2.device, dtype=torch.int32)
     prev, _LABEL = _LABEL, "ctc_head"
     try:
         _call("stac_ctc_head_bf16", ptr(x2, torch.bfloat16), ptr(weight_bf16, torch.bfloat16), ptr(bias), m, v, d,

@@ -116,8 +116,12 @@ class EncoderPipeline:
 
     @torch.no_grad()
     def __call__(self, wavs: torch.Tensor, wav_lens: Optional[torch.Tensor], want_posteriors: bool = True,
-                 want_greedy: bool = True, stop_after: Optional[str] = None):
+                 want_greedy: bool = True, stop_after: Optional[str] = None,
+                 outputs: Optional[Dict[str, torch.Tensor]] = None):
+        """outputs: optional caller-owned result buffers {"enc_out", "p_ctc", "greedy"} (bf16 mode) that the last kernels
+        write directly, e.g. the peer-visible slots of distributed.PeerGather."""
         m = self.mods
+        outputs = outputs or {}
         dev = wavs.device
         fb, norm = m["compute_features"], m["normalize"]
         mean, std = norm.device_stats(dev, ops.N_MELS)
@@ -134,7 +138,7 @@ class EncoderPipeline:
         kv_len = ops.kv_lengths(wav_lens, b, t2, dev, self.train_mask)
         res = {"kv_len": kv_len}
         if bf16:
-            enc, enc_b = ops.encoder_stack(src, tr.packed(), kv_len, want_bf16_copy=True)
+            enc, enc_b = ops.encoder_stack(src, tr.packed(), kv_len, want_bf16_copy=True, enc_out=outputs.get("enc_out"))
         else:
             enc = ops.encoder_stack(src, tr.packed(), kv_len)
             enc_b = enc
@@ -143,7 +147,10 @@ class EncoderPipeline:
             ctc = m["ctc_lin"]
             bias = None if ctc.w.bias is None else ctc.w.bias.detach().float().contiguous()
             if bf16:
-                p, ids = ops.ctc_head_bf16(enc_b, ctc.packed_weight(), bias, self.posterior_dtype)
+                p, ids = ops.ctc_head_bf16(enc_b, ctc.packed_weight(), bias, self.posterior_dtype,
+                                           out=outputs.get("p_ctc"), ids_out=outputs.get("greedy"))
+                p = p.view(b, t2, -1)
+                ids = ids.view(b, t2)
             else:
                 logits = ops.linear(enc_b, ctc.packed_weight(), bias, self.precision, tag="ctc_lin")
                 p, ids = ops.log_softmax(logits, want_argmax=True, inplace=True)
