@@ -286,12 +286,17 @@ def run_ours(args, rank, world, local_rank):
         d = hp.d_model
         pdt = torch.bfloat16 if (args.gather == "bf16" and args.precision == "bf16") else torch.float32
         if args.gather_transport == "peer":
-            from stac_speech_translation_b200.distributed import PeerGather
+            from stac_speech_translation_b200.distributed import PeerGather, PeerGatherUnavailable
             specs = {"enc_out": ((args.batch, t2, d), torch.float32), "greedy": ((args.batch, t2), torch.int32)}
             if args.gather != "ids":
                 specs["p_ctc"] = ((args.batch, t2, VOCAB), pdt)
-            peer = PeerGather(specs, dev)
-        elif rank == 0:
+            try:
+                peer = PeerGather(specs, dev)
+            except PeerGatherUnavailable as e:     # raised on every rank together: all fall back to NCCL p2p
+                if rank == 0:
+                    print(f"bench: peer transport unavailable ({e}); using NCCL point-to-point", file=sys.stderr)
+                args.gather_transport = "nccl"
+        if args.gather_transport == "nccl" and rank == 0:
             gather_bufs = {"enc": [torch.empty(args.batch, t2, d, device=dev) for _ in range(world)],
                            "ids": [torch.empty(args.batch, t2, device=dev, dtype=torch.int32) for _ in range(world)]}
             if args.gather != "ids":

@@ -132,6 +132,10 @@ class _IpcEvent:
         self._check(self.rt().cudaStreamWaitEvent(ctypes.c_void_p(stream.cuda_stream), self.ev, 0), "cudaStreamWaitEvent")
 
 
+class PeerGatherUnavailable(RuntimeError):
+    """The peer-memory transport cannot be set up on this box (raised on every rank together)."""
+
+
 class PeerGather:
     """Results of every rank to rank 0 WITHOUT a communication kernel: rank 0 pulls them over NVLink with
     copy-engine peer copies out of result buffers that the producing kernels wrote directly.
@@ -149,49 +153,72 @@ class PeerGather:
         rank 0 : collect(step)     -> pulls every peer's slot into self.gathered[r] on a side stream
     """
 
+    def _agree(self, ok: bool, what: str):
+        """All ranks learn whether a set-up phase worked everywhere; raises PeerGatherUnavailable on EVERY rank if it
+        did not on any, so the caller can fall back to another transport without leaving a rank behind."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ctl)
+        if int(flag) == 0:
+            raise PeerGatherUnavailable(what)
+
     def __init__(self, specs: Dict[str, tuple], device: torch.device, slots: int = 2):
         from torch.multiprocessing.reductions import reduce_tensor
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device, self.n_slots, self.keys = device, slots, list(specs)
         self.ctl = dist.new_group(backend="gloo")
         self._msg = torch.zeros(1, dtype=torch.int64)
-        payload = None
-        if self.rank != 0:
-            self._slots = [{k: torch.empty(shape, dtype=dt, device=device) for k, (shape, dt) in specs.items()}
-                           for _ in range(slots)]
-            self._ready = [_IpcEvent() for _ in range(slots)]
-            for ev in self._ready:
-                ev.record(torch.cuda.current_stream(device))
-            payload = {"device": device.index,
-                       "tensors": [{k: reduce_tensor(t) for k, t in s.items()} for s in self._slots],
-                       "ready": [ev.handle() for ev in self._ready]}
+        payload, ok = None, True
+        try:                                    # phase 1 (local): result slots, ordering events, their IPC handles
+            if self.rank != 0:
+                self._slots = [{k: torch.empty(shape, dtype=dt, device=device) for k, (shape, dt) in specs.items()}
+                               for _ in range(slots)]
+                self._ready = [_IpcEvent() for _ in range(slots)]
+                for ev in self._ready:
+                    ev.record(torch.cuda.current_stream(device))
+                payload = {"device": device.index,
+                           "tensors": [{k: reduce_tensor(t) for k, t in s.items()} for s in self._slots],
+                           "ready": [ev.handle() for ev in self._ready]}
+        except Exception as e:                  # noqa: BLE001 - any failure here means "no peer transport on this box"
+            ok, self._why = False, repr(e)
+        self._agree(ok, "CUDA IPC export of the result buffers failed")
         gathered = [None] * self.world if self.rank == 0 else None
         dist.gather_object(payload, gathered, dst=0, group=self.ctl)
         done_handles = [None] * self.world
-        if self.rank == 0:
-            self._peer, self._peer_ready, self._done, self._pstream, self._pdev, self._last = {}, {}, {}, {}, {}, {}
-            self.gathered = {}
-            for r in range(1, self.world):
-                p = gathered[r]
-                pd = p["device"]
-                self._pdev[r] = pd
-                self._peer[r] = [{k: fn(*args) for k, (fn, args) in s.items()} for s in p["tensors"]]
-                self.gathered[r] = {k: torch.empty(shape, dtype=dt, device=device) for k, (shape, dt) in specs.items()}
-                # one torch cross-device copy makes torch enable peer access between the two devices
-                self.gathered[r][self.keys[0]].view(-1)[:1].copy_(self._peer[r][0][self.keys[0]].view(-1)[:1])
-                with torch.cuda.device(pd):         # everything that touches an IPC event lives on the peer's device
-                    self._pstream[r] = torch.cuda.Stream(device=pd)
-                    self._peer_ready[r] = [_IpcEvent(h) for h in p["ready"]]
-                    self._done[r] = [_IpcEvent() for _ in range(slots)]
-                    for ev in self._done[r]:
-                        ev.record(self._pstream[r])
-                    done_handles[r] = {"device": pd, "done": [ev.handle() for ev in self._done[r]]}
-            torch.cuda.synchronize(device)
+        try:                                    # phase 2 (rank 0): open the peers' buffers and events
+            if self.rank == 0:
+                self._peer, self._peer_ready, self._done, self._pstream, self._pdev, self._last = {}, {}, {}, {}, {}, {}
+                self.gathered = {}
+                for r in range(1, self.world):
+                    p = gathered[r]
+                    pd = p["device"]
+                    if not torch.cuda.can_device_access_peer(device.index, pd):
+                        raise RuntimeError(f"no peer access {device.index} -> {pd}")
+                    self._pdev[r] = pd
+                    self._peer[r] = [{k: fn(*args) for k, (fn, args) in s.items()} for s in p["tensors"]]
+                    self.gathered[r] = {k: torch.empty(shape, dtype=dt, device=device)
+                                        for k, (shape, dt) in specs.items()}
+                    # one torch cross-device copy makes torch enable peer access between the two devices
+                    self.gathered[r][self.keys[0]].view(-1)[:1].copy_(self._peer[r][0][self.keys[0]].view(-1)[:1])
+                    with torch.cuda.device(pd):     # everything that touches an IPC event lives on the peer's device
+                        self._pstream[r] = torch.cuda.Stream(device=pd)
+                        self._peer_ready[r] = [_IpcEvent(h) for h in p["ready"]]
+                        self._done[r] = [_IpcEvent() for _ in range(slots)]
+                        for ev in self._done[r]:
+                            ev.record(self._pstream[r])
+                        done_handles[r] = {"device": pd, "done": [ev.handle() for ev in self._done[r]]}
+                torch.cuda.synchronize(device)
+        except Exception as e:                  # noqa: BLE001
+            ok, self._why = False, repr(e)
+        self._agree(ok, "rank 0 could not open the peers' buffers (devices not visible to it, or no peer access)")
         mine = [None]
         dist.scatter_object_list(mine, done_handles if self.rank == 0 else None, src=0, group=self.ctl)
-        if self.rank != 0:
-            d = mine[0]
-            self._done_here = [_IpcEvent(h) for h in d["done"]]       # created by rank 0 on MY device
+        try:
+            if self.rank != 0:
+                d = mine[0]
+                self._done_here = [_IpcEvent(h) for h in d["done"]]       # created by rank 0 on MY device
+        except Exception as e:                  # noqa: BLE001
+            ok, self._why = False, repr(e)
+        self._agree(ok, "a rank could not open rank 0's completion events")
         dist.barrier(group=self.ctl)
 
     def _post(self, value: int, dst: int) -> None:
