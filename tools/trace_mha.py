@@ -18,6 +18,9 @@ lib.stac_mha_trace(buf.data_ptr())
 f(qkv.data_ptr(), None, kv.data_ptr(), b, t, 752, d, h, ctx.data_ptr(), st)
 torch.cuda.synchronize()
 tr = (buf.cpu().long() & 0xffffffff).view(5, 64, 8)
+import json, os
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(tr.tolist(), open(sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/mha_trace_raw.json", "w"))
 t0 = int(tr[tr > 0].min())
 names = {0: "producer: kv_empty passed", 1: "mma0: 0 S-start 1 kv_full 2 s_free 3 S-issued 4 PV-start 5 p_full 6 PV-issued",
          3: "softmax0: 0 start 1 s_full 2 ld+s_free 3 p_free 4 exp/store done 5 p_full arrived"}
