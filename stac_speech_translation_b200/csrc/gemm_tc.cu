@@ -20,6 +20,7 @@
 //     loaded into the SM.
 //   conv mode: 4 epilogue warps, direct stores (K = 2304: the MMAs hide the epilogue).
 #include <algorithm>
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace {
@@ -522,6 +523,19 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
 
 }  // namespace
 
+// gemm_wres.cu: the weight-resident kernel for K = 256, N % 256 == 0 (same tensor maps)
+int stac_gemm_wres_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const float* bias,
+                          int c_bf16, int reduce_add, int64_t m, int64_t n, int64_t k, cudaStream_t st);
+
+static bool wres_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("STAC_WRES");      // STAC_WRES=0: always the general kernel (A/B measurements)
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 // tensor maps + launch of the linear-mode kernel; `ep` carries the epilogue options (c/m/n are filled in here)
 static int launch_linear(const uint16_t* a, const uint16_t* w, void* c, int c_dtype, int64_t m, int64_t n, int64_t k,
                          EpiParams ep, void* stream) {
@@ -552,6 +566,11 @@ static int launch_linear(const uint16_t* a, const uint16_t* w, void* c, int c_dt
   }
   ep.c = c; ep.c_bf16 = c_dtype == STAC_DT_BF16; ep.m = m; ep.n = n;
   ep.t2_len = 0; ep.tiles_per_utt = 1;
+  // plain projections of a d_model = 256 layer with enough row tiles to amortise a resident weight block
+  if (k == 256 && n % BLOCK_N == 0 && n / BLOCK_N <= 8 && ep.act == STAC_ACT_NONE && !ep.vt && !ep.resid && !ep.stats &&
+      !ep.row_sub && (!ep.reduce_add || !ep.c_bf16) && ceil_div64(m, BLOCK_M) * (n / BLOCK_N) >= 2 * num_sms() &&
+      wres_enabled())
+    return stac_gemm_wres_launch(ta, tb, tcm, ep.bias, ep.c_bf16, ep.reduce_add, m, n, k, as_stream(stream));
   return launch<false>(ta, tb, tcm, ep, (int)ceil_div64(m, BLOCK_M), (int)ceil_div64(n, BLOCK_N),
                        (int)(k / BLOCK_K), as_stream(stream));
 }

@@ -62,6 +62,27 @@ def test_many_tiles_persistent_loop():
     assert rel_max(got, ref) < 1e-4
 
 
+@pytest.mark.parametrize("m,n", [(128 * 100 + 37, 768), (128 * 300 + 5, 256), (128 * 40, 2048), (128 * 149, 512)])
+def test_weight_resident_projection(m, n):
+    """K = 256 with enough row tiles: stac_gemm_bf16 routes to the weight-resident kernel (csrc/gemm_wres.cu).
+    bf16 store with bias (QKV), fp32 store without bias, fp32 in-place residual through TMA reduce-add (out-proj)."""
+    got, ref = _run(m, n, 256, out_bf16=True, seed=5)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 4e-3
+    got, ref = _run(m, n, 256, bias=False, seed=6)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 1e-5 and rel_max(got, ref) < 1e-4
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(m, 256, generator=g).to(torch.bfloat16)
+    w = (torch.randn(n, 256, generator=g) / 16).to(torch.bfloat16)
+    b = torch.randn(n, generator=g)
+    x = torch.randn(m, n, generator=g)
+    c = x.cuda()
+    ops._gemm(a.cuda(), w.cuda(), b.cuda(), c, "bf16", resid=c)
+    ref = x + a.float() @ w.float().T + b
+    assert rel_l2(c.cpu(), ref) < 1e-5 and rel_max(c.cpu(), ref) < 1e-4
+
+
 def test_qkv_with_transposed_v():
     g = torch.Generator().manual_seed(1)
     b, t, d, h = 3, 77, 256, 4
