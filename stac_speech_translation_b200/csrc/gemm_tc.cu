@@ -524,7 +524,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm,
 }  // namespace
 
 // gemm_wres.cu: the weight-resident kernel for K = 256, N % 256 == 0 (same tensor maps)
-int stac_gemm_wres_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const float* bias,
+int stac_gemm_wres_launch(const CUtensorMap& ta, const uint16_t* w, const CUtensorMap& tcm, const float* bias,
                           int c_bf16, int reduce_add, int64_t m, int64_t n, int64_t k, cudaStream_t st);
 
 static bool wres_enabled() {
@@ -570,7 +570,7 @@ static int launch_linear(const uint16_t* a, const uint16_t* w, void* c, int c_dt
   if (k == 256 && n % BLOCK_N == 0 && n / BLOCK_N <= 8 && ep.act == STAC_ACT_NONE && !ep.vt && !ep.resid && !ep.stats &&
       !ep.row_sub && (!ep.reduce_add || !ep.c_bf16) && ceil_div64(m, BLOCK_M) * (n / BLOCK_N) >= 2 * num_sms() &&
       wres_enabled())
-    return stac_gemm_wres_launch(ta, tb, tcm, ep.bias, ep.c_bf16, ep.reduce_add, m, n, k, as_stream(stream));
+    return stac_gemm_wres_launch(ta, w, tcm, ep.bias, ep.c_bf16, ep.reduce_add, m, n, k, as_stream(stream));
   return launch<false>(ta, tb, tcm, ep, (int)ceil_div64(m, BLOCK_M), (int)ceil_div64(n, BLOCK_N),
                        (int)(k / BLOCK_K), as_stream(stream));
 }

@@ -13,25 +13,38 @@
 // overlaps the MMAs of tile i+1), warps 2-9 epilogue (TMEM lane quarter = warp & 3, 128 columns each, four 32-column
 // chunks -> bias -> swizzled staging tile -> TMA store / reduce-add, so the residual stream is never loaded).
 #include <algorithm>
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace {
 
 using namespace tc;
 
-constexpr int kK = 256, BM = 128, BN = 256, BK = 64;
-constexpr int kAStages = 4;
+constexpr int kK = 256, BM = 128, BK = 64;
 constexpr int kABytes = BM * BK * 2;              // 16 KB
-constexpr int kBBlock = BN * BK * 2;              // 32 KB per k-block of the resident weight tile
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kOffB = 0;                          // 4 x 32 KB
-constexpr int kOffA = 4 * kBBlock;                // ring
-constexpr int kOffStage = kOffA + kAStages * kABytes;      // 8 x 4 KB output staging
-constexpr int kOffBias = kOffStage + kEpiWarps * 4096;     // 256 floats
-constexpr int kOffBar = kOffBias + BN * 4;
-constexpr int kNumBars = 1 + 2 * kAStages + 4;
-constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+constexpr int kSmemLimit = 232448;                // 227 KB per CTA
+
+// BN = columns of W resident per CTA.  256 (default): each row tile of the activations is read N/256 times from L2 and
+// four ring stages fit beside the 128 KB block; 128: 64 KB block, eight ring stages.  Measured on the QKV projection
+// (48064 x 768): ring of 2 / 3 / 4 stages at BN = 256 -> 37 / 28 / 25 us; BN = 128 with 8 stages -> 25 us as well.  At
+// 25 us the launch moves its 74 MB of output at the 3.9 TB/s this pool sustains for write-dominated traffic.
+template <int BN>
+struct Cfg {
+  static constexpr int kBBlock = BN * BK * 2;               // one k-block of the resident weight tile
+  static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+  static constexpr int kChunks = kColsPerWarp / 32;
+  static constexpr int kAStages = BN == 256 ? 4 : 8;
+  static constexpr int kOffB = 0;
+  static constexpr int kOffA = 4 * kBBlock;
+  static constexpr int kOffStage = kOffA + kAStages * kABytes;       // 8 x 4 KB output staging
+  static constexpr int kOffBias = kOffStage + kEpiWarps * 4096;
+  static constexpr int kOffBar = kOffBias + BN * 4;
+  static constexpr int kNumBars = 1 + 2 * kAStages + 4;
+  static constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+  static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
+};
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -48,10 +61,15 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const float* __restrict__ bias, const int c_bf16,
                  const int reduce_add, const int m_rows, const int num_m_tiles, const int num_n_blocks) {
+  using C = Cfg<BN>;
+  constexpr int kAStages = C::kAStages, kBBlock = C::kBBlock, kOffA = C::kOffA, kOffB = C::kOffB;
+  constexpr int kOffStage = C::kOffStage, kOffBias = C::kOffBias, kOffBar = C::kOffBar, kNumBars = C::kNumBars;
+  constexpr int kColsPerWarp = C::kColsPerWarp, kChunks = C::kChunks;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* sptr = smem_raw + (sbase - smem_u32(smem_raw));
@@ -78,7 +96,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int i = 0; i < 2; ++i) { mbar_init(t_full(i), 1); mbar_init(t_empty(i), kEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   for (int i = threadIdx.x; i < BN; i += kThreads) bias_s[i] = bias ? __ldg(bias + n_blk * BN + i) : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -138,7 +156,7 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue: 8 warps, 128 columns each =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
-    const int cgrp = ew >> 2;              // 128-column half of the 256-wide tile
+    const int cgrp = ew >> 2;              // column group of the 256-wide tile
     const uint32_t stage_buf = sbase + kOffStage + ew * 4096;
     const uint32_t my_row = stage_buf + lane * 128;
     const int sw = lane & 7;
@@ -148,19 +166,19 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row0 = m_tile * BM + quarter * 32;
       mbar_wait(t_full(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + cgrp * 128 + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * BN + cgrp * kColsPerWarp + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
+      for (int chunk = 0; chunk < kChunks; ++chunk) {
         uint32_t v[32];
         tmem_ld32(t_addr + chunk * 32, v);
         tmem_ld_wait();
-        if (chunk == 3) {
+        if (chunk == kChunks - 1) {
           // the whole accumulator has been read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(t_empty(acc));
         }
-        const int lcol = cgrp * 128 + chunk * 32;                 // column inside the 256-wide block
+        const int lcol = cgrp * kColsPerWarp + chunk * 32;                 // column inside the 256-wide block
         const float* bc = bias_s + lcol;
         if (c_bf16) {
           // 64 bf16 columns = one 128-byte staging row; an even chunk fills 16-byte pieces 0..3, an odd one 4..7
@@ -215,16 +233,21 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
-}  // namespace
-
-// Called by launch_linear (gemm_tc.cu) with the tensor maps it has built: A box {64, 128}, W box {64, 256},
-// C box {64 bf16 | 32 fp32, 32}.  Returns STAC_ERR_UNSUPPORTED_SHAPE when the shape is not this kernel's.
-int stac_gemm_wres_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tcm, const float* bias,
-                          int c_bf16, int reduce_add, int64_t m, int64_t n, int64_t k, cudaStream_t st) {
-  if (k != kK || n % BN != 0 || n / BN > 8) return STAC_ERR_UNSUPPORTED_SHAPE;
+template <int BN>
+int launch_wres(const CUtensorMap& ta, const uint16_t* w, const CUtensorMap& tcm, const float* bias, int c_bf16,
+                int reduce_add, int64_t m, int64_t n, cudaStream_t st) {
+  using C = Cfg<BN>;
+  CUtensorMap tb;
+  {
+    const uint64_t dims[2] = {(uint64_t)kK, (uint64_t)n};
+    const uint64_t str[1] = {(uint64_t)kK * 2};
+    const uint32_t box[2] = {BK, BN};
+    int r = encode_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w, 2, dims, str, box);
+    if (r != STAC_OK) return r;
+  }
   const int n_blocks = (int)(n / BN);
   const int m_tiles = (int)ceil_div64(m, BM);
   int grid = std::min(stac_grid_limit(), m_tiles * n_blocks);
@@ -232,10 +255,28 @@ int stac_gemm_wres_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   if (grid < n_blocks) return STAC_ERR_UNSUPPORTED_SHAPE;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_wres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_wres_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr = true;
   }
-  gemm_wres_kernel<<<grid, kThreads, kSmemBytes, st>>>(ta, tb, tcm, bias, c_bf16, reduce_add, (int)m, m_tiles, n_blocks);
+  gemm_wres_kernel<BN><<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, tcm, bias, c_bf16, reduce_add, (int)m, m_tiles,
+                                                             n_blocks);
   STAC_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+// Called by launch_linear (gemm_tc.cu) with the tensor maps it has built for A (box {64, 128}) and C (box {64 bf16 |
+// 32 fp32, 32}).  Returns STAC_ERR_UNSUPPORTED_SHAPE when the shape is not this kernel's.
+int stac_gemm_wres_launch(const CUtensorMap& ta, const uint16_t* w, const CUtensorMap& tcm, const float* bias,
+                          int c_bf16, int reduce_add, int64_t m, int64_t n, int64_t k, cudaStream_t st) {
+  if (k != kK || n % 256 != 0 || n / 256 > 8) return STAC_ERR_UNSUPPORTED_SHAPE;
+  static int bn = 0;
+  if (bn == 0) {
+    const char* e = getenv("STAC_WRES_BN");          // timing experiments: force the resident block width
+    bn = (e && atoi(e) == 256) ? 256 : (e && atoi(e) == 128) ? 128 : -1;
+  }
+  const int use = bn > 0 ? bn : 256;
+  if (use == 256) return launch_wres<256>(ta, w, tcm, bias, c_bf16, reduce_add, m, n, st);
+  return launch_wres<128>(ta, w, tcm, bias, c_bf16, reduce_add, m, n, st);
 }

@@ -2,7 +2,10 @@
 weight-resident kernel and with the general one (STAC_WRES=0 in a child process).  python tools/bench_gemm.py"""
 import os, subprocess, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from stac_speech_translation_b200 import ops
+from stac_speech_translation_b200 import ops, _lib
+if os.environ.get("STAC_LIB"):                      # timing experiments: a variant build of the library
+    from pathlib import Path
+    _lib.LIB_PATH = Path(os.environ["STAC_LIB"]).resolve()
 
 def time_it(fn, n=50):
     for _ in range(5):
@@ -23,8 +26,8 @@ bq, bo = torch.randn(768, device="cuda"), torch.randn(256, device="cuda")
 qkv = torch.empty(m, 768, device="cuda", dtype=torch.bfloat16)
 x = torch.zeros(m, 256, device="cuda")
 big = torch.empty(1 << 28, device="cuda")          # 1 GiB: flush L2 between variants
-print("STAC_WRES", os.environ.get("STAC_WRES", "1"),
+print(os.environ.get("STAC_LIB", "in-tree"), "STAC_WRES", os.environ.get("STAC_WRES", "1"),
       "qkv %.1f us" % time_it(lambda: ops._gemm(a, wq, bq, qkv, "bf16")),
       "out_proj %.1f us" % time_it(lambda: ops._gemm(a, wo, bo, x, "bf16", resid=x)))
-if os.environ.get("STAC_WRES") is None:
+if os.environ.get("STAC_WRES") is None and not os.environ.get("STAC_LIB"):
     subprocess.run([sys.executable, __file__], env={**os.environ, "STAC_WRES": "0"})
