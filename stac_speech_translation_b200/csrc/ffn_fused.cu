@@ -14,7 +14,7 @@
 //   then x += O + b2 as TMA reduce-add from a staging tile (the residual stream is never loaded into the SM).
 // W1 / W2 stream from L2 through a ring of 16 KB units ([128 rows x 64 k] bf16, 128-byte swizzle) in exactly the order
 // the MMA warp consumes them.  Roles: warps 0-15 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = column group),
-// warp 16 TMA producer, warp 17 MMA issuer (warp-uniform loops, one elected lane issues).
+// warp 16 TMA producer, warps 17 / 18 MMA issuers for S / O (warp-uniform loops, one elected lane issues).
 #include <algorithm>
 #include "tc_common.cuh"
 
@@ -27,7 +27,7 @@ constexpr int kHC = 128;           // hidden units per chunk
 constexpr int kUnit = 16384;       // ring unit: [128 rows x 64 k] bf16
 constexpr int kRing = 5;
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kThreads = (kEpiWarps + 3) * 32;
 
 constexpr int kOffH = 0;                       // 4 k-blocks x 16 KB: the h tile (A operand of GEMM 1)
 constexpr int kOffP = 65536;                   // 2 buffers x (2 k-blocks x 16 KB): P (A operand of GEMM 2) / output staging
@@ -40,6 +40,9 @@ constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 
 // the same tanh-form minimax fit of the exact-erf GELU as the GEMM epilogue (gemm_tc.cu)
 __device__ __forceinline__ float gelu_fast(float x) {
+#ifdef FFN_NOGELU     // timing experiment only
+  return x;
+#endif
   const float u = fminf(x * x, 64.0f);
   float p = fmaf(-3.51516785e-04f, u, 3.70056460e-02f);
   p = fmaf(p, u, 7.97507884e-01f);
@@ -120,8 +123,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
     auto load_unit = [&](const CUtensorMap* map, int c0, int c1) {
       mbar_wait(w_empty(stage), phase ^ 1);
       if (elect_one()) {
+#ifdef FFN_NOLOAD    // timing experiment only (tools/bench_ffn.py): the weight stream is not loaded, results are wrong
+        mbar_arrive(w_full(stage));
+#else
         mbar_arrive_expect_tx(w_full(stage), kUnit);
         tma_load_2d(sbase + kOffW + stage * kUnit, map, w_full(stage), c0, c1);
+#endif
       }
       __syncwarp();
       if (++stage == kRing) { stage = 0; phase ^= 1; }
@@ -145,13 +152,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         if (c + 2 < n_chunks) load_w1(c + 2);
       }
     }
-  } else if (warp == 17) {
-    // ============================ MMA issuer ============================
+  } else if (warp == 17 || warp == 18) {
+    // ============================ MMA issuers ============================
+    // warp 17 issues every S = h . W1^T, warp 18 every O += P . W2^T.  One warp doing both is the bottleneck of the
+    // kernel (traced: ~1600 clk to issue a 4-unit block of 16 MMAs on a sub-partition shared with four GELU warps, two
+    // blocks per chunk against 2048 clk of MMA work).  Both walk the same unit sequence of the weight ring and skip the
+    // units that belong to the other.
     constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    const bool s_role = warp == 17;
     int stage = 0;
     uint32_t phase = 0;
     int n_done = 0;
     int g = 0;                              // running chunk index over all tiles: selects S / P buffer and barrier parity
+    auto skip4 = [&]() {                    // four units of the other issuer
+      stage += 4;
+      if (stage >= kRing) { stage -= kRing; phase ^= 1; }
+    };
     auto issue_s = [&](int gi) {
       // S(gi) = h . W1[chunk]^T : four 64-wide k-blocks, one ring unit each
       const int i = gi & 1;
@@ -199,24 +215,33 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         }
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n_done) {
-      mbar_wait(h_full(), (uint32_t)n_done & 1);
-      issue_s(g);
-      if (n_chunks > 1) issue_s(g + 1);
-      auto release_h = [&]() {       // the last S of the tile has been issued: once it retires the h tile may be reloaded
-        if (elect_one()) umma_commit(h_free());
-        __syncwarp();
-      };
-      if (n_chunks <= 2) release_h();
-      for (int c = 0; c < n_chunks; ++c) {
-        if (c == 0) mbar_wait(o_free(), ((uint32_t)n_done & 1) ^ 1);     // the previous tile's O has been read out
-        issue_o(g + c, c == 0);
-        if (c + 2 < n_chunks) {
-          issue_s(g + c + 2);
-          if (c + 2 == n_chunks - 1) release_h();
+      if (s_role) {
+        auto release_h = [&]() {     // the last S of the tile has been issued: once it retires the h tile may be reloaded
+          if (elect_one()) umma_commit(h_free());
+          __syncwarp();
+        };
+        mbar_wait(h_full(), (uint32_t)n_done & 1);
+        issue_s(g);
+        if (n_chunks > 1) issue_s(g + 1);
+        if (n_chunks <= 2) release_h();
+        for (int c = 0; c < n_chunks; ++c) {
+          skip4();                                           // W2[c]
+          if (c + 2 < n_chunks) {
+            issue_s(g + c + 2);
+            if (c + 2 == n_chunks - 1) release_h();
+          }
         }
+      } else {
+        skip4();                                             // W1[0]
+        if (n_chunks > 1) skip4();                           // W1[1]
+        for (int c = 0; c < n_chunks; ++c) {
+          if (c == 0) mbar_wait(o_free(), ((uint32_t)n_done & 1) ^ 1);     // the previous tile's O has been read out
+          issue_o(g + c, c == 0);
+          if (c + 2 < n_chunks) skip4();                     // W1[c + 2]
+        }
+        if (elect_one()) umma_commit(o_full());
+        __syncwarp();
       }
-      if (elect_one()) umma_commit(o_full());
-      __syncwarp();
       g += n_chunks;
     }
   } else {
@@ -227,6 +252,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
     const int sw = r & 7;
     const uint32_t stage_buf = sbase + kOffP + warp * 4096;    // output staging (after the last P of a tile was consumed)
     int n_done = 0, g = 0;
+    bool staged = false;               // output staging tiles of the previous tile may still be being read
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n_done) {
       for (int c = 0; c < n_chunks; ++c, ++g) {
         const int i = g & 1;
@@ -255,6 +281,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         }
         if (warp == 0 && lane == 0 && x[0] != 123.f) FTRACE(1, 2, g);
         mbar_wait(p_free(i), u ^ 1);                     // P.W2 of chunk g - 2 has retired
+        if (staged) {
+          // the previous tile's output staging tiles live in the P buffers: nobody may write P before every store has
+          // read them.  Waiting here, after the first chunk's GELU, hides most of the ~3500 clk a reduce-add takes to
+          // read its source behind useful work.
+          bulk_wait_read0();
+          epi_bar_sync();
+          staged = false;
+        }
         if (warp == 0 && lane == 0) FTRACE(1, 3, g);
         // my 32 hidden columns = k-block cgrp >> 1, 16-byte chunks (cgrp & 1) * 4 .. +3 of row r
         const uint32_t prow = sbase + kOffP + i * 32768 + (cgrp >> 1) * kUnit + r * 128;
@@ -298,9 +332,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         if (row0 < m_rows && elect_one()) { tma_reduce_add_2d(&tmap_x, stage_buf, col0, row0); bulk_commit(); }
         __syncwarp();
       }
-      // the staging tiles live in the P buffers: nobody may write the next tile's P before every store has read them
-      bulk_wait_read0();
-      epi_bar_sync();
+      staged = true;
     }
     bulk_wait0();
     __syncwarp();
