@@ -329,7 +329,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         }
         fence_proxy_async_smem();
         __syncwarp();
+#if defined(FFN_NOOUT)       // timing experiments only (tools/bench_ffn.py): results are wrong
+        if (false) {}
+#elif defined(FFN_PLAINSTORE)
+        if (row0 < m_rows && elect_one()) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(stage_buf), "r"(col0), "r"(row0) : "memory");
+          bulk_commit();
+        }
+#else
         if (row0 < m_rows && elect_one()) { tma_reduce_add_2d(&tmap_x, stage_buf, col0, row0); bulk_commit(); }
+#endif
         __syncwarp();
       }
       staged = true;
