@@ -24,17 +24,18 @@ using namespace tc;
 
 constexpr int kD = 256;            // d_model this kernel is specialised for
 constexpr int kHC = 128;           // hidden units per chunk
-constexpr int kUnit = 16384;       // ring unit: [128 rows x 64 k] bf16
-constexpr int kRing = 5;
+constexpr int kKB = 16384;         // one [128 rows x 64 k] bf16 k-block (h, P, and the halves of a W1 unit)
+constexpr int kUnit = 32768;       // ring unit: W1 [128 hidden x 128 k] (two k-blocks) or W2 [256 outputs x 64 hidden]
+constexpr int kRing = 3;
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (kEpiWarps + 3) * 32;
 
 constexpr int kOffH = 0;                       // 4 k-blocks x 16 KB: the h tile (A operand of GEMM 1)
 constexpr int kOffP = 65536;                   // 2 buffers x (2 k-blocks x 16 KB): P (A operand of GEMM 2) / output staging
 constexpr int kOffW = 131072;                  // weight ring
-constexpr int kOffBias = kOffW + kRing * kUnit;   // b1 [<= 4096] fp32 + b2 [256] fp32
+constexpr int kOffBias = kOffW + kRing * kUnit;   // b2 [256] fp32 (b1 is read through L1: no room for it here)
 constexpr int kMaxFfn = 4096;
-constexpr int kOffBar = kOffBias + (kMaxFfn + kD) * 4;
+constexpr int kOffBar = kOffBias + kD * 4;
 constexpr int kNumBars = 2 + 2 * kRing + 8 + 2;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 
@@ -92,8 +93,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
   const uint32_t tmem_slot = bars + 8u * kNumBars;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* b1_s = reinterpret_cast<float*>(sptr + kOffBias);
-  float* b2_s = b1_s + kMaxFfn;
+  float* b2_s = reinterpret_cast<float*>(sptr + kOffBias);
 
   if (tid == 0) {
     prefetch_tmap(&tmap_h); prefetch_tmap(&tmap_w1); prefetch_tmap(&tmap_w2); prefetch_tmap(&tmap_x);
@@ -106,7 +106,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 17) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  for (int i = tid; i < n_chunks * kHC; i += kThreads) b1_s[i] = __ldg(b1 + i);
   for (int i = tid; i < kD; i += kThreads) b2_s[i] = __ldg(b2 + i);
   tc_fence_before();
   __syncthreads();
@@ -116,33 +115,48 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
 
   if (warp == 16) {
     // ============================ TMA producer ============================
-    // unit order per tile = MMA consumption order: W1[0] W1[1] | W2[0] W1[2] | W2[1] W1[3] | ... | W2[n-2] | W2[n-1]
+    // unit order per tile = MMA consumption order: W1[0] W1[1] | W2[0] W1[2] | W2[1] W1[3] | ... | W2[n-2] | W2[n-1],
+    // two 32 KB units each
     int stage = 0;
     uint32_t phase = 0;
     int n_done = 0;
-    auto load_unit = [&](const CUtensorMap* map, int c0, int c1) {
-      mbar_wait(w_empty(stage), phase ^ 1);
-      if (elect_one()) {
+    auto next_stage = [&]() { if (++stage == kRing) { stage = 0; phase ^= 1; } };
+    auto load_w1 = [&](int c) {
+      for (int u = 0; u < 2; ++u) {            // k-blocks 2u, 2u+1 of the 128 hidden rows of chunk c
+        mbar_wait(w_empty(stage), phase ^ 1);
+        if (elect_one()) {
 #ifdef FFN_NOLOAD    // timing experiment only (tools/bench_ffn.py): the weight stream is not loaded, results are wrong
-        mbar_arrive(w_full(stage));
+          mbar_arrive(w_full(stage));
 #else
-        mbar_arrive_expect_tx(w_full(stage), kUnit);
-        tma_load_2d(sbase + kOffW + stage * kUnit, map, w_full(stage), c0, c1);
+          mbar_arrive_expect_tx(w_full(stage), kUnit);
+          tma_load_2d(sbase + kOffW + stage * kUnit, &tmap_w1, w_full(stage), (2 * u) * 64, c * kHC);
+          tma_load_2d(sbase + kOffW + stage * kUnit + kKB, &tmap_w1, w_full(stage), (2 * u + 1) * 64, c * kHC);
 #endif
+        }
+        __syncwarp();
+        next_stage();
       }
-      __syncwarp();
-      if (++stage == kRing) { stage = 0; phase ^= 1; }
     };
-    auto load_w1 = [&](int c) { for (int kb = 0; kb < 4; ++kb) load_unit(&tmap_w1, kb * 64, c * kHC); };
     auto load_w2 = [&](int c) {
-      for (int nh = 0; nh < 2; ++nh)
-        for (int kb = 0; kb < 2; ++kb) load_unit(&tmap_w2, c * kHC + kb * 64, nh * 128);
+      for (int kb = 0; kb < 2; ++kb) {         // all 256 output rows x 64 hidden units of chunk c
+        mbar_wait(w_empty(stage), phase ^ 1);
+        if (elect_one()) {
+#ifdef FFN_NOLOAD
+          mbar_arrive(w_full(stage));
+#else
+          mbar_arrive_expect_tx(w_full(stage), kUnit);
+          tma_load_2d(sbase + kOffW + stage * kUnit, &tmap_w2, w_full(stage), c * kHC + kb * 64, 0);
+#endif
+        }
+        __syncwarp();
+        next_stage();
+      }
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n_done) {
       mbar_wait(h_free(), (uint32_t)(n_done & 1) ^ 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(h_full(), 4 * kUnit);
-        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sbase + kOffH + kb * kUnit, &tmap_h, h_full(), kb * 64, tile * 128);
+        mbar_arrive_expect_tx(h_full(), 4 * kKB);
+        for (int kb = 0; kb < 4; ++kb) tma_load_2d(sbase + kOffH + kb * kKB, &tmap_h, h_full(), kb * 64, tile * 128);
       }
       __syncwarp();
       load_w1(0);
@@ -158,61 +172,64 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
     // kernel (traced: ~1600 clk to issue a 4-unit block of 16 MMAs on a sub-partition shared with four GELU warps, two
     // blocks per chunk against 2048 clk of MMA work).  Both walk the same unit sequence of the weight ring and skip the
     // units that belong to the other.
-    constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 256);
     const bool s_role = warp == 17;
     int stage = 0;
     uint32_t phase = 0;
     int n_done = 0;
     int g = 0;                              // running chunk index over all tiles: selects S / P buffer and barrier parity
-    auto skip4 = [&]() {                    // four units of the other issuer
-      stage += 4;
+    auto skip2 = [&]() {                    // two units of the other issuer
+      stage += 2;
       if (stage >= kRing) { stage -= kRing; phase ^= 1; }
     };
     auto issue_s = [&](int gi) {
-      // S(gi) = h . W1[chunk]^T : four 64-wide k-blocks, one ring unit each
+      // S(gi) = h . W1[chunk]^T : two ring units of two 64-wide k-blocks each
       const int i = gi & 1;
       if (lane == 0) FTRACE(0, 3, gi);
       mbar_wait(s_free(i), ((uint32_t)(gi >> 1) & 1) ^ 1);
       if (lane == 0) FTRACE(0, 4, gi);
-      for (int kb = 0; kb < 4; ++kb) {
+      for (int u = 0; u < 2; ++u) {
         mbar_wait(w_full(stage), phase);
-        if (lane == 0 && kb == 0) FTRACE(0, 5, gi);
+        if (lane == 0 && u == 0) FTRACE(0, 5, gi);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t ad = make_smem_desc_sw128(sbase + kOffH + kb * kUnit);
-          const uint64_t bd = make_smem_desc_sw128(sbase + kOffW + stage * kUnit);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + i * 128, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0);
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t ad = make_smem_desc_sw128(sbase + kOffH + (2 * u + h) * kKB);
+            const uint64_t bd = make_smem_desc_sw128(sbase + kOffW + stage * kUnit + h * kKB);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + i * 128, ad + 2 * k, bd + 2 * k, idesc_s, (u | h | k) != 0);
+          }
           umma_commit(w_empty(stage));
-          if (kb == 3) umma_commit(s_full(i));
+          if (u == 1) umma_commit(s_full(i));
         }
         __syncwarp();
         if (++stage == kRing) { stage = 0; phase ^= 1; }
       }
     };
     auto issue_o = [&](int gi, bool first) {
-      // O[:, nh*128 ..] += P(gi) . W2[nh half, chunk]^T : two 64-wide k-blocks per N half
+      // O += P(gi) . W2[:, chunk]^T : two 64-wide k-blocks, each one ring unit holding all 256 output rows (N = 256)
       const int i = gi & 1;
       if (lane == 0) FTRACE(0, 0, gi);
       mbar_wait(p_full(i), (uint32_t)(gi >> 1) & 1);
       if (lane == 0) FTRACE(0, 1, gi);
-      for (int nh = 0; nh < 2; ++nh)
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait(w_full(stage), phase);
-          if (lane == 0 && nh == 0 && kb == 0) FTRACE(0, 2, gi);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t ad = make_smem_desc_sw128(sbase + kOffP + i * 32768 + kb * kUnit);
-            const uint64_t bd = make_smem_desc_sw128(sbase + kOffW + stage * kUnit);
+      for (int kb = 0; kb < 2; ++kb) {
+        mbar_wait(w_full(stage), phase);
+        if (lane == 0 && kb == 0) FTRACE(0, 2, gi);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = make_smem_desc_sw128(sbase + kOffP + i * 32768 + kb * kKB);
+          const uint64_t bd = make_smem_desc_sw128(sbase + kOffW + stage * kUnit);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + 256 + nh * 128, ad + 2 * k, bd + 2 * k, idesc, !(first && kb == 0 && k == 0));
-            umma_commit(w_empty(stage));
-            if (nh == 1 && kb == 1) umma_commit(p_free(i));
-          }
-          __syncwarp();
-          if (++stage == kRing) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + 256, ad + 2 * k, bd + 2 * k, idesc_o, !(first && kb == 0 && k == 0));
+          umma_commit(w_empty(stage));
+          if (kb == 1) umma_commit(p_free(i));
         }
+        __syncwarp();
+        if (++stage == kRing) { stage = 0; phase ^= 1; }
+      }
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n_done) {
       if (s_role) {
@@ -225,19 +242,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         if (n_chunks > 1) issue_s(g + 1);
         if (n_chunks <= 2) release_h();
         for (int c = 0; c < n_chunks; ++c) {
-          skip4();                                           // W2[c]
+          skip2();                                           // W2[c]
           if (c + 2 < n_chunks) {
             issue_s(g + c + 2);
             if (c + 2 == n_chunks - 1) release_h();
           }
         }
       } else {
-        skip4();                                             // W1[0]
-        if (n_chunks > 1) skip4();                           // W1[1]
+        skip2();                                             // W1[0]
+        if (n_chunks > 1) skip2();                           // W1[1]
         for (int c = 0; c < n_chunks; ++c) {
           if (c == 0) mbar_wait(o_free(), ((uint32_t)n_done & 1) ^ 1);     // the previous tile's O has been read out
           issue_o(g + c, c == 0);
-          if (c + 2 < n_chunks) skip4();                     // W1[c + 2]
+          if (c + 2 < n_chunks) skip2();                     // W1[c + 2]
         }
         if (elect_one()) umma_commit(o_full());
         __syncwarp();
@@ -272,10 +289,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free(i));
-        const float* bc = b1_s + c * kHC + cgrp * 32;
+        const float* bc = b1 + c * kHC + cgrp * 32;      // warp-uniform addresses: broadcast loads served by L1
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(bc + k);
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(bc + k));
           x[k] = gelu_fast(x[k] + bv.x); x[k + 1] = gelu_fast(x[k + 1] + bv.y);
           x[k + 2] = gelu_fast(x[k + 2] + bv.z); x[k + 3] = gelu_fast(x[k + 3] + bv.w);
         }
@@ -291,7 +308,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         }
         if (warp == 0 && lane == 0) FTRACE(1, 3, g);
         // my 32 hidden columns = k-block cgrp >> 1, 16-byte chunks (cgrp & 1) * 4 .. +3 of row r
-        const uint32_t prow = sbase + kOffP + i * 32768 + (cgrp >> 1) * kUnit + r * 128;
+        const uint32_t prow = sbase + kOffP + i * 32768 + (cgrp >> 1) * kKB + r * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           st_shared_v4(prow + ((((cgrp & 1) * 4 + j) ^ sw) << 4), pack_bf16x2(x[8 * j], x[8 * j + 1]),
@@ -384,7 +401,7 @@ extern "C" int stac_ffn_fused_bf16(const uint16_t* h, const uint16_t* w1, const 
   {
     const uint64_t dims[2] = {(uint64_t)d_ffn, (uint64_t)kD};
     const uint64_t str[1] = {(uint64_t)d_ffn * 2};
-    const uint32_t box[2] = {64, 128};
+    const uint32_t box[2] = {64, 256};
     int r = encode_map(&tw2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w2, 2, dims, str, box);
     if (r != STAC_OK) return r;
   }
