@@ -252,15 +252,6 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         c.valid = c.item < n_items;
         if (c.valid) { const Item it = decode_item(c.item, c.n_done, len_cache, n_qblk, n_head, seq_len, kv_len); c.n_kt = it.n_kt; c.active1 = it.active1; }
       };
-      auto skip_inactive = [&](Cursor& c) {
-        // group 1 has no query tile in some items: its cursor jumps over them (and over their ring stages)
-        while (c.valid && w == 1 && !c.active1) {
-          for (int k = 0; k < c.n_kt; ++k) if (++c.stage == kKvStages) { c.stage = 0; c.phase ^= 1; }
-          c.item += gridDim.x;
-          ++c.n_done;
-          load_item(c);
-        }
-      };
       auto advance = [&](Cursor& c) {
         if (++c.stage == kKvStages) { c.stage = 0; c.phase ^= 1; }
         if (++c.j == c.n_kt) {
@@ -268,26 +259,31 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           c.item += gridDim.x;
           ++c.n_done;
           load_item(c);
-          skip_inactive(c);
         }
       };
       Cursor sc;
       sc.item = blockIdx.x; sc.j = 0; sc.n_done = 0; sc.stage = 0; sc.phase = 0;
       load_item(sc);
-      skip_inactive(sc);
       Cursor pc = sc;
-      int g_s = 0, g_p = 0;                 // per-group step indices of the next S and the next P.V
+      // Group 1 has no query tile in some items (last block of an utterance with <= 128 rows left).  Its issuer still
+      // walks every K/V stage of those items as virtual steps - it waits for the fill and hands the stage back - instead
+      // of jumping over them: a warp that skips uses of a parity-tracked mbarrier can later test it while an EARLIER use
+      // is still pending, and the parity aliases to "complete".
+      int g_s = 0, g_p = 0;                 // per-group indices of the next real S and the next real P.V
+      int t_s = 0, t_p = 0;                 // the same counting virtual steps (bounds the lead of S over P.V)
       uint32_t q_fill0 = 0, q_fill1 = 0;    // consumed fills of Q buffers 0 / 1 of this group
       uint32_t items_started = 0;
       const uint32_t q_base = sbase + kOffQ + w * 16384;
       const uint32_t s_tmem = tmem_base + w * 2 * kKTile;
       const uint32_t o_tmem = tmem_base + 256 + w * kHd;
       while (pc.valid) {
-        while (sc.valid && g_s < g_p + 2) {
+        while (sc.valid && t_s < t_p + 2) {
           // ---- S(g_s) = Q K^T into score buffer g_s & 1 ----
           const int i = g_s & 1, buf = sc.n_done & 1;
           TRACE(1 + w, 0, g_s);
           mbar_wait(kv_full(sc.stage), sc.phase);
+          ++t_s;
+          if (w == 1 && !sc.active1) { advance(sc); continue; }      // virtual step: the fill has been observed
           TRACE(1 + w, 1, g_s);
           mbar_wait(s_free(w, i), ((uint32_t)(g_s >> 1) & 1) ^ 1);
           TRACE(1 + w, 2, g_s);
@@ -309,7 +305,12 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           advance(sc);
         }
         // ---- O += P(g_p) V ----
-        {
+        ++t_p;
+        if (w == 1 && !pc.active1) {                                   // virtual step: hand the stage back
+          if (lane == 0) mbar_arrive(kv_empty(pc.stage));
+          __syncwarp();
+          advance(pc);
+        } else {
           const int i = g_p & 1;
           TRACE(1 + w, 4, g_p);
           mbar_wait(p_full(w, i), (uint32_t)(g_p >> 1) & 1);
@@ -325,8 +326,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               umma_bf16(o_tmem, pd + 2 * k, vd + (kVT ? 2 * k : 128 * k), idesc_o, (k | pc.j) != 0);
             }
             umma_commit(p_free(w, i));
-            umma_commit(kv_empty(pc.stage));                 // second arrival comes from the other group's issuer ...
-            if (w == 0 && !pc.active1) mbar_arrive(kv_empty(pc.stage));   // ... or from here when it has no tile in this item
+            umma_commit(kv_empty(pc.stage));                 // the second arrival comes from the other group's issuer
           }
           __syncwarp();
           TRACE(1 + w, 6, g_p);

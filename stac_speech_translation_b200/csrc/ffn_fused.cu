@@ -14,7 +14,7 @@
 //   then x += O + b2 as TMA reduce-add from a staging tile (the residual stream is never loaded into the SM).
 // W1 / W2 stream from L2 through a ring of 16 KB units ([128 rows x 64 k] bf16, 128-byte swizzle) in exactly the order
 // the MMA warp consumes them.  Roles: warps 0-15 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = column group),
-// warp 16 TMA producer, warps 17 / 18 MMA issuers for S / O (warp-uniform loops, one elected lane issues).
+// warp 16 TMA producer, warp 17 MMA issuer (warp-uniform loops, one elected lane issues).
 #include <algorithm>
 #include "tc_common.cuh"
 
@@ -28,7 +28,7 @@ constexpr int kKB = 16384;         // one [128 rows x 64 k] bf16 k-block (h, P, 
 constexpr int kUnit = 32768;       // ring unit: W1 [128 hidden x 128 k] (two k-blocks) or W2 [256 outputs x 64 hidden]
 constexpr int kRing = 3;
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (kEpiWarps + 3) * 32;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
 
 constexpr int kOffH = 0;                       // 4 k-blocks x 16 KB: the h tile (A operand of GEMM 1)
 constexpr int kOffP = 65536;                   // 2 buffers x (2 k-blocks x 16 KB): P (A operand of GEMM 2) / output staging
@@ -166,23 +166,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
         if (c + 2 < n_chunks) load_w1(c + 2);
       }
     }
-  } else if (warp == 17 || warp == 18) {
-    // ============================ MMA issuers ============================
-    // warp 17 issues every S = h . W1^T, warp 18 every O += P . W2^T.  One warp doing both is the bottleneck of the
-    // kernel (traced: ~1600 clk to issue a 4-unit block of 16 MMAs on a sub-partition shared with four GELU warps, two
-    // blocks per chunk against 2048 clk of MMA work).  Both walk the same unit sequence of the weight ring and skip the
-    // units that belong to the other.
+  } else if (warp == 17) {
+    // ============================ MMA issuer ============================
+    // ONE warp consumes the weight ring, in the producer's order.  (Two issuer warps - one for S, one for O, each
+    // skipping the other's units - were 8 % faster but are not safe with parity-tracked mbarriers: the warp that runs
+    // ahead can test a slot's w_full barrier while the slot's PREVIOUS use, owned by the other warp, has not even been
+    // filled; the parity then aliases to "complete" and it reads a slot that is still being written.  It showed up as a
+    // barrier time-out on rank 0 of an 8-GPU run, where NVLink ingress slows the TMA loads.)
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
     constexpr uint32_t idesc_o = make_idesc_bf16(128, 256);
-    const bool s_role = warp == 17;
     int stage = 0;
     uint32_t phase = 0;
     int n_done = 0;
     int g = 0;                              // running chunk index over all tiles: selects S / P buffer and barrier parity
-    auto skip2 = [&]() {                    // two units of the other issuer
-      stage += 2;
-      if (stage >= kRing) { stage -= kRing; phase ^= 1; }
-    };
     auto issue_s = [&](int gi) {
       // S(gi) = h . W1[chunk]^T : two ring units of two 64-wide k-blocks each
       const int i = gi & 1;
@@ -232,33 +228,24 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmap_h, const __grid_consta
       }
     };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n_done) {
-      if (s_role) {
-        auto release_h = [&]() {     // the last S of the tile has been issued: once it retires the h tile may be reloaded
-          if (elect_one()) umma_commit(h_free());
-          __syncwarp();
-        };
-        mbar_wait(h_full(), (uint32_t)n_done & 1);
-        issue_s(g);
-        if (n_chunks > 1) issue_s(g + 1);
-        if (n_chunks <= 2) release_h();
-        for (int c = 0; c < n_chunks; ++c) {
-          skip2();                                           // W2[c]
-          if (c + 2 < n_chunks) {
-            issue_s(g + c + 2);
-            if (c + 2 == n_chunks - 1) release_h();
-          }
-        }
-      } else {
-        skip2();                                             // W1[0]
-        if (n_chunks > 1) skip2();                           // W1[1]
-        for (int c = 0; c < n_chunks; ++c) {
-          if (c == 0) mbar_wait(o_free(), ((uint32_t)n_done & 1) ^ 1);     // the previous tile's O has been read out
-          issue_o(g + c, c == 0);
-          if (c + 2 < n_chunks) skip2();                     // W1[c + 2]
-        }
-        if (elect_one()) umma_commit(o_full());
+      auto release_h = [&]() {       // the last S of the tile has been issued: once it retires the h tile may be reloaded
+        if (elect_one()) umma_commit(h_free());
         __syncwarp();
+      };
+      mbar_wait(h_full(), (uint32_t)n_done & 1);
+      issue_s(g);
+      if (n_chunks > 1) issue_s(g + 1);
+      if (n_chunks <= 2) release_h();
+      for (int c = 0; c < n_chunks; ++c) {
+        if (c == 0) mbar_wait(o_free(), ((uint32_t)n_done & 1) ^ 1);     // the previous tile's O has been read out
+        issue_o(g + c, c == 0);
+        if (c + 2 < n_chunks) {
+          issue_s(g + c + 2);
+          if (c + 2 == n_chunks - 1) release_h();
+        }
       }
+      if (elect_one()) umma_commit(o_full());
+      __syncwarp();
       g += n_chunks;
     }
   } else {
