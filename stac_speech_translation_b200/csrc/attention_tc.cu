@@ -26,6 +26,7 @@
 //     shape TMA delivers for K), so no transposed copy of V is ever written.  A K-major V^T tensor is still
 //     accepted (v_t != NULL) for callers that have one.
 #include <algorithm>
+#include <type_traits>
 #include "tc_common.cuh"
 
 namespace {
@@ -234,10 +235,11 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // Per group the order is fixed: S(0) S(1) | P.V(0) S(2) | P.V(1) S(3) | ...  (the scores run two tiles ahead of
     // the softmax; s_free(g) always arrives before p_full(g), so blocking waits in this order never stall a ready
     // operation).  The two groups are independent instruction streams on different sub-partitions.
-    {
+    // (the group index is a compile-time constant of the issuer body: group 0 carries none of the idle-item logic)
+    auto issuer = [&](auto group) {
       // every lane runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions, which lets
       // ptxas keep descriptors in uniform registers instead of wrapping each MMA in a broadcast loop
-      const int w = warp - 16;
+      constexpr int w = decltype(group)::value;
       constexpr uint32_t idesc_s = make_idesc_bf16(128, kKTile);
       // P.V: N = head_dim; V straight from the QKV projection is an MN-major B operand (bit 16)
       constexpr uint32_t idesc_o = make_idesc_bf16(128, kHd) | (kVT ? 0u : (1u << 16));
@@ -247,10 +249,12 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint32_t phase;
         int n_kt;
         bool active1, valid;
+        bool virt;                // group 1 has no query tile in this item: its stages are walked, not used
       };
       auto load_item = [&](Cursor& c) {
         c.valid = c.item < n_items;
-        if (c.valid) { const Item it = decode_item(c.item, c.n_done, len_cache, n_qblk, n_head, seq_len, kv_len); c.n_kt = it.n_kt; c.active1 = it.active1; }
+        c.virt = false;
+        if (c.valid) { const Item it = decode_item(c.item, c.n_done, len_cache, n_qblk, n_head, seq_len, kv_len); c.n_kt = it.n_kt; c.active1 = it.active1; c.virt = w == 1 && !it.active1; }
       };
       auto advance = [&](Cursor& c) {
         if (++c.stage == kKvStages) { c.stage = 0; c.phase ^= 1; }
@@ -269,21 +273,32 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // walks every K/V stage of those items as virtual steps - it waits for the fill and hands the stage back - instead
       // of jumping over them: a warp that skips uses of a parity-tracked mbarrier can later test it while an EARLIER use
       // is still pending, and the parity aliases to "complete".
-      int g_s = 0, g_p = 0;                 // per-group indices of the next real S and the next real P.V
-      int t_s = 0, t_p = 0;                 // the same counting virtual steps (bounds the lead of S over P.V)
+      // The S cursor stops in front of such an item; when the P.V cursor has caught up, both walk it together.
+      int g_s = 0, g_p = 0;                 // per-group step indices of the next S and the next P.V
       uint32_t q_fill0 = 0, q_fill1 = 0;    // consumed fills of Q buffers 0 / 1 of this group
       uint32_t items_started = 0;
       const uint32_t q_base = sbase + kOffQ + w * 16384;
       const uint32_t s_tmem = tmem_base + w * 2 * kKTile;
       const uint32_t o_tmem = tmem_base + 256 + w * kHd;
       while (pc.valid) {
-        while (sc.valid && t_s < t_p + 2) {
+        if (w == 1 && pc.virt) {
+          // both cursors stand at the first stage of an item without a query tile for this group: observe every fill
+          // and hand the stage back, in order
+          const int n = pc.n_kt;
+          for (int k = 0; k < n; ++k) {
+            mbar_wait(kv_full(pc.stage), pc.phase);
+            if (lane == 0) mbar_arrive(kv_empty(pc.stage));
+            __syncwarp();
+            advance(pc);
+          }
+          sc = pc;
+          continue;
+        }
+        while (sc.valid && !(w == 1 && sc.virt) && g_s < g_p + 2) {
           // ---- S(g_s) = Q K^T into score buffer g_s & 1 ----
           const int i = g_s & 1, buf = sc.n_done & 1;
           TRACE(1 + w, 0, g_s);
           mbar_wait(kv_full(sc.stage), sc.phase);
-          ++t_s;
-          if (w == 1 && !sc.active1) { advance(sc); continue; }      // virtual step: the fill has been observed
           TRACE(1 + w, 1, g_s);
           mbar_wait(s_free(w, i), ((uint32_t)(g_s >> 1) & 1) ^ 1);
           TRACE(1 + w, 2, g_s);
@@ -305,12 +320,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           advance(sc);
         }
         // ---- O += P(g_p) V ----
-        ++t_p;
-        if (w == 1 && !pc.active1) {                                   // virtual step: hand the stage back
-          if (lane == 0) mbar_arrive(kv_empty(pc.stage));
-          __syncwarp();
-          advance(pc);
-        } else {
+        {
           const int i = g_p & 1;
           TRACE(1 + w, 4, g_p);
           mbar_wait(p_full(w, i), (uint32_t)(g_p >> 1) & 1);
@@ -334,7 +344,9 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           advance(pc);
         }
       }
-    }
+    };
+    if (warp == 16) issuer(std::integral_constant<int, 0>{});
+    else issuer(std::integral_constant<int, 1>{});
     __syncwarp();
   } else {
     // ============================ softmax groups ============================
