@@ -10,10 +10,10 @@
 //   per 128-row tile, for every chunk c of 128 hidden units
 //     S_c = h . W1[c]^T            tcgen05.mma 128x128xK=256  -> TMEM (two S buffers, S runs two chunks ahead)
 //     P_c = GELU(S_c + b1[c])      16 epilogue warps: TMEM -> registers -> bf16 -> smem (two P buffers, K-major UMMA layout)
-//     O  += P_c . W2[:, c]^T       tcgen05.mma 128x256xK=128 (two N=128 halves) accumulating in TMEM
+//     O  += P_c . W2[:, c]^T       tcgen05.mma 128x256xK=128 (N = 256) accumulating in TMEM
 //   then x += O + b2 as TMA reduce-add from a staging tile (the residual stream is never loaded into the SM).
-// W1 / W2 stream from L2 through a ring of 16 KB units ([128 rows x 64 k] bf16, 128-byte swizzle) in exactly the order
-// the MMA warp consumes them.  Roles: warps 0-15 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = column group),
+// W1 / W2 stream from L2 through a ring of three 32 KB units (W1: [128 hidden x 128 k] as two k-blocks; W2: [256
+// outputs x 64 hidden]; bf16, 128-byte swizzle) in exactly the order the MMA warp consumes them.  Roles: warps 0-15 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = column group),
 // warp 16 TMA producer, warp 17 MMA issuer (warp-uniform loops, one elected lane issues).
 #include <algorithm>
 #include "tc_common.cuh"
