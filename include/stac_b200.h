@@ -144,7 +144,11 @@ int stac_gemm_f32(const float* a, const float* w, const float* bias, const float
  * TMEM, fused epilogue; c_dtype selects fp32 or bf16 output.
  * vt_out/vt_cols: if vt_out != NULL the last `vt_cols` output columns (the V third of a
  * packed QKV projection) are written transposed to vt_out as bf16 [B*H][64][t_pad]
- * (t = row % seq_len, b = row / seq_len) instead of to C.                             */
+ * (t = row % seq_len, b = row / seq_len) instead of to C.
+ * Plain projections with K = 256 and N a multiple of 256 (the QKV and output projections of a d_model = 256
+ * layer: bias only, bf16 store or in-place fp32 residual) over enough rows run on the weight-resident kernel
+ * (csrc/gemm_wres.cu); environment STAC_WRES=0 forces the general kernel for A/B timing.  Same results either way.
+ * Replaces nn.Linear / MultiheadAttention in_proj / out_proj (TransformerMultiTask.py:296,304-308). */
 int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float* bias, const float* resid,
                    int64_t resid_period, int act, void* c, int c_dtype, int64_t m, int64_t n,
                    int64_t k, uint16_t* vt_out, int64_t vt_cols, int64_t seq_len, int64_t t_pad,
