@@ -54,3 +54,39 @@ def test_shard_and_gather_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok and n_batches > 4 and min(split) >= 1 and sum(split) == n_batches
+
+
+def _agree_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pg = sd.PeerGather.__new__(sd.PeerGather)          # the agreement step alone (the rest needs CUDA IPC)
+        pg.ctl = dist.new_group(backend="gloo")
+        pg._agree(True, "phase that works everywhere")     # must not raise
+        raised = False
+        try:
+            pg._agree(rank != 1, "phase that fails on rank 1 only")
+        except sd.PeerGatherUnavailable:
+            raised = True
+        dist.barrier(group=pg.ctl)                         # every rank is still in step after the failure
+        ret.put((rank, raised))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_gather_setup_failure_is_raised_on_every_rank():
+    """One rank failing a set-up phase makes PeerGather raise PeerGatherUnavailable on ALL ranks together, so the caller
+    (bench.py) can fall back to NCCL point-to-point without leaving a rank behind in a collective."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_agree_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(ret.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: True, 1: True}
