@@ -179,6 +179,11 @@ int stac_mha_f32(const float* qkv, const int32_t* kv_len, int64_t batch, int64_t
 int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int32_t* kv_len, int64_t batch,
                   int64_t seq_len, int64_t t_pad, int64_t d_model, int64_t n_head, uint16_t* ctx,
                   void* stream);
+/* EXPERIMENTAL (csrc/attention_tc2.cu; not on the default path, selected by STAC_MHA_V2=1 in ops.py; not yet run
+ * on a B200): same contract as stac_mha_bf16 with v_t = NULL.  128-key tiles, one thread per query row, P kept in
+ * TMEM as the A operand of P.V, epilogue warpgroup with O double-buffered in TMEM.                               */
+int stac_mha_bf16_v2(const uint16_t* qkv, const int32_t* kv_len, int64_t batch, int64_t seq_len,
+                     int64_t d_model, int64_t n_head, uint16_t* ctx, void* stream);
 
 /* ---------------------------------------------------------------------------
  * a8/a9  CTC head -- replaces hparams.log_softmax(modules.ctc_lin(enc_out)) and

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "stac_kv_lengths": (c_int, [_P, c_int64, c_int64, c_int, _P, _P]),
     "stac_mha_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P]),
     "stac_mha_bf16": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P]),
+    "stac_mha_bf16_v2": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P]),
     "stac_log_softmax": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "stac_ctc_head_workspace_floats": (c_int64, [c_int64, c_int64]),
     "stac_ctc_head_bf16": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int, _P, _P]),

@@ -1,0 +1,535 @@
+// EXPERIMENTAL second decomposition of the tcgen05 flash attention (stac_mha_bf16_v2).  NOT on the default path:
+// ops.py calls it only when STAC_MHA_V2=1.  It compiles for sm_100a (ptxas accepts every instruction form used), but it
+// was written after the round's GPU budget was spent and HAS NOT RUN ON A B200 YET; its parity test
+// (tests/test_gpu_tc_attention.py::test_mha_bf16_v2) is skipped unless STAC_EXPERIMENTAL=1.
+//
+// Reference behaviour replaced: the same as attention_tc.cu (torch.nn.MultiheadAttention slow path with a -inf
+// key-padding mask, reached from /root/reference/stac-st/modules/TransformerMultiTask.py:304-308).
+//
+// Why a second decomposition ("Attention, what the trace says now"): the first kernel balances two halves
+// that are both too slow - two threads per row over 64-key tiles with P going through shared memory cost a softmax
+// step ~1950 clk per 64 keys (MUFU floor 512), and its MMA issue loop costs ~1150 clk per step.  This one is the layout
+// FlashAttention-4 / CUTLASS' sm100 FMHA use:
+//   * 128-key tiles: half as many steps, barriers, commits and MMA blocks per key;
+//   * ONE thread per query row (no row-max exchange between warps, no named barrier in the step);
+//   * P never touches shared memory: the bf16 probabilities are written back into TMEM over the scores they came from
+//     (tcgen05.st) and P.V takes its A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc) - no st.shared, no
+//     fence.proxy.async, and 32 KB of shared memory per stage set free for 128-key K/V tiles;
+//   * S is single-buffered per query group (P aliases it), the two query groups of a work item alternate on the
+//     tensor pipe: while one group runs its exponentials the other group's P.V and next Q.K^T execute;
+//   * O is double-buffered in TMEM and the item epilogue (O / l -> bf16 -> smem -> TMA store) belongs to its own
+//     warpgroup, so the softmax warps go straight on to the next item;
+//   * an optional share of the exponentials is evaluated on the FMA pipe (Cody-Waite split + cubic), -DMHA2_POLY=n
+//     (n of every 8 columns), default 0, to get under the MUFU floor once the rest of the chain is tight.
+// Budget per 128-key step of one CTA (2 x 128 query rows): MUFU 2 x 128 x 128 / 16 = 2048 clk, tensor pipe
+// 2 x (256 + 256) = 1024 clk; the first kernel needs 2 x 1950 = 3900 clk for the same work.
+//
+// TMEM (512 columns): S/P group 0 at 0, group 1 at 128 (128 fp32 score columns; P = 64 columns of packed bf16 pairs
+// on top of the first 64); O[group][buffer] at 256 + (group * 2 + buffer) * 64.
+// Threads (512): warps 0-3 softmax group 0, 4-7 softmax group 1 (warp & 3 = TMEM lane quarter), 8-11 epilogue
+// warpgroup, 12/13 MMA issuers of group 0/1, 14 TMA producer, 15 idle.  setmaxnreg: 176 / 80 / 80.
+#include <algorithm>
+#include <type_traits>
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kHd = 64, kQTile = 128, kKTile = 128;
+constexpr int kKvStages = 3;
+constexpr int kThreads = 512;
+constexpr int kRegsSoftmax = 176, kRegsOther = 80;     // 256 * 176 + 256 * 80 = 512 * 128
+#ifndef MHA2_POLY
+#define MHA2_POLY 0
+#endif
+// shared memory map (bytes, from a 1024-aligned base)
+constexpr int kOffQ = 0;                               // [2 bufs][2 groups] x 16 KB
+constexpr int kOffOut = 65536;                         // [2 groups] x 16 KB: normalised bf16 O tile for the TMA store
+constexpr int kOffKV = 98304;                          // [stages] x (K 16 KB + V 16 KB)
+constexpr int kOffX = kOffKV + kKvStages * 32768;      // float [2 groups][2 O buffers][128 rows]: 1 / row sum
+constexpr int kOffLen = kOffX + 2 * 2 * 128 * 4;       // int [kLenCache]
+constexpr int kLenCache = 128;
+constexpr int kOffBar = kOffLen + kLenCache * 4;
+constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 8;
+constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_mufu(float x) {
+#ifdef MHA2_NOEXP     // timing experiment only: results are wrong
+  return x;
+#else
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#endif
+}
+// 2^x on the FMA pipe for x in [-126, 126]: round-to-nearest split x = n + f, |f| <= 0.5, cubic for 2^f (relative error
+// < 1e-4 after the minimax adjustment of the Taylor coefficients, far below bf16 resolution), exponent added as integer
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;                     // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = 0.0558263f;
+  p = fmaf(p, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+// tcgen05.st: thread i of the warp writes TMEM lane (base_lane + i), 16 / 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]: A = 128 lanes (rows) x 8 columns of packed bf16 pairs per K = 16 step
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Item {
+  int b, h, q0, n_keys, n_kt;
+  bool active1;      // the second query tile of the block exists
+};
+
+__device__ __forceinline__ Item decode_item(int item, int ordinal, const int* len_cache, int n_qblk, int n_head,
+                                            int seq_len, const int* __restrict__ kv_len) {
+  Item it;
+  const int qb = item % n_qblk;
+  const int bh = item / n_qblk;
+  it.h = bh % n_head;
+  it.b = bh / n_head;
+  it.q0 = qb * 2 * kQTile;
+  it.n_keys = min(max(ordinal < kLenCache ? len_cache[ordinal] : __ldg(kv_len + it.b), 1), seq_len);
+  it.n_kt = (it.n_keys + kKTile - 1) / kKTile;
+  it.active1 = it.q0 + kQTile < seq_len;
+  return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                 const __grid_constant__ CUtensorMap tmap_ctx, const int* __restrict__ kv_len, int seq_len,
+                 int d_model, int n_head, int n_qblk, int n_items) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* sptr = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bars = sbase + kOffBar;
+  auto q_full = [&](int buf, int w) { return bars + 8u * (buf * 2 + w); };
+  auto q_empty = [&](int buf, int w) { return bars + 8u * (4 + buf * 2 + w); };
+  auto kv_full = [&](int s) { return bars + 8u * (8 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (8 + kKvStages + s); };
+  // per group (8 each).  One phase of s_full / p_full per key-tile step of the group (parity = step & 1); one phase of
+  // o_full / l_full / o_free per use of an O buffer (parity = (use >> 1) & 1, use = ordinal of the item among the
+  // items in which the group has a query tile).
+  const uint32_t gb = bars + 8u * (8 + 2 * kKvStages);
+  auto s_full = [&](int w) { return gb + 8u * (w * 8); };              // MMA commit: S(step) is in TMEM
+  auto p_full = [&](int w) { return gb + 8u * (w * 8 + 1); };          // 4 softmax warps: P(step) is in TMEM
+  auto o_full = [&](int w, int ob) { return gb + 8u * (w * 8 + 2 + ob); };   // MMA commit: last P.V of the item retired
+  auto l_full = [&](int w, int ob) { return gb + 8u * (w * 8 + 4 + ob); };   // 4 softmax warps: 1 / l is in smem
+  auto o_free = [&](int w, int ob) { return gb + 8u * (w * 8 + 6 + ob); };   // 4 epilogue warps: O and 1 / l were read
+  const uint32_t tmem_slot = bars + 8u * kNumBars;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int* len_cache = reinterpret_cast<int*>(sptr + kOffLen);
+  for (int n = tid; n < kLenCache; n += kThreads) {
+    const long long item = (long long)blockIdx.x + (long long)n * gridDim.x;
+    if (item < n_items) len_cache[n] = __ldg(kv_len + (int)(item / n_qblk) / n_head);
+  }
+  if (tid == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_kv);
+    prefetch_tmap(&tmap_ctx);
+    for (int i = 0; i < 4; ++i) { mbar_init(q_full(i >> 1, i & 1), 1); mbar_init(q_empty(i >> 1, i & 1), 1); }
+    for (int s = 0; s < kKvStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(s_full(w), 1);
+      mbar_init(p_full(w), 4);
+      for (int ob = 0; ob < 2; ++ob) { mbar_init(o_full(w, ob), 1); mbar_init(l_full(w, ob), 4); mbar_init(o_free(w, ob), 4); }
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // (setmaxnreg at the top of each role's branch: ptxas derives the register limit of a region from the setmaxnreg that
+  // dominates it; the two 80-register warpgroups release before the softmax warpgroups can grow)
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    if (warp == 14) {
+      // ============================ TMA producer ============================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t kv_phase = 0;
+        int n_done = 0;
+        uint32_t q_par = 0;                         // bit (buf * 2 + w): parity of the fills of that Q buffer
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
+          const Item it = decode_item(item, n_done, len_cache, n_qblk, n_head, seq_len, kv_len);
+          const int buf = n_done & 1;
+          const int row_base = it.b * seq_len;
+          for (int w = 0; w < 2; ++w) {
+            if (w == 1 && !it.active1) continue;
+            const uint32_t qph = (q_par >> (buf * 2 + w)) & 1;
+            q_par ^= 1u << (buf * 2 + w);
+            mbar_wait(q_empty(buf, w), qph ^ 1);
+            mbar_arrive_expect_tx(q_full(buf, w), kQTile * kHd * 2);
+            tma_load_2d(sbase + kOffQ + (buf * 2 + w) * 16384, &tmap_q, q_full(buf, w), it.h * kHd,
+                        row_base + it.q0 + w * kQTile);
+          }
+          for (int j = 0; j < it.n_kt; ++j) {
+            mbar_wait(kv_empty(stage), kv_phase ^ 1);
+            const uint32_t kdst = sbase + kOffKV + stage * 32768;
+            mbar_arrive_expect_tx(kv_full(stage), 32768);
+            // rows past the utterance (or past the batch: zero fill) carry finite values and meet P = 0
+            tma_load_2d(kdst, &tmap_kv, kv_full(stage), d_model + it.h * kHd, row_base + j * kKTile);
+            tma_load_2d(kdst + 16384, &tmap_kv, kv_full(stage), 2 * d_model + it.h * kHd, row_base + j * kKTile);
+            if (++stage == kKvStages) { stage = 0; kv_phase ^= 1; }
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp < 14) {
+      // ============================ MMA issuers: warp 12 -> group 0, warp 13 -> group 1 ============================
+      // Order per group: S(0) | P.V(0) S(1) | P.V(1) S(2) | ...  P(g) lives on top of S(g), so S(g+1) is issued right
+      // behind P.V(g): tcgen05.mma of one thread execute in issue order, which is what keeps S(g+1) from overwriting
+      // P(g) before P.V(g) has read it.  p_full(g) also says that every softmax thread has pulled S(g) out of TMEM.
+      auto issuer = [&](auto group) {
+        constexpr int w = decltype(group)::value;
+        constexpr uint32_t idesc_s = make_idesc_bf16(128, kKTile);
+        constexpr uint32_t idesc_o = make_idesc_bf16(128, kHd) | (1u << 16);     // V: MN-major B operand
+        struct Cursor {
+          int item, j, n_done;      // work item, key tile inside it, ordinal of the item on this CTA
+          int stage;                // K/V ring stage of the flattened key-tile sequence of this CTA
+          uint32_t phase;
+          int n_kt;
+          bool valid;
+          bool virt;                // group 1 has no query tile in this item: its stages are walked, not used
+        };
+        auto load_item = [&](Cursor& c) {
+          c.valid = c.item < n_items;
+          c.virt = false;
+          if (c.valid) {
+            const Item it = decode_item(c.item, c.n_done, len_cache, n_qblk, n_head, seq_len, kv_len);
+            c.n_kt = it.n_kt;
+            c.virt = w == 1 && !it.active1;
+          }
+        };
+        auto advance = [&](Cursor& c) {
+          if (++c.stage == kKvStages) { c.stage = 0; c.phase ^= 1; }
+          if (++c.j == c.n_kt) {
+            c.j = 0;
+            c.item += gridDim.x;
+            ++c.n_done;
+            load_item(c);
+          }
+        };
+        Cursor sc;
+        sc.item = blockIdx.x; sc.j = 0; sc.n_done = 0; sc.stage = 0; sc.phase = 0; sc.n_kt = 1;
+        load_item(sc);
+        Cursor pc = sc;
+        int g_s = 0, g_p = 0;                 // per-group step indices of the next S and the next P.V
+        uint32_t q_fill0 = 0, q_fill1 = 0;    // consumed fills of Q buffers 0 / 1 of this group
+        uint32_t uses = 0;                    // items of this group whose P.V sequence has started
+        const uint32_t q_base = sbase + kOffQ + w * 16384;
+        const uint32_t s_tmem = tmem_base + w * 128;
+        while (pc.valid) {
+          if (w == 1 && pc.virt) {
+            // an item without a query tile for this group: every K/V stage of it is still observed and handed back in
+            // order (a consumer that jumps over uses of a parity-tracked mbarrier can alias a pending phase)
+            const int n = pc.n_kt;
+            for (int k = 0; k < n; ++k) {
+              mbar_wait(kv_full(pc.stage), pc.phase);
+              if (lane == 0) mbar_arrive(kv_empty(pc.stage));
+              __syncwarp();
+              advance(pc);
+            }
+            sc = pc;
+            continue;
+          }
+          if (sc.valid && !(w == 1 && sc.virt) && g_s < g_p + 1) {
+            // ---- S(g_s) = Q K^T ----
+            const int buf = sc.n_done & 1;
+            mbar_wait(kv_full(sc.stage), sc.phase);
+            if (sc.j == 0) mbar_wait(q_full(buf, w), (buf ? q_fill1 : q_fill0) & 1);
+            tc_fence_after();
+            const bool last_of_item = sc.j == sc.n_kt - 1;
+            if (elect_one()) {
+              const uint64_t qd = make_smem_desc_sw128(q_base + buf * 32768);
+              const uint64_t kd = make_smem_desc_sw128(sbase + kOffKV + sc.stage * 32768);
+#pragma unroll
+              for (int k = 0; k < kHd / 16; ++k) umma_bf16(s_tmem, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+              umma_commit(s_full(w));
+              if (last_of_item) umma_commit(q_empty(buf, w));
+            }
+            __syncwarp();
+            if (last_of_item) { if (buf) ++q_fill1; else ++q_fill0; }
+            ++g_s;
+            advance(sc);
+          }
+          // ---- O += P(g_p) V ----
+          {
+            const int ob = uses & 1;
+            mbar_wait(p_full(w), (uint32_t)g_p & 1);
+            if (pc.j == 0) mbar_wait(o_free(w, ob), ((uses >> 1) & 1) ^ 1);    // the epilogue has drained this O buffer
+            tc_fence_after();
+            const bool last_of_item = pc.j == pc.n_kt - 1;
+            if (elect_one()) {
+              const uint32_t o_tmem = tmem_base + 256 + (w * 2 + ob) * kHd;
+              const uint64_t vd = make_smem_desc_sw128(sbase + kOffKV + pc.stage * 32768 + 16384);
+#pragma unroll
+              for (int k = 0; k < kKTile / 16; ++k) {
+                // A: 16 keys = 8 TMEM columns of bf16 pairs; B: 16 keys = 16 rows of 128 bytes of the MN-major V tile
+                umma_bf16_ts(o_tmem, s_tmem + 8 * k, vd + 128 * k, idesc_o, (k | pc.j) != 0);
+              }
+              umma_commit(kv_empty(pc.stage));                 // the second arrival comes from the other group's issuer
+              if (last_of_item) umma_commit(o_full(w, ob));
+            }
+            __syncwarp();
+            if (last_of_item) ++uses;
+            ++g_p;
+            advance(pc);
+          }
+        }
+      };
+      if (warp == 12) issuer(std::integral_constant<int, 0>{});
+      else issuer(std::integral_constant<int, 1>{});
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // ============================ epilogue warpgroup ============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int sw = r & 7;
+    const float* xch = reinterpret_cast<const float*>(sptr + kOffX);
+    uint32_t uses[2] = {0, 0};
+    int ordinal = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
+      const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (w == 1 && !it.active1) continue;
+        const int ob = uses[w] & 1;
+        const uint32_t ph = (uses[w] >> 1) & 1;
+        ++uses[w];
+        mbar_wait(l_full(w, ob), ph);
+        const float inv = xch[(w * 2 + ob) * 128 + r];
+        mbar_wait(o_full(w, ob), ph);
+        tc_fence_after();
+        // the previous TMA store out of this group's staging tile must have read it
+        if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        named_bar_sync(1, 128);
+        const uint32_t srow = sbase + kOffOut + w * 16384 + r * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t o[32];
+          tmem_ld32(tmem_base + 256 + (w * 2 + ob) * kHd + half * 32 + lane_off, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t a0 = pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+            const uint32_t a1 = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+            const uint32_t a2 = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+            const uint32_t a3 = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(srow + (((half * 4 + c) ^ sw) << 4)), "r"(a0), "r"(a1), "r"(a2), "r"(a3) : "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free(w, ob));     // O buffer and 1 / l slot may be reused
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == 8 && lane == 0) {
+          // rows past the end of the utterance are clipped by the 3-D map
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmap_ctx)), "r"(sbase + kOffOut + w * 16384),
+                         "r"(it.h * kHd), "r"(it.q0 + w * kQTile), "r"(it.b) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // ============================ softmax groups (thread = query row) ============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
+    const int w = warp >> 2;                       // group / query tile
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;             // row inside the tile = TMEM lane
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t s_tmem = tmem_base + w * 128 + lane_off;
+    float* xch = reinterpret_cast<float*>(sptr + kOffX);
+    uint32_t g = 0;                                // per-group step index
+    uint32_t uses = 0;
+    int ordinal = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
+      const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
+      if (w == 1 && !it.active1) continue;
+      const int ob = uses & 1;
+      const uint32_t o_tmem = tmem_base + 256 + (w * 2 + ob) * kHd + lane_off;
+      // m_ref: the maximum the exponents are taken against.  It is only raised (and O / l rescaled) when the running
+      // maximum exceeds it by more than 2^kRaise: P <= 2^kRaise stays far inside bf16 / fp32 range, and O in TMEM is
+      // touched by the CUDA cores only on those rare steps.
+      constexpr float kRaise = 40.0f;
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < it.n_kt; ++j, ++g) {
+        mbar_wait(s_full(w), g & 1);
+        tc_fence_after();
+        uint32_t v[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, v[c]);
+        tmem_ld_wait();
+        const int valid = it.n_keys - j * kKTile;      // my columns < valid are real keys
+        if (valid < kKTile) {
+          // last tile of the utterance only (a real branch: the full tiles must not pay 128 compare / select pairs)
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= valid) v[c >> 5][c & 31] = 0xff800000u;        // -inf: exp2 gives exactly 0
+        }
+        float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          tm0 = max3(tm0, __uint_as_float(v[c >> 5][c & 31]), __uint_as_float(v[c >> 5][(c & 31) + 1]));
+          tm1 = max3(tm1, __uint_as_float(v[c >> 5][(c & 31) + 2]), __uint_as_float(v[c >> 5][(c & 31) + 3]));
+        }
+        const float tile_max = fmaxf(tm0, tm1);
+        if (j == 0) {
+          m_ref = tile_max;                            // O is overwritten by the first P.V of the item
+        } else {
+          const bool raise = (tile_max - m_ref) * kLog2e > kRaise;
+          if (__any_sync(0xffffffffu, raise)) {
+            // s_full(g) was committed behind P.V(g - 1): O holds every earlier step and no MMA is in flight on it
+            const float factor = raise ? ex2_mufu((m_ref - tile_max) * kLog2e) : 1.0f;
+            if (raise) m_ref = tile_max;
+            l_run *= factor;
+            // (rare path: 8 columns at a time so that the 128 live scores are not spilled around it)
+#pragma unroll 1
+            for (int c = 0; c < kHd; c += 8) {
+              uint32_t o[8];
+              tmem_ld8(o_tmem + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * factor);
+              tmem_st8(o_tmem + c, o);
+            }
+          }
+        }
+        const float m_scaled = m_ref * kLog2e;
+        float2 l0 = make_float2(0.f, 0.f), l1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // P columns 16 c .. 16 c + 15 cover score columns that are already in registers (16 c + 15 < 32 (c + 1))
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            // packed fp32x2 arithmetic (FFMA2 / FADD2): half the issue slots of the scalar forms
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * e]), __uint_as_float(v[c][2 * e + 1])),
+                                        make_float2(kLog2e, kLog2e), make_float2(-m_scaled, -m_scaled));
+            const float x0 = x.x, x1 = x.y;
+            // (the masked last tile of an utterance keeps every exponential on the MUFU: exp2(-inf) must be exactly 0)
+            const bool fma_pipe = (e & 3) < (MHA2_POLY + 1) / 2 && valid >= kKTile;
+            const float p0 = fma_pipe ? ex2_fma(x0) : ex2_mufu(x0);
+            const float p1 = (fma_pipe && ((e & 3) * 2 + 1 < MHA2_POLY)) ? ex2_fma(x1) : ex2_mufu(x1);
+            if (e & 1) l1 = __fadd2_rn(l1, make_float2(p0, p1));
+            else l0 = __fadd2_rn(l0, make_float2(p0, p1));
+            pk[e] = pack_bf16x2(p0, p1);
+          }
+          tmem_st16(s_tmem + c * 16, pk);
+        }
+        l_run += (l0.x + l0.y) + (l1.x + l1.y);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(w));
+      }
+      // end of the item: hand 1 / l to the epilogue warpgroup.  The slot (and the O buffer) were last used two items of
+      // this group ago; o_free says the epilogue is done with both.
+      mbar_wait(o_free(w, ob), ((uses >> 1) & 1) ^ 1);
+      xch[(w * 2 + ob) * 128 + r] = 1.0f / l_run;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(l_full(w, ob));
+      ++uses;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace
+
+extern "C" int stac_mha_bf16_v2(const uint16_t* qkv, const int32_t* kv_len, int64_t batch, int64_t seq_len,
+                                int64_t d_model, int64_t n_head, uint16_t* ctx, void* stream) {
+  STAC_REQUIRE(qkv && kv_len && ctx && batch > 0 && batch < 65536 && seq_len > 0);
+  if (d_model != n_head * kHd || n_head > 65535 || batch * seq_len >= (1ll << 31)) return STAC_ERR_UNSUPPORTED_SHAPE;
+  const int64_t n_qblk = ceil_div64(seq_len, 2 * kQTile);
+  const int64_t n_items = batch * n_head * n_qblk;
+  if (n_items >= (1ll << 31)) return STAC_ERR_UNSUPPORTED_SHAPE;
+  CUtensorMap tq, tkv, tctx;
+  const uint64_t dims[2] = {(uint64_t)(3 * d_model), (uint64_t)(batch * seq_len)};
+  const uint64_t str[1] = {(uint64_t)(3 * d_model) * 2};
+  {
+    const uint32_t box[2] = {kHd, kQTile};
+    int r = encode_map(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 2, dims, str, box);
+    if (r != STAC_OK) return r;
+  }
+  {
+    const uint32_t box[2] = {kHd, kKTile};
+    int r = encode_map(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 2, dims, str, box);
+    if (r != STAC_OK) return r;
+  }
+  {
+    // ctx [B][T][d_model]: a tile that runs past the end of its utterance is clipped in the T dimension
+    const uint64_t cdims[3] = {(uint64_t)d_model, (uint64_t)seq_len, (uint64_t)batch};
+    const uint64_t cstr[2] = {(uint64_t)d_model * 2, (uint64_t)seq_len * d_model * 2};
+    const uint32_t cbox[3] = {kHd, kQTile, 1};
+    int r = encode_map(&tctx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, ctx, 3, cdims, cstr, cbox);
+    if (r != STAC_OK) return r;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(mha2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int grid = (int)std::min<int64_t>(n_items, stac_grid_limit());
+  mha2_bf16_kernel<<<grid, kThreads, kSmemBytes, as_stream(stream)>>>(tq, tkv, tctx, kv_len, (int)seq_len,
+                                                                    (int)d_model, (int)n_head, (int)n_qblk,
+                                                                    (int)n_items);
+  STAC_LAUNCH_CHECK();
+}

@@ -8,6 +8,7 @@ a8/a9 CTC head.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -23,6 +24,8 @@ CNN_CH = 256
 F1, F2 = 40, 20
 PRECISIONS = ("fp32", "bf16")
 FUSED_FFN = True       # tests flip this to compare against the two-GEMM path
+# Experimental second attention kernel (csrc/attention_tc2.cu).  Off unless asked for: it has not run on a B200 yet.
+MHA_V2 = os.environ.get("STAC_MHA_V2", "0") == "1"
 
 # Optional launch tracing: bench.py sets TRACE to a list to get (kernel, label, start_event, end_event)
 # per launch; LAUNCHES counts kernel launches either way.
@@ -399,8 +402,11 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
             _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_bf16=hbuf)
             _gemm(hbuf, L.w_qkv, L.b_qkv, qkv, prec, tag="qkv")
             # V is read straight from the packed projection (MN-major B operand): no transposed copy
-            _call("stac_mha_bf16", ptr(qkv), ptr(None), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
-                                      stream())
+            if MHA_V2:
+                _call("stac_mha_bf16_v2", ptr(qkv), ptr(kv_len, torch.int32), b, t2, d, h, ptr(ctx), stream())
+            else:
+                _call("stac_mha_bf16", ptr(qkv), ptr(None), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
+                      stream())
         _gemm(ctx, L.w_o, L.b_o, x, prec, resid=x, tag="out_proj")
         if prec == "fp32":
             _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_f32=hbuf)

@@ -1,4 +1,6 @@
 """tcgen05 flash attention (stac_mha_bf16) against an fp32 softmax-attention with -inf key padding."""
+import os
+
 import pytest
 import torch
 
@@ -32,4 +34,33 @@ def test_mha_bf16(t, lens, d, h, use_vt):
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, d)
     got = ctx.float().cpu()
     assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
+
+
+# stac_mha_bf16_v2 (csrc/attention_tc2.cu) was written after the round-1 GPU budget was spent: it compiles for sm_100a but
+# has not run on a B200 yet, so it is not part of the default GPU suite.  STAC_EXPERIMENTAL=1 enables it
+# (tools/gpu_v2_check.sh runs it under a time limit, then times it against stac_mha_bf16).
+@pytest.mark.skipif(os.environ.get("STAC_EXPERIMENTAL") != "1", reason="attention v2 not yet run on a B200")
+@pytest.mark.parametrize("t,lens,d,h", [(128, [128], 64, 1), (256, [256], 64, 1), (251, [251, 100, 1], 256, 4),
+                                         (64, [64, 33], 128, 2), (130, [129, 130, 5], 256, 4),
+                                         (751, [751, 400], 256, 4), (300, [300, 299], 512, 8),
+                                         (300, [300 - 3 * i for i in range(40)], 256, 4),
+                                         (100, [100 - i for i in range(90)], 128, 2), (1501, [1501, 1200], 128, 2)])
+def test_mha_bf16_v2(t, lens, d, h):
+    g = torch.Generator().manual_seed(t + d)
+    b = len(lens)
+    qkv = (torch.randn(b * t, 3 * d, generator=g)).to(torch.bfloat16)
+    kv = torch.tensor(lens, dtype=torch.int32)
+    ctx = torch.full((b * t, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    guard = torch.full((4096,), 7.0, device="cuda", dtype=torch.bfloat16)      # allocated right behind ctx
+    qkv_d, kv_d = qkv.cuda(), kv.cuda()
+    ops.check(ops.lib().stac_mha_bf16_v2(ops.ptr(qkv_d), ops.ptr(kv_d), b, t, d, h, ops.ptr(ctx), ops.stream()))
+    torch.cuda.synchronize()
+    q, k, v = (x.float().view(b, t, h, 64).transpose(1, 2) for x in qkv.split(d, dim=-1))
+    mask = torch.arange(t)[None, :] >= kv[:, None]
+    s = (q @ k.transpose(-1, -2)).masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(b * t, d)
+    got = ctx.float().cpu()
+    assert not torch.isnan(got).any()
+    assert (guard == 7.0).all()
     assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)

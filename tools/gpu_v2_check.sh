@@ -1,0 +1,16 @@
+#!/bin/bash
+# First thing to run on a B200 next round (one gpurun call, one GPU):
+#   gpurun --timeout 900 -- bash tools/gpu_v2_check.sh
+# Runs the parity tests of the kernels that were written after the round-1 GPU budget was spent (STAC_EXPERIMENTAL=1),
+# each under its own time limit (every mbarrier wait in them traps after ~2 s, so a protocol bug is a launch failure, not
+# a hang), then times attention v2 against the default kernel and the whole path with STAC_MHA_V2=1.
+mkdir -p gpurun_out
+export STAC_EXPERIMENTAL=1
+timeout 300 python -m pytest tests/test_gpu_tc_attention.py -q -x -m gpu -k v2 > gpurun_out/v2_mha_tests.log 2>&1
+echo "attention v2 tests rc $?"; tail -5 gpurun_out/v2_mha_tests.log
+timeout 300 python -m pytest tests/test_gpu_turns.py -q -x -m gpu > gpurun_out/v2_turn_tests.log 2>&1
+echo "turn-detection tests rc $?"; tail -5 gpurun_out/v2_turn_tests.log
+timeout 120 python tools/bench_mha.py stac_speech_translation_b200/libstac_b200.so > gpurun_out/v2_mha_bench.log 2>&1
+echo "bench_mha rc $?"; cat gpurun_out/v2_mha_bench.log
+STAC_MHA_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v2_bench.json 2> gpurun_out/v2_bench.err
+echo "bench (STAC_MHA_V2=1) rc $?"; tail -c 1200 gpurun_out/v2_bench.json
