@@ -64,15 +64,16 @@ __device__ __forceinline__ float ex2_mufu(float x) {
   return y;
 #endif
 }
-// 2^x on the FMA pipe for x in [-126, 126]: round-to-nearest split x = n + f, |f| <= 0.5, cubic for 2^f (relative error
-// < 1e-4 after the minimax adjustment of the Taylor coefficients, far below bf16 resolution), exponent added as integer
+// 2^x on the FMA pipe for x in [-126, 126]: round-to-nearest split x = n + f, |f| <= 0.5, minimax cubic for 2^f with
+// p(0) = 1 (maximum relative error 1.0e-4, checked in float32 over [-126, 40]; bf16 resolution is 3.9e-3), exponent
+// added as an integer
 __device__ __forceinline__ float ex2_fma(float x) {
   x = fmaxf(x, -126.0f);
   const float t = x + 12582912.0f;                     // 1.5 * 2^23: the integer part lands in the low mantissa bits
   const float f = x - (t - 12582912.0f);
-  float p = 0.0558263f;
-  p = fmaf(p, f, 0.2402265f);
-  p = fmaf(p, f, 0.6931472f);
+  float p = 0.0550129f;
+  p = fmaf(p, f, 0.24221165f);
+  p = fmaf(p, f, 0.69328244f);
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
