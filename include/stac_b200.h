@@ -205,6 +205,18 @@ int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const float* bias
                        int64_t d_model, float* workspace, void* log_probs, int out_dtype, int32_t* argmax,
                        void* stream);
 
+/* ---------------------------------------------------------------------------
+ * turn detection -- replaces append_speaker_turns
+ *        (/root/reference/stac-st/inference.py:54-84): argmax, == turn / == xt, dense masks to the host, Python loop
+ *        over every frame.
+ * stac_argmax_rows: out[r] = first index of the row maximum (for callers that hold posteriors, not greedy ids).
+ * stac_ctc_spikes:  ids int32 [B, T2] -> ascending flat positions b * T2 + j of the frames equal to turn_id
+ *        (spikes_turn) / xt_id (spikes_xt), both int32 [B * T2] capacity, and their counts n_out int32 [2];
+ *        row_counts int32 [B][2] is workspace.  The order is the one the reference's loop appends RTTM lines in. */
+int stac_argmax_rows(const float* x, int64_t rows, int64_t cols, int32_t* out, void* stream);
+int stac_ctc_spikes(const int32_t* ids, int64_t batch, int64_t t2, int32_t turn_id, int32_t xt_id,
+                    int32_t* row_counts, int32_t* spikes_turn, int32_t* spikes_xt, int32_t* n_out, void* stream);
+
 /* fp32 -> bf16 conversion (weight packing / activation hand-off) */
 int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);
 

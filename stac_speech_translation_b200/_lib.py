@@ -7,7 +7,7 @@ device the call raises.  Build the library with ``python -m stac_speech_translat
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 from pathlib import Path
 
 import torch
@@ -47,6 +47,8 @@ _SIGNATURES = {
     "stac_log_softmax": (c_int, [_P, c_int64, c_int64, _P, _P, _P]),
     "stac_ctc_head_workspace_floats": (c_int64, [c_int64, c_int64]),
     "stac_ctc_head_bf16": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int, _P, _P]),
+    "stac_argmax_rows": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "stac_ctc_spikes": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "stac_cast_bf16": (c_int, [_P, c_int64, _P, _P]),
 }
 

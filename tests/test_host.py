@@ -174,3 +174,23 @@ def test_fbank_tables_match_oracle_filterbank():
     for m in range(80):
         dense[start[m]:start[m] + count[m], m] = w[m, :count[m]]
     assert torch.equal(dense, fb)                                    # bit-identical sparse copy of the matrix
+
+
+def test_turn_detection_host_side():
+    """turns.rttm_line formats a spike exactly as the reference's append_speaker_turns does (golden lines produced by the
+    reference function itself), and the device entry points refuse CPU tensors (no CPU fallback)."""
+    import json
+    import os
+    from stac_speech_translation_b200 import turns
+    from stac_speech_translation_b200._lib import StacB200Error
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "turns_reference.json")))
+    for c in cases:
+        ids = np.asarray(c["ids"])
+        t2 = ids.shape[1]
+        flat = ids.reshape(-1)
+        assert [turns.rttm_line(c["utt"][f // t2], f % t2) for f in np.nonzero(flat == 7)[0]] == c["turn_rttm"]
+        assert [turns.rttm_line(c["utt"][f // t2], f % t2) for f in np.nonzero(flat == 8)[0]] == c["xt_rttm"]
+    with pytest.raises(StacB200Error):
+        turns.append_speaker_turns(["a-b-0000100-c"], torch.zeros(1, 4, dtype=torch.int32), 7, 8, [], [])
+    with pytest.raises(StacB200Error):
+        turns.greedy_ids(torch.zeros(1, 4, 9))

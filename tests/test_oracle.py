@@ -214,3 +214,22 @@ def test_oracle_glue_against_reference_generated_fixture():
         assert rel_l2(sp.EncoderWrapper(tr)(src, wl), torch.from_numpy(d["enc_encode"])) < 1e-6
     # the two mask rules really differ on this fixture (0.5 * 37 = 18.5: floor+1 = 19 keys vs round = 18)
     assert rel_l2(torch.from_numpy(d["enc_forward"])[2], torch.from_numpy(d["enc_encode"])[2]) > 1e-4
+
+
+def test_turn_detection_oracle_matches_the_reference_function():
+    """oracle/turns.py against the output of the reference's own append_speaker_turns (inference.py:54-84), recorded by
+    tests/golden/make_turns_golden.py; ids and one-hot-like posteriors give the same lines."""
+    import json
+    from oracle import turns as oturns
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "turns_reference.json")))
+    assert len(cases) >= 4
+    for c in cases:
+        ids = np.asarray(c["ids"])
+        for as_posteriors in (False, True):
+            x = ids
+            if as_posteriors:
+                x = np.full(ids.shape + (c["vocab"],), -20.0, dtype=np.float32)
+                np.put_along_axis(x, ids[..., None], -0.1, axis=2)
+            turn, xt = [], []
+            oturns.append_speaker_turns(c["utt"], x, 7, 8, turn, xt)
+            assert turn == c["turn_rttm"] and xt == c["xt_rttm"]
