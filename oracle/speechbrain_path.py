@@ -464,13 +464,122 @@ class TransformerEncoder(nn.Module):
         return self.norm(output), attention_lst
 
 
-def length_to_mask(length, max_len=None):
-    """speechbrain/dataio/dataio.py::length_to_mask."""
+# --------------------------------------------------------------------------
+# Decoder side (the consumer right behind the path):
+# speechbrain.lobes.models.transformer.Transformer.{TransformerDecoderLayer, TransformerDecoder,
+# NormalizedEmbedding, get_lookahead_mask, get_key_padding_mask}, as reached from
+# /root/reference/stac-st/modules/TransformerMultiTask.py:185-209 (forward) and :234-271 (decode).
+# Same pinning status as the encoder classes: SpeechBrain's arithmetic restated from memory of ~v0.5.14
+# (attribute names included: the cross-attention module really is spelled ``mutihead_attn`` there), the
+# in-repo glue pinned by the reference's own decode()/forward() (tests/golden/make_decoder_golden.py).
+# --------------------------------------------------------------------------
+class _Embedding(nn.Module):
+    """speechbrain/nnet/embedding.py::Embedding (wraps nn.Embedding as ``.Embedding``, padding_idx = blank_id)."""
+
+    def __init__(self, num_embeddings, embedding_dim, blank_id=0):
+        super().__init__()
+        self.Embedding = nn.Embedding(num_embeddings, embedding_dim, padding_idx=blank_id)
+
+    def forward(self, x):
+        return self.Embedding(x.long())
+
+
+class NormalizedEmbedding(nn.Module):
+    """Embedding scaled by sqrt(d_model) (Transformer.py::NormalizedEmbedding)."""
+
+    def __init__(self, d_model, vocab):
+        super().__init__()
+        self.emb = _Embedding(num_embeddings=vocab, embedding_dim=d_model, blank_id=0)
+        self.d_model = d_model
+
+    def forward(self, x):
+        return self.emb(x) * math.sqrt(self.d_model)
+
+
+def get_lookahead_mask(padded_input):
+    """Float mask [L, L]: 0 on and below the diagonal, -inf above (Transformer.py::get_lookahead_mask)."""
+    seq_len = padded_input.shape[1]
+    mask = (torch.triu(torch.ones((seq_len, seq_len), device=padded_input.device)) == 1).transpose(0, 1)
+    mask = mask.float().masked_fill(mask == 0, float("-inf")).masked_fill(mask == 1, float(0.0))
+    return mask.detach().to(padded_input.device)
+
+
+def get_key_padding_mask(padded_input, pad_idx):
+    """Bool mask [B, L], True where the token is padding (Transformer.py::get_key_padding_mask)."""
+    if len(padded_input.shape) == 4:
+        bz, time, ch1, ch2 = padded_input.shape
+        padded_input = padded_input.reshape(bz, time, ch1 * ch2)
+    key_padded_mask = padded_input.eq(pad_idx).to(padded_input.device)
+    return key_padded_mask.detach()
+
+
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, d_ffn, nhead, d_model, dropout, activation, normalize_before):
+        super().__init__()
+        self.self_attn = MultiheadAttention(nhead=nhead, d_model=d_model, dropout=dropout)
+        self.mutihead_attn = MultiheadAttention(nhead=nhead, d_model=d_model, dropout=dropout)
+        self.pos_ffn = PositionalwiseFeedForward(d_ffn=d_ffn, input_size=d_model,
+                                                 dropout=dropout, activation=activation)
+        self.norm1 = LayerNorm(d_model, eps=1e-6)
+        self.norm2 = LayerNorm(d_model, eps=1e-6)
+        self.norm3 = LayerNorm(d_model, eps=1e-6)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.normalize_before = normalize_before
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, pos_embs_tgt=None, pos_embs_src=None):
+        tgt1 = self.norm1(tgt) if self.normalize_before else tgt
+        tgt2, self_attn = self.self_attn(tgt1, tgt1, tgt1, attn_mask=tgt_mask,
+                                         key_padding_mask=tgt_key_padding_mask)
+        tgt = tgt + self.dropout1(tgt2)
+        if not self.normalize_before:
+            tgt = self.norm1(tgt)
+        tgt1 = self.norm2(tgt) if self.normalize_before else tgt
+        tgt2, multihead_attention = self.mutihead_attn(tgt1, memory, memory, attn_mask=memory_mask,
+                                                       key_padding_mask=memory_key_padding_mask)
+        tgt = tgt + self.dropout2(tgt2)
+        if not self.normalize_before:
+            tgt = self.norm2(tgt)
+        tgt1 = self.norm3(tgt) if self.normalize_before else tgt
+        tgt2 = self.pos_ffn(tgt1)
+        tgt = tgt + self.dropout3(tgt2)
+        if not self.normalize_before:
+            tgt = self.norm3(tgt)
+        return tgt, self_attn, multihead_attention
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, num_layers, nhead, d_ffn, d_model, dropout, activation, normalize_before):
+        super().__init__()
+        self.layers = nn.ModuleList([
+            TransformerDecoderLayer(d_ffn, nhead, d_model, dropout, activation, normalize_before)
+            for _ in range(num_layers)])
+        self.norm = LayerNorm(d_model, eps=1e-6)
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, pos_embs_tgt=None, pos_embs_src=None):
+        output = tgt
+        self_attns, multihead_attns = [], []
+        for dec_layer in self.layers:
+            output, self_attn, multihead_attn = dec_layer(
+                output, memory, tgt_mask=tgt_mask, memory_mask=memory_mask,
+                tgt_key_padding_mask=tgt_key_padding_mask, memory_key_padding_mask=memory_key_padding_mask,
+                pos_embs_tgt=pos_embs_tgt, pos_embs_src=pos_embs_src)
+            self_attns.append(self_attn)
+            multihead_attns.append(multihead_attn)
+        return self.norm(output), self_attns, multihead_attns
+
+
+def length_to_mask(length, max_len=None, dtype=None):
+    """speechbrain/dataio/dataio.py::length_to_mask (the mask takes the dtype of `length` unless one is given, which
+    is what lets the reference write ``1 - length_to_mask(enc_len)``, TransformerMultiTask.py:250)."""
     if max_len is None:
         max_len = length.max().long().item()
     mask = torch.arange(max_len, device=length.device, dtype=length.dtype).expand(
         len(length), max_len) < length.unsqueeze(1)
-    return mask
+    return torch.as_tensor(mask, dtype=length.dtype if dtype is None else dtype, device=length.device)
 
 
 class TransformerMultiTask(nn.Module):
@@ -479,8 +588,12 @@ class TransformerMultiTask(nn.Module):
     ``encode``   follows :273-309 (mask ``j > floor(wav_len*T)``).
     ``forward_encoder`` follows the encoder half of ``forward`` :144-183 with
     ``make_masks`` :211-232 (mask ``~length_to_mask(round(wav_len*T))``).
-    The decoder (:185-209, :234-271) is out of scope for this path.
-    ``_init_params`` :311-314 re-initialises every dim>1 parameter with xavier_normal_.
+    ``forward`` (decoder half :185-209) and ``decode`` :234-271 run SpeechBrain's TransformerDecoder over the
+    encoder output.
+    ``_init_params`` :311-314 re-initialises every dim>1 parameter with xavier_normal_.  The decoder and the target
+    embedding are created and initialised under a forked random stream (after, not between, the encoder-side
+    modules) so that the encoder-side weights drawn for a given seed - which the committed golden files depend on -
+    are the same with and without a decoder; the distribution is the reference's.
     """
 
     def __init__(self, tgt_vocab, input_size, d_model=512, nhead=8,
@@ -495,11 +608,52 @@ class TransformerMultiTask(nn.Module):
             Linear(input_size=input_size, n_neurons=d_model, bias=True, combine_dims=False),
             nn.Dropout(dropout))
         self._init_params()
+        self.decoder = None
+        self.custom_tgt_module = None
+        if num_decoder_layers > 0:
+            with torch.random.fork_rng(devices=[]):
+                torch.manual_seed(torch.initial_seed() + 1)
+                self.decoder = TransformerDecoder(num_decoder_layers, nhead, d_ffn, d_model, dropout, activation,
+                                                  normalize_before)
+                self.custom_tgt_module = _Layers(NormalizedEmbedding(d_model, tgt_vocab))
+                for m in (self.decoder, self.custom_tgt_module):
+                    for p in m.parameters():
+                        if p.dim() > 1:
+                            nn.init.xavier_normal_(p)
 
     def _init_params(self):
         for p in self.parameters():
             if p.dim() > 1:
                 nn.init.xavier_normal_(p)
+
+    def forward(self, src, tgt, wav_len=None, pad_idx=0):
+        """:144-209: encoder with the make_masks rule, then the decoder over the whole target."""
+        encoder_out = self.forward_encoder(src, wav_len)
+        src_key_padding_mask = None
+        if wav_len is not None:
+            abs_len = torch.round(wav_len * encoder_out.shape[1])
+            src_key_padding_mask = ~length_to_mask(abs_len, max_len=encoder_out.shape[1]).bool()
+        tgt_key_padding_mask = get_key_padding_mask(tgt, pad_idx=pad_idx)
+        tgt_mask = get_lookahead_mask(tgt)
+        tgt = self.custom_tgt_module(tgt)
+        tgt = tgt + self.positional_encoding(tgt)
+        decoder_out, _, _ = self.decoder(tgt=tgt, memory=encoder_out, memory_mask=None, tgt_mask=tgt_mask,
+                                         tgt_key_padding_mask=tgt_key_padding_mask,
+                                         memory_key_padding_mask=src_key_padding_mask)
+        return encoder_out, decoder_out
+
+    @torch.no_grad()
+    def decode(self, tgt, encoder_out, enc_len=None):
+        """:234-271: one decoding step = the whole decoder over the whole prefix."""
+        tgt_mask = get_lookahead_mask(tgt)
+        src_key_padding_mask = None
+        if enc_len is not None:
+            src_key_padding_mask = (1 - length_to_mask(enc_len)).bool()
+        tgt = self.custom_tgt_module(tgt)
+        tgt = tgt + self.positional_encoding(tgt)
+        prediction, self_attns, multihead_attns = self.decoder(
+            tgt, encoder_out, tgt_mask=tgt_mask, memory_key_padding_mask=src_key_padding_mask)
+        return prediction, multihead_attns[-1]
 
     def _embed(self, src):
         if src.dim() == 4:

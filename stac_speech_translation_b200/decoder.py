@@ -1,0 +1,203 @@
+"""Decoder side of ``modules.Transformer``: parameters under SpeechBrain's names and the
+orchestration of one decoder pass on the device.
+
+Mirrors what /root/reference/stac-st/modules/TransformerMultiTask.py builds and runs:
+  * ``custom_tgt_module = ModuleList(NormalizedEmbedding(d_model, tgt_vocab))`` :139 and the
+    ``TransformerDecoder(num_decoder_layers, nhead, d_ffn, d_model, dropout, activation, normalize_before)`` that
+    ``TransformerInterface.__init__`` creates (:64-84), with SpeechBrain's attribute names so that a reference
+    checkpoint loads unchanged: ``decoder.layers.N.{self_attn,mutihead_attn}.att.*`` (sic),
+    ``decoder.layers.N.pos_ffn.ffn.{0,3}.*``, ``decoder.layers.N.norm{1,2,3}.norm.*``, ``decoder.norm.norm.*``,
+    ``custom_tgt_module.layers.0.emb.Embedding.weight``;
+  * ``decode(tgt, encoder_out, enc_len)`` :234-271 and the decoder half of ``forward`` :185-209: embedding * sqrt(d)
+    + positional encoding, N pre-LN layers (causal self-attention, cross-attention over the encoder output,
+    feed-forward), final LayerNorm; the head-averaged cross-attention weights of the last layer are returned because
+    the beam searcher receives them (``mutitask_decoder.py:126``).
+
+First correct path: fp32 on the CUDA cores in both precision modes (stac_gemm_f32, stac_layernorm, stac_embed_scale_pe,
+stac_attention_f32), the whole prefix per call exactly as the reference's ``forward_step`` asks for it.  None of the
+torch modules' ``forward`` is called; there is no CPU fallback.  Not yet run on a B200 (see csrc/decoder_f32.cu).
+"""
+from __future__ import annotations
+
+import math
+from ctypes import c_void_p
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import ACT_GELU_ERF, StacB200Error, ptr, stream
+from .convolution import _Holder, _params_version
+
+
+class _DecoderLayerParams(nn.Module):
+    def __init__(self, d_model, nhead, d_ffn, dropout, activation):
+        super().__init__()
+        self.self_attn = _Holder(att=nn.MultiheadAttention(d_model, nhead, dropout=dropout, bias=True))
+        self.mutihead_attn = _Holder(att=nn.MultiheadAttention(d_model, nhead, dropout=dropout, bias=True))
+        self.pos_ffn = _Holder(ffn=nn.Sequential(nn.Linear(d_model, d_ffn), activation(), nn.Dropout(dropout),
+                                                 nn.Linear(d_ffn, d_model)))
+        self.norm1 = _Holder(norm=nn.LayerNorm(d_model, eps=1e-6))
+        self.norm2 = _Holder(norm=nn.LayerNorm(d_model, eps=1e-6))
+        self.norm3 = _Holder(norm=nn.LayerNorm(d_model, eps=1e-6))
+
+
+class DecoderParams(nn.Module):
+    """``Transformer.decoder``: parameter tree of SpeechBrain's TransformerDecoder."""
+
+    def __init__(self, num_layers, d_model, nhead, d_ffn, dropout, activation):
+        super().__init__()
+        self.layers = nn.ModuleList([_DecoderLayerParams(d_model, nhead, d_ffn, dropout, activation)
+                                     for _ in range(num_layers)])
+        self.norm = _Holder(norm=nn.LayerNorm(d_model, eps=1e-6))
+
+
+class TgtModule(nn.Module):
+    """``Transformer.custom_tgt_module``: ModuleList(NormalizedEmbedding) -> ``layers.0.emb.Embedding.weight``."""
+
+    def __init__(self, d_model, vocab):
+        super().__init__()
+        self.layers = nn.ModuleList([_Holder(emb=_Holder(Embedding=nn.Embedding(vocab, d_model, padding_idx=0)))])
+
+    @property
+    def weight(self):
+        return self.layers[0].emb.Embedding.weight
+
+
+@dataclass
+class DecoderLayerWeights:
+    ln1_g: torch.Tensor
+    ln1_b: torch.Tensor
+    w_qkv: torch.Tensor      # self-attention in_proj [3d, d]; q rows (and bias) pre-scaled by 1/sqrt(64)
+    b_qkv: torch.Tensor
+    w_o: torch.Tensor
+    b_o: torch.Tensor
+    ln2_g: torch.Tensor
+    ln2_b: torch.Tensor
+    w_q2: torch.Tensor       # cross-attention query projection [d, d], pre-scaled
+    b_q2: torch.Tensor
+    w_kv2: torch.Tensor      # cross-attention key / value projection of the encoder output [2d, d]
+    b_kv2: torch.Tensor
+    w_o2: torch.Tensor
+    b_o2: torch.Tensor
+    ln3_g: torch.Tensor
+    ln3_b: torch.Tensor
+    w_1: torch.Tensor
+    b_1: torch.Tensor
+    w_2: torch.Tensor
+    b_2: torch.Tensor
+
+
+@dataclass
+class DecoderWeights:
+    d_model: int
+    nhead: int
+    vocab: int
+    emb: torch.Tensor        # [vocab, d]
+    pe: torch.Tensor         # [max_len, d]
+    layers: List[DecoderLayerWeights] = field(default_factory=list)
+    lnf_g: torch.Tensor = None
+    lnf_b: torch.Tensor = None
+
+
+def pack_decoder(decoder: DecoderParams, tgt_module: TgtModule, pe: torch.Tensor, nhead: int) -> DecoderWeights:
+    f = lambda t: t.detach().float().contiguous()
+    emb = f(tgt_module.weight)
+    d = emb.shape[1]
+    if d % nhead != 0 or d // nhead != 64:
+        raise StacB200Error("attention kernels are specialised for head_dim 64 (all STAC-ST sizes)")
+    dw = DecoderWeights(d, nhead, emb.shape[0], emb, f(pe).reshape(-1, d))
+    scale = 1.0 / math.sqrt(64.0)   # exact power of two: folding it into W_q / b_q is lossless
+    for L in decoder.layers:
+        sa, ca, ffn = L.self_attn.att, L.mutihead_attn.att, L.pos_ffn.ffn
+        wq = sa.in_proj_weight.detach().float().clone()
+        bq = sa.in_proj_bias.detach().float().clone()
+        wq[:d] *= scale
+        bq[:d] *= scale
+        wc = ca.in_proj_weight.detach().float()
+        bc = ca.in_proj_bias.detach().float()
+        dw.layers.append(DecoderLayerWeights(
+            f(L.norm1.norm.weight), f(L.norm1.norm.bias), wq.contiguous(), bq.contiguous(),
+            f(sa.out_proj.weight), f(sa.out_proj.bias),
+            f(L.norm2.norm.weight), f(L.norm2.norm.bias),
+            (wc[:d] * scale).contiguous(), (bc[:d] * scale).contiguous(), wc[d:].contiguous(), bc[d:].contiguous(),
+            f(ca.out_proj.weight), f(ca.out_proj.bias),
+            f(L.norm3.norm.weight), f(L.norm3.norm.bias),
+            f(ffn[0].weight), f(ffn[0].bias), f(ffn[3].weight), f(ffn[3].bias)))
+    dw.lnf_g, dw.lnf_b = f(decoder.norm.norm.weight), f(decoder.norm.norm.bias)
+    return dw
+
+
+def _off(t: torch.Tensor, elems: int) -> c_void_p:
+    """Device address `elems` elements into a contiguous CUDA tensor (column offset inside a packed projection)."""
+    ptr(t)                       # CUDA / contiguity checks
+    return c_void_p(t.data_ptr() + elems * t.element_size())
+
+
+def decoder_stack(tgt: torch.Tensor, memory: torch.Tensor, w: DecoderWeights, mem_len: Optional[torch.Tensor] = None,
+                  pad_idx: Optional[int] = None):
+    """One pass of the decoder over the whole target prefix.
+
+    tgt      int64 [R, L] token ids (R hypothesis rows)
+    memory   fp32 [Bm, T2, d] encoder output; R must be a multiple of Bm (row r reads memory[r // (R // Bm)]; the
+             reference's beam searcher passes the inflated tensor, Bm == R)
+    mem_len  int32 [R] valid encoder frames per row (keys j >= mem_len[r] are masked) or None
+    pad_idx  if not None, target keys equal to it are masked in the self-attention (``tgt_key_padding_mask`` of
+             ``forward``; ``decode`` passes None)
+    Returns (prediction fp32 [R, L, d], cross-attention weights of the last layer, head-averaged, fp32 [R, L, T2])."""
+    if tgt.dim() != 2 or memory.dim() != 3:
+        raise StacB200Error("decoder expects tgt [rows, length] and encoder_out [batch, frames, d_model]")
+    r, L = tgt.shape
+    bm, t2, d = memory.shape
+    if d != w.d_model or r % bm != 0:
+        raise StacB200Error("encoder_out does not match the decoder (d_model / rows not a multiple of its batch)")
+    if L > w.pe.shape[0]:
+        raise StacB200Error(f"prefix of {L} tokens exceeds the positional-encoding table ({w.pe.shape[0]})")
+    if not w.layers:
+        raise StacB200Error("the decoder has no layers")
+    dev = memory.device
+    h = w.nhead
+    m = r * L
+    tok = tgt.to(device=dev, dtype=torch.int64).contiguous()
+    mem = memory.float().contiguous().view(bm * t2, d)
+    f32 = dict(device=dev, dtype=torch.float32)
+    x = torch.empty(m, d, **f32)
+    ops._call("stac_embed_scale_pe", ptr(tok, torch.int64), ptr(w.emb), ptr(w.pe), m, L, d, w.vocab, math.sqrt(d), ptr(x),
+              stream())
+    hbuf = torch.empty(m, d, **f32)
+    qkv = torch.empty(m, 3 * d, **f32)
+    q2 = torch.empty(m, d, **f32)
+    kv2 = torch.empty(bm * t2, 2 * d, **f32)
+    ctx = torch.empty(m, d, **f32)
+    ff = torch.empty(m, w.layers[0].w_1.shape[0], **f32)
+    weights = torch.empty(r, L, t2, **f32)
+    key_tok = ptr(tok, torch.int64) if pad_idx is not None else ptr(None)
+    for n, lw in enumerate(w.layers):
+        last = n == len(w.layers) - 1
+        # causal self-attention over the prefix
+        ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_f32=hbuf)
+        ops._gemm(hbuf, lw.w_qkv, lw.b_qkv, qkv, "fp32", tag="dec_qkv")
+        ops._call("stac_attention_f32", ptr(qkv), 3 * d, _off(qkv, d), _off(qkv, 2 * d), 3 * d, r, L, L, h, 1, 1,
+                  ptr(None), key_tok, 0 if pad_idx is None else int(pad_idx), ptr(ctx), d, ptr(None), stream())
+        ops._gemm(ctx, lw.w_o, lw.b_o, x, "fp32", resid=x, tag="dec_out_proj")
+        # cross-attention over the encoder output
+        ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=hbuf)
+        ops._gemm(hbuf, lw.w_q2, lw.b_q2, q2, "fp32", tag="dec_q")
+        ops._gemm(mem, lw.w_kv2, lw.b_kv2, kv2, "fp32", tag="dec_mem_kv")
+        ops._call("stac_attention_f32", ptr(q2), d, ptr(kv2), _off(kv2, d), 2 * d, r, L, t2, h, r // bm, 0,
+                  ptr(mem_len, torch.int32) if mem_len is not None else ptr(None), ptr(None), 0, ptr(ctx), d,
+                  ptr(weights) if last else ptr(None), stream())
+        ops._gemm(ctx, lw.w_o2, lw.b_o2, x, "fp32", resid=x, tag="dec_out_proj2")
+        # feed-forward
+        ops._layernorm(x, lw.ln3_g, lw.ln3_b, 1e-6, out_f32=hbuf)
+        ops._gemm(hbuf, lw.w_1, lw.b_1, ff, "fp32", act=ACT_GELU_ERF, tag="dec_ffn1")
+        ops._gemm(ff, lw.w_2, lw.b_2, x, "fp32", resid=x, tag="dec_ffn2")
+    out = torch.empty(r, L, d, **f32)
+    ops._layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=out.view(m, d))
+    return out, weights
+
+
+def decoder_params_version(decoder: nn.Module, tgt_module: nn.Module):
+    return _params_version(decoder), _params_version(tgt_module)

@@ -12,9 +12,10 @@ reference checkpoint (``custom_src_module.layers.0.w.*``, ``encoder.layers.N.sel
 ``encoder.norm.norm.*``, ``positional_encoding.pe``).  None of those modules' ``forward`` is ever
 called: the arithmetic runs in libstac_b200 (ops.encoder_stack).
 
-The autoregressive decoder (``decode`` / decoder half of ``forward``) is not on the accelerated
-path.  An external decoder can be attached with ``attach_decoder`` so that
-``forward``/``decode`` keep working for the beam searcher.
+The decoder side (``decode`` :234-271, decoder half of ``forward`` :185-209) runs on the
+device too when ``num_decoder_layers > 0`` (decoder.py: parameters under ``decoder.*`` / ``custom_tgt_module.*`` with
+SpeechBrain's names, a first fp32 CUDA path that has not run on a B200 yet).  An external decoder can still be attached
+with ``attach_decoder``; it then takes precedence.
 """
 from __future__ import annotations
 
@@ -24,6 +25,7 @@ from typing import Optional
 import torch
 from torch import nn
 
+from . import decoder as dec
 from . import ops
 from ._lib import StacB200Error
 from .convolution import _Holder, _params_version
@@ -100,11 +102,26 @@ class TransformerMultiTask(nn.Module):
         self.positional_encoding = PositionalEncoding(d_model, max_length)
         self.encoder = _EncoderParams(num_encoder_layers, d_model, nhead, d_ffn, dropout, activation)
         self.custom_src_module = _SrcModule(input_size, d_model, dropout)
+        self._init_params()
+        # Decoder and target embedding (reference: TransformerInterface.__init__ / :139).  They are created and
+        # xavier-initialised under a forked random stream, after the encoder-side modules, so that the encoder-side
+        # weights drawn for a given seed do not depend on the decoder's presence (the oracle does the same).
         self.decoder = None
         self.custom_tgt_module = None
-        self._init_params()
+        self._external_decoder = False
+        if num_decoder_layers > 0:
+            with torch.random.fork_rng(devices=[]):
+                torch.manual_seed(torch.initial_seed() + 1)
+                self.decoder = dec.DecoderParams(num_decoder_layers, d_model, nhead, d_ffn, dropout, activation)
+                self.custom_tgt_module = dec.TgtModule(d_model, tgt_vocab)
+                for m in (self.decoder, self.custom_tgt_module):
+                    for p in m.parameters():
+                        if p.dim() > 1:
+                            torch.nn.init.xavier_normal_(p)
         self._packed = None
         self._packed_key = None
+        self._packed_dec = None
+        self._packed_dec_key = None
 
     def _init_params(self):
         for p in self.parameters():
@@ -160,23 +177,43 @@ class TransformerMultiTask(nn.Module):
         """Encoder half of ``forward`` (reference :144-183) with the ``make_masks`` length rule."""
         return self._run_encoder(src, wav_len, train_mask=True)
 
-    # ---- decoder side: not accelerated, delegated if attached ----
+    # ---- decoder side ----
     def attach_decoder(self, decoder: nn.Module, custom_tgt_module: nn.Module):
-        """Attach SpeechBrain's TransformerDecoder / NormalizedEmbedding (or equivalents) so that
-        ``forward`` and ``decode`` serve train_multitask.py and the beam searcher."""
+        """Use an external decoder (e.g. SpeechBrain's TransformerDecoder / NormalizedEmbedding) for ``forward`` and
+        ``decode`` instead of the built-in device path."""
         self.decoder = decoder
         self.custom_tgt_module = custom_tgt_module
+        self._external_decoder = True
 
     def _need_decoder(self):
         if self.decoder is None:
             raise StacB200Error(
-                "the autoregressive decoder is outside the accelerated encoder path; attach the reference's "
-                "TransformerDecoder with attach_decoder(decoder, custom_tgt_module) to use forward()/decode()")
+                "this TransformerMultiTask was built with num_decoder_layers=0: forward()/decode() need a decoder "
+                "(construct with num_decoder_layers > 0 or attach one with attach_decoder)")
+
+    def packed_decoder(self) -> dec.DecoderWeights:
+        key = dec.decoder_params_version(self.decoder, self.custom_tgt_module)
+        if self._packed_dec is None or self._packed_dec_key != key:
+            self._packed_dec = dec.pack_decoder(self.decoder, self.custom_tgt_module, self.positional_encoding.pe[0],
+                                                self.nhead)
+            self._packed_dec_key = key
+        return self._packed_dec
 
     def forward(self, src, tgt, wav_len=None, pad_idx=0):
+        """Reference :144-209: encoder with the ``make_masks`` length rule, decoder over the whole target with the
+        look-ahead mask, ``tgt == pad_idx`` key padding and the encoder's key padding on the memory."""
         self._need_decoder()
         encoder_out = self.forward_encoder(src, wav_len)
         t2 = encoder_out.shape[1]
+        if not self._external_decoder:
+            if self.training:
+                raise StacB200Error("stac_b200 TransformerMultiTask is inference-only: call .eval()")
+            mem_len = None
+            if wav_len is not None:
+                mem_len = ops.kv_lengths(wav_len, encoder_out.shape[0], t2, encoder_out.device, True)
+            decoder_out, _ = dec.decoder_stack(tgt, encoder_out, self.packed_decoder(), mem_len=mem_len,
+                                               pad_idx=pad_idx)
+            return encoder_out, decoder_out
         src_key_padding_mask = None
         if wav_len is not None:
             n = ops.kv_lengths(wav_len, encoder_out.shape[0], t2, encoder_out.device, True)
@@ -193,7 +230,14 @@ class TransformerMultiTask(nn.Module):
 
     @torch.no_grad()
     def decode(self, tgt, encoder_out, enc_len=None):
+        """Reference :234-271: one decoding step = the decoder over the whole prefix; returns the prediction
+        [rows, length, d_model] and the last layer's head-averaged cross-attention weights [rows, length, frames]."""
         self._need_decoder()
+        if not self._external_decoder:
+            mem_len = None
+            if enc_len is not None:       # (1 - length_to_mask(enc_len)).bool(): keys j >= enc_len are masked
+                mem_len = enc_len.to(device=encoder_out.device, dtype=torch.int32).contiguous()
+            return dec.decoder_stack(tgt, encoder_out, self.packed_decoder(), mem_len=mem_len, pad_idx=None)
         sz = tgt.shape[1]
         tgt_mask = torch.triu(torch.full((sz, sz), float("-inf"), device=tgt.device), diagonal=1)
         src_key_padding_mask = None

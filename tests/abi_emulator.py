@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE ONLY: a numpy stand-in for a few libstac_b200 entry points, so that the HOST-side orchestration
+(argument order, pointer offsets into packed projections, leading dimensions, mask plumbing, weight packing) can be
+exercised by the CPU test-suite, which has no GPU.  It is not a fallback: it lives under tests/, is patched in by the
+``emulated_abi`` fixture only, and the product raises on CPU tensors without it.
+
+Every emulated function takes exactly the arguments of its C prototype (include/stac_b200.h) - raw addresses and
+sizes - and is checked against the ctypes signature table before it runs."""
+import ctypes
+from ctypes import c_void_p
+
+import numpy as np
+import torch
+from scipy.special import erf
+
+from stac_speech_translation_b200 import _lib
+
+
+def _arr(addr, n, dtype=np.float32):
+    if not addr:
+        return None
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    return np.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=dtype)
+
+
+class Emulator:
+    def __init__(self):
+        self.calls = []
+
+    def call(self, name, *args):
+        res, sig = _lib._SIGNATURES[name]
+        assert len(args) == len(sig), (name, len(args), len(sig))
+        vals = []
+        for a, t in zip(args, sig):
+            if t is c_void_p:
+                assert a is None or isinstance(a, c_void_p), (name, a)
+                vals.append((a.value or 0) if a is not None else 0)
+            elif t is ctypes.c_float:
+                vals.append(float(a))
+            else:
+                assert isinstance(a, int) and not isinstance(a, bool), (name, a)
+                vals.append(int(a))
+        self.calls.append(name)
+        getattr(self, name)(*vals)
+
+    # ---- entry points (arguments exactly as in include/stac_b200.h) ----
+    def stac_embed_scale_pe(self, tokens, emb, pe, rows, seq_len, d_model, vocab, scale, out, stream):
+        tok = _arr(tokens, rows, np.int64)
+        e = _arr(emb, vocab * d_model).reshape(vocab, d_model)
+        p = _arr(pe, seq_len * d_model).reshape(seq_len, d_model)
+        o = _arr(out, rows * d_model).reshape(rows, d_model)
+        o[:] = e[tok] * np.float32(scale) + p[np.arange(rows) % seq_len]
+
+    def stac_layernorm(self, x, rows, dim, gamma, beta, eps, out_f32, out_bf16, stream):
+        assert out_bf16 == 0, "emulator: fp32 output only"
+        xx = _arr(x, rows * dim).reshape(rows, dim).astype(np.float64)
+        mu = xx.mean(1, keepdims=True)
+        var = xx.var(1, keepdims=True)
+        y = (xx - mu) / np.sqrt(var + eps) * _arr(gamma, dim) + _arr(beta, dim)
+        _arr(out_f32, rows * dim).reshape(rows, dim)[:] = y.astype(np.float32)
+
+    def stac_gemm_f32(self, a, w, bias, resid, resid_period, act, c, m, n, k, stream):
+        y = _arr(a, m * k).reshape(m, k).astype(np.float64) @ _arr(w, n * k).reshape(n, k).astype(np.float64).T
+        if bias:
+            y = y + _arr(bias, n)
+        if act == _lib.ACT_GELU_ERF:
+            y = 0.5 * y * (1.0 + erf(y / np.sqrt(2.0)))
+        if resid:
+            if resid_period:
+                y = y + _arr(resid, resid_period * n).reshape(resid_period, n)[np.arange(m) % resid_period]
+            else:
+                y = y + _arr(resid, m * n).reshape(m, n)
+        _arr(c, m * n).reshape(m, n)[:] = y.astype(np.float32)
+
+    def stac_mha_f32(self, qkv, kv_len, batch, seq_len, d_model, n_head, ctx, stream):
+        x = _arr(qkv, batch * seq_len * 3 * d_model).reshape(batch, seq_len, 3, n_head, 64).astype(np.float64)
+        n = _arr(kv_len, batch, np.int32)
+        out = _arr(ctx, batch * seq_len * d_model).reshape(batch, seq_len, n_head, 64)
+        for b in range(batch):
+            nk = min(max(int(n[b]), 1), seq_len)
+            for h in range(n_head):
+                s = x[b, :, 0, h] @ x[b, :nk, 1, h].T
+                p = np.exp(s - s.max(1, keepdims=True))
+                out[b, :, h] = (p / p.sum(1, keepdims=True)) @ x[b, :nk, 2, h]
+
+    def stac_attention_f32(self, q, ldq, k, v, ldkv, rows, lq, lk, n_head, mem_rows_div, causal, kv_len, key_tokens,
+                           pad_idx, ctx, ldctx, weights, stream):
+        n_mem = (rows + mem_rows_div - 1) // mem_rows_div
+        d = n_head * 64
+        qq = _arr(q, (rows * lq - 1) * ldq + d)
+        kk = _arr(k, (n_mem * lk - 1) * ldkv + d)
+        vv = _arr(v, (n_mem * lk - 1) * ldkv + d)
+        cc = _arr(ctx, (rows * lq - 1) * ldctx + d)
+        kl = _arr(kv_len, rows, np.int32)
+        kt = _arr(key_tokens, rows * lk, np.int64)
+        ww = _arr(weights, rows * lq * lk)
+        for r in range(rows):
+            rb = r // mem_rows_div
+            for i in range(lq):
+                row = r * lq + i
+                nk = lk if kl is None else min(max(int(kl[r]), 0), lk)
+                if causal:
+                    nk = min(nk, i + 1)
+                wacc = np.zeros(lk)
+                for h in range(n_head):
+                    qv = qq[row * ldq + h * 64: row * ldq + h * 64 + 64].astype(np.float64)
+                    s = np.full(lk, -np.inf)
+                    for j in range(nk):
+                        if kt is not None and kt[r * lk + j] == pad_idx:
+                            continue
+                        o = (rb * lk + j) * ldkv + h * 64
+                        s[j] = qv @ kk[o:o + 64]
+                    p = np.exp(s - s.max())
+                    p /= p.sum()
+                    acc = np.zeros(64)
+                    for j in range(nk):
+                        o = (rb * lk + j) * ldkv + h * 64
+                        acc += p[j] * vv[o:o + 64]
+                    cc[row * ldctx + h * 64: row * ldctx + h * 64 + 64] = acc.astype(np.float32)
+                    wacc += p / n_head
+                if ww is not None:
+                    ww[row * lk:(row + 1) * lk] = wacc.astype(np.float32)
+
+
+def cpu_ptr(t, dtype=None):
+    """`_lib.ptr` without the is_cuda requirement (same contiguity / dtype checks)."""
+    if t is None:
+        return c_void_p(0)
+    assert t.is_contiguous()
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.StacB200Error(f"expected {dtype}, got {t.dtype}")
+    return c_void_p(t.data_ptr())
+
+
+def install(monkeypatch):
+    """Route the host orchestration's kernel calls to the emulator (CPU tensors)."""
+    from stac_speech_translation_b200 import decoder, ops
+    emu = Emulator()
+    for mod in (ops, decoder):
+        monkeypatch.setattr(mod, "ptr", cpu_ptr)
+        monkeypatch.setattr(mod, "stream", lambda: c_void_p(0))
+    monkeypatch.setattr(ops, "_call", emu.call)
+    return emu

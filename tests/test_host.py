@@ -33,6 +33,29 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().stac_conv0_padded_elems(2, 501) == 2 * 4 * 252 * 21 * 256
 
 
+def test_ctypes_signatures_mirror_the_header():
+    """Every prototype of include/stac_b200.h, parameter by parameter, against the ctypes table the Python side binds
+    with (a mismatch would corrupt arguments silently on the GPU box)."""
+    from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+    header = open(os.path.join(ROOT, "include", "stac_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(int64_t|int|const char\s*\*)\s+(stac_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)
+    assert len(protos) == len(_lib.exported_symbols())
+
+    def ctype_of(param):
+        param = param.strip()
+        if "*" in param:
+            return c_void_p
+        base = param.split()[0] if not param.startswith("const") else param.split()[1]
+        return {"int64_t": c_int64, "int32_t": c_int32, "int": c_int, "float": c_float}[base]
+
+    for ret, name, params in protos:
+        res, args = _lib._SIGNATURES[name]
+        want = [] if params.strip() in ("", "void") else [ctype_of(p) for p in params.split(",")]
+        assert args == want, (name, args, want)
+        assert res == {"int": c_int, "int64_t": c_int64}.get(ret, c_char_p), name
+
+
 def test_state_dict_layout_matches_speechbrain_keys():
     mods = sb.build_modules(sb.HParams(**TINY, output_neurons=64), "bf16", device="cpu")
     model = torch.nn.ModuleList([mods["CNN"], mods["Transformer"], mods["ctc_lin"], mods["ctc_lin"]])
@@ -104,8 +127,13 @@ def test_no_cpu_fallback_and_clear_errors():
         sb.Fbank(n_mels=40)
     with pytest.raises(sb.StacB200Error):
         sb.TransformerMultiTask(5000, 5120, d_model=256, nhead=4, normalize_before=False, activation=torch.nn.GELU)
-    with pytest.raises(sb.StacB200Error, match="decoder"):
+    # the built-in decoder path is a device path too
+    with pytest.raises(sb.StacB200Error, match="no CPU fallback"):
         mods["Transformer"].eval().decode(torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 4, 128))
+    no_dec = sb.TransformerMultiTask(64, 5120, d_model=128, nhead=2, num_encoder_layers=1, num_decoder_layers=0,
+                                     d_ffn=256, normalize_before=True, activation=torch.nn.GELU).eval()
+    with pytest.raises(sb.StacB200Error, match="decoder"):
+        no_dec.decode(torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 4, 128))
 
 
 def test_kv_lengths_match_reference_masks():

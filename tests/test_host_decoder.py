@@ -1,0 +1,101 @@
+"""Host-side orchestration of the decoder (decoder.py, transformer.decode / forward) on the CPU, against the vectors the
+REFERENCE'S OWN decode() / forward() produced (tests/golden/decoder_reference.npz, make_decoder_golden.py).
+
+The kernels cannot run here; tests/abi_emulator.py stands in for the five entry points the fp32 path uses, taking the
+raw addresses and sizes the host code passes across the C ABI.  What this pins without a GPU: weight packing (q rows
+pre-scaled, cross-attention in_proj split), argument order, pointer offsets into the packed projections, leading
+dimensions, which masks reach which attention, the returned attention weights.  The kernels themselves are compared with
+the same vectors in tests/test_gpu_decoder.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import abi_emulator
+import stac_speech_translation_b200 as sb
+from oracle import speechbrain_path as sp
+from util import rel_l2
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "decoder_reference.npz")
+
+
+def fixture():
+    d = np.load(GOLDEN)
+    state = {k[len("state/"):]: torch.from_numpy(d[k].astype(np.float32)) for k in d.files if k.startswith("state/")}
+    return d, state
+
+
+def build(cls, state, **extra):
+    d_model = state["encoder.norm.norm.weight"].shape[0]
+    n_dec = 1 + max(int(k.split(".")[2]) for k in state if k.startswith("decoder.layers."))
+    tr = cls(tgt_vocab=state["custom_tgt_module.layers.0.emb.Embedding.weight"].shape[0],
+             input_size=state["custom_src_module.layers.0.w.weight"].shape[1], d_model=d_model, nhead=d_model // 64,
+             num_encoder_layers=1, num_decoder_layers=n_dec,
+             d_ffn=state["encoder.layers.0.pos_ffn.ffn.0.weight"].shape[0], dropout=0.1, activation=torch.nn.GELU,
+             normalize_before=True, causal=False, **extra)
+    res = tr.load_state_dict(state, strict=False)
+    assert res.missing_keys == ["positional_encoding.pe"] and not res.unexpected_keys     # every decoder key present
+    return tr.eval()
+
+
+def test_oracle_decoder_against_reference_generated_fixture():
+    d, state = fixture()
+    tr = build(sp.TransformerMultiTask, state)
+    src, wl = torch.from_numpy(d["src"].astype(np.float32)), torch.from_numpy(d["wav_lens"])
+    tgt, prefix = torch.from_numpy(d["tgt"]), torch.from_numpy(d["prefix"])
+    enc_out = torch.from_numpy(d["enc_out"])
+    torch.set_num_threads(1)
+    with torch.no_grad():
+        enc_f, dec_f = tr(src, tgt, wl, pad_idx=0)
+        pred, attn = tr.decode(prefix, enc_out)
+        pred_len, attn_len = tr.decode(prefix, enc_out, torch.from_numpy(d["enc_len"]))
+        pred1, attn1 = tr.decode(prefix[:, :1], enc_out)
+    for got, key in [(enc_f, "enc_forward"), (dec_f, "dec_forward"), (pred, "pred"), (attn, "attn"),
+                     (pred_len, "pred_len"), (attn_len, "attn_len"), (pred1, "pred1"), (attn1, "attn1")]:
+        assert rel_l2(got, torch.from_numpy(d[key])) < 1e-6, key
+    # the fixture separates the cases: memory padding changes decode(), and forward() pads both sides
+    assert rel_l2(torch.from_numpy(d["pred_len"]), torch.from_numpy(d["pred"])) > 1e-4
+    assert np.abs(d["attn_len"][1, :, 15:]).max() == 0 and np.abs(d["attn"][1, :, 15:]).max() > 0
+
+
+def test_host_decoder_orchestration_against_reference_vectors(monkeypatch):
+    d, state = fixture()
+    emu = abi_emulator.install(monkeypatch)
+    tr = build(sb.TransformerMultiTask, state, precision="fp32")
+    prefix = torch.from_numpy(d["prefix"])
+    enc_out = torch.from_numpy(d["enc_out"])
+    pred, attn = tr.decode(prefix, enc_out)                                    # mutitask_decoder.py:126
+    assert pred.dtype == torch.float32 and pred.shape == d["pred"].shape and attn.shape == d["attn"].shape
+    assert rel_l2(pred, torch.from_numpy(d["pred"])) < 1e-5
+    assert rel_l2(attn, torch.from_numpy(d["attn"])) < 1e-5
+    assert emu.calls.count("stac_attention_f32") == 2 * len(tr.decoder.layers)
+    pred_len, attn_len = tr.decode(prefix, enc_out, torch.from_numpy(d["enc_len"]))
+    assert rel_l2(pred_len, torch.from_numpy(d["pred_len"])) < 1e-5
+    assert rel_l2(attn_len, torch.from_numpy(d["attn_len"])) < 1e-5
+    pred1, attn1 = tr.decode(prefix[:, :1], enc_out)
+    assert rel_l2(pred1, torch.from_numpy(d["pred1"])) < 1e-5 and rel_l2(attn1, torch.from_numpy(d["attn1"])) < 1e-5
+    # forward(): encoder (round-rule lengths) + decoder with look-ahead, tgt == pad and memory padding
+    src, wl = torch.from_numpy(d["src"].astype(np.float32)), torch.from_numpy(d["wav_lens"])
+    enc_f, dec_f = tr(src, torch.from_numpy(d["tgt"]), wl, pad_idx=0)
+    assert rel_l2(enc_f, torch.from_numpy(d["enc_forward"])) < 1e-5
+    assert rel_l2(dec_f, torch.from_numpy(d["dec_forward"])) < 1e-5
+    # beam-inflated rows over a shared (not inflated) memory: row r reads memory[r // beam]
+    from stac_speech_translation_b200 import decoder as dec
+    beam = 2
+    out, w = dec.decoder_stack(prefix.repeat_interleave(beam, 0), enc_out, tr.packed_decoder())
+    assert rel_l2(out[::beam], torch.from_numpy(d["pred"])) < 1e-5 and torch.equal(out[::beam], out[1::beam])
+    assert rel_l2(w[1::beam], torch.from_numpy(d["attn"])) < 1e-5
+
+
+def test_decoder_weights_follow_checkpoint_updates(monkeypatch):
+    d, state = fixture()
+    abi_emulator.install(monkeypatch)
+    tr = build(sb.TransformerMultiTask, state, precision="fp32")
+    prefix, enc_out = torch.from_numpy(d["prefix"]), torch.from_numpy(d["enc_out"])
+    a, _ = tr.decode(prefix, enc_out)
+    sd = tr.state_dict()
+    sd["decoder.layers.1.pos_ffn.ffn.3.weight"] = sd["decoder.layers.1.pos_ffn.ffn.3.weight"] * 2.0
+    tr.load_state_dict(sd)                                   # e.g. checkpoint averaging, inference.py:228-233
+    b, _ = tr.decode(prefix, enc_out)
+    assert rel_l2(b, a) > 1e-3

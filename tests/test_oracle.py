@@ -203,7 +203,9 @@ def test_oracle_glue_against_reference_generated_fixture():
                                  num_encoder_layers=2, d_ffn=state["encoder.layers.0.pos_ffn.ffn.0.weight"].shape[0],
                                  activation=torch.nn.GELU, normalize_before=True).eval()
     res = tr.load_state_dict(state, strict=False)
-    assert res.missing_keys == ["positional_encoding.pe"] and not res.unexpected_keys
+    # (the fixture holds the encoder side only; the decoder side has its own, decoder_reference.npz)
+    assert not res.unexpected_keys and all(
+        k == "positional_encoding.pe" or k.startswith(("decoder.", "custom_tgt_module.")) for k in res.missing_keys)
     src = torch.from_numpy(d["src"].astype(np.float32))
     wl = torch.from_numpy(d["wav_lens"])
     torch.set_num_threads(1)

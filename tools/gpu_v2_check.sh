@@ -10,6 +10,8 @@ timeout 300 python -m pytest tests/test_gpu_tc_attention.py -q -x -m gpu -k v2 >
 echo "attention v2 tests rc $?"; tail -5 gpurun_out/v2_mha_tests.log
 timeout 300 python -m pytest tests/test_gpu_turns.py -q -x -m gpu > gpurun_out/v2_turn_tests.log 2>&1
 echo "turn-detection tests rc $?"; tail -5 gpurun_out/v2_turn_tests.log
+timeout 600 python -m pytest tests/test_gpu_decoder.py -q -x -m gpu > gpurun_out/v2_decoder_tests.log 2>&1
+echo "decoder tests rc $?"; tail -8 gpurun_out/v2_decoder_tests.log
 timeout 120 python tools/bench_mha.py stac_speech_translation_b200/libstac_b200.so > gpurun_out/v2_mha_bench.log 2>&1
 echo "bench_mha rc $?"; cat gpurun_out/v2_mha_bench.log
 STAC_MHA_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v2_bench.json 2> gpurun_out/v2_bench.err
