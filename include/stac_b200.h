@@ -225,15 +225,18 @@ int stac_ctc_spikes(const int32_t* ids, int64_t batch, int64_t t2, int32_t turn_
  * stac_embed_scale_pe: out[row] = emb[tokens[row]] * scale + pe[row % seq_len]   (NormalizedEmbedding + positional
  *        encoding, :248-256); tokens int64 [rows], emb [vocab, d_model], pe [>= seq_len, d_model].
  * stac_attention_f32: softmax(q k^T + masks) v per head (head_dim 64; q is expected pre-scaled by 1/8).
- *        q row (r, i) at q + (r * lq + i) * ldq, key / value row (r / mem_rows_div, j) at k|v + (.. * lk + j) * ldkv,
- *        ctx row at ctx + (r * lq + i) * ldctx; head h uses columns h*64 .. h*64+63 of each.
+ *        q row (r, i) at q + (r * lq + i) * ldq; key / value row j of row r at
+ *        k|v + (r / mem_rows_div) * kv_batch_stride + j * kv_row_stride (packed [batch][lk][ld]: strides lk*ld, ld;
+ *        time-major cache [lk][rows][ld]: strides ld, rows*ld); ctx row at ctx + (r * lq + i) * ldctx;
+ *        head h uses columns h*64 .. h*64+63 of each.
  *        Masks: causal != 0 hides keys j > i; kv_len int32 [rows] (or NULL) hides j >= kv_len[r]; key_tokens int64
  *        [rows, lk] (or NULL) hides keys whose token equals pad_idx.  weights (or NULL): fp32 [rows, lq, lk], the
  *        probabilities averaged over heads (what nn.MultiheadAttention returns with need_weights=True). */
 int stac_embed_scale_pe(const int64_t* tokens, const float* emb, const float* pe, int64_t rows, int64_t seq_len,
                         int64_t d_model, int64_t vocab, float scale, float* out, void* stream);
-int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldkv, int64_t rows,
-                       int64_t lq, int64_t lk, int64_t n_head, int64_t mem_rows_div, int causal,
+int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
+                       int64_t kv_row_stride, int64_t rows, int64_t lq, int64_t lk, int64_t n_head,
+                       int64_t mem_rows_div, int causal,
                        const int32_t* kv_len, const int64_t* key_tokens, int64_t pad_idx, float* ctx, int64_t ldctx,
                        float* weights, void* stream);
 

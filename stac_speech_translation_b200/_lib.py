@@ -50,7 +50,7 @@ _SIGNATURES = {
     "stac_argmax_rows": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "stac_ctc_spikes": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "stac_embed_scale_pe": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P]),
-    "stac_attention_f32": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
+    "stac_attention_f32": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                                    _P, _P, c_int64, _P, c_int64, _P, _P]),
     "stac_cast_bf16": (c_int, [_P, c_int64, _P, _P]),
 }

@@ -12,7 +12,9 @@
 //   * stac_attention_f32  : attention with separate query and key/value tensors, causal and padding masks, optional
 //                           head-averaged weights (torch's need_weights=True output)
 // Both are what the reference's forward_step costs per call (the whole prefix, every step, mutitask_decoder.py:119-128);
-// the KV-cached single-token step on tensor cores is the next step of this row.
+// decoder.DecoderCache drives the same kernels one token at a time over cached keys / values (the key / value tensor
+// is addressed with a batch stride and a row stride so that a time-major cache works); tensor-core versions are the
+// next step of this row.
 #include <algorithm>
 #include "common.cuh"
 
@@ -43,7 +45,7 @@ embed_scale_pe_kernel(const long long* __restrict__ tokens, const float* __restr
 // plain sum in shared memory.  Dynamic shared memory: sc[lk] | wacc[lk] | q[64] | part[128] | red[40].
 __global__ void __launch_bounds__(kThreads)
 attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
-                     const float* __restrict__ v, long long ldkv, int lq, int lk, int n_head, int mem_rows_div,
+                     const float* __restrict__ v, long long kv_bs, long long kv_rs, int lq, int lk, int n_head, int mem_rows_div,
                      int causal, const int* __restrict__ kv_len, const long long* __restrict__ key_tokens,
                      long long pad_idx, float* __restrict__ ctx, long long ldctx, float* __restrict__ weights) {
   extern __shared__ float sm[];
@@ -71,7 +73,7 @@ attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __
       float s = -INFINITY;
       const bool masked = j >= n_keys || (key_tokens != nullptr && key_tokens[r * lk + j] == pad_idx);
       if (!masked) {
-        const float4* kp = reinterpret_cast<const float4*>(k + (rb * lk + j) * ldkv + h * kHd);
+        const float4* kp = reinterpret_cast<const float4*>(k + rb * kv_bs + j * kv_rs + h * kHd);
         float a = 0.f;
 #pragma unroll
         for (int c = 0; c < kHd / 4; ++c) {
@@ -99,7 +101,7 @@ attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __
     const int dim = tid & (kHd - 1), half = tid >> 6;
     float acc = 0.f;
     for (int j = half; j < n_keys; j += kThreads / kHd)
-      acc = fmaf(sc[j], __ldg(v + (rb * lk + j) * ldkv + h * kHd + dim), acc);
+      acc = fmaf(sc[j], __ldg(v + rb * kv_bs + j * kv_rs + h * kHd + dim), acc);
     part[tid] = acc;
     __syncthreads();
     if (tid < kHd) ctx[qrow * ldctx + h * kHd + tid] = (part[tid] + part[tid + kHd]) * inv;
@@ -124,14 +126,16 @@ extern "C" int stac_embed_scale_pe(const int64_t* tokens, const float* emb, cons
   STAC_LAUNCH_CHECK();
 }
 
-extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t ldkv,
-                                  int64_t rows, int64_t lq, int64_t lk, int64_t n_head, int64_t mem_rows_div,
+extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
+                                  int64_t kv_row_stride, int64_t rows, int64_t lq, int64_t lk, int64_t n_head,
+                                  int64_t mem_rows_div,
                                   int causal, const int32_t* kv_len, const int64_t* key_tokens, int64_t pad_idx,
                                   float* ctx, int64_t ldctx, float* weights, void* stream) {
   STAC_REQUIRE(q && k && v && ctx && rows > 0 && lq > 0 && lk > 0 && n_head > 0 && mem_rows_div > 0);
-  STAC_REQUIRE(ldq >= n_head * kHd && ldkv >= n_head * kHd && ldctx >= n_head * kHd);
+  STAC_REQUIRE(ldq >= n_head * kHd && kv_row_stride >= n_head * kHd && kv_batch_stride > 0 && ldctx >= n_head * kHd);
   // float4 key loads: 16-byte aligned rows
-  if (ldkv % 4 != 0 || (reinterpret_cast<uintptr_t>(k) & 15) != 0) return STAC_ERR_UNSUPPORTED_SHAPE;
+  if (kv_row_stride % 4 != 0 || kv_batch_stride % 4 != 0 || (reinterpret_cast<uintptr_t>(k) & 15) != 0)
+    return STAC_ERR_UNSUPPORTED_SHAPE;
   if (rows * lq >= (1ll << 31) || lk >= (1 << 24) || n_head > 65535) return STAC_ERR_UNSUPPORTED_SHAPE;
   const size_t smem = (size_t)(2 * lk + kHd + kThreads + 40) * sizeof(float);
   if (smem > 200 * 1024) return STAC_ERR_UNSUPPORTED_SHAPE;
@@ -140,7 +144,7 @@ extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, c
     if (e != cudaSuccess) return (int)e;
   }
   attention_f32_kernel<<<(unsigned)(rows * lq), kThreads, smem, as_stream(stream)>>>(
-      q, (long long)ldq, k, v, (long long)ldkv, (int)lq, (int)lk, (int)n_head, (int)mem_rows_div, causal, kv_len,
+      q, (long long)ldq, k, v, (long long)kv_batch_stride, (long long)kv_row_stride, (int)lq, (int)lk, (int)n_head, (int)mem_rows_div, causal, kv_len,
       reinterpret_cast<const long long*>(key_tokens), (long long)pad_idx, ctx, (long long)ldctx, weights);
   STAC_LAUNCH_CHECK();
 }

@@ -179,14 +179,14 @@ def decoder_stack(tgt: torch.Tensor, memory: torch.Tensor, w: DecoderWeights, me
         # causal self-attention over the prefix
         ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_f32=hbuf)
         ops._gemm(hbuf, lw.w_qkv, lw.b_qkv, qkv, "fp32", tag="dec_qkv")
-        ops._call("stac_attention_f32", ptr(qkv), 3 * d, _off(qkv, d), _off(qkv, 2 * d), 3 * d, r, L, L, h, 1, 1,
+        ops._call("stac_attention_f32", ptr(qkv), 3 * d, _off(qkv, d), _off(qkv, 2 * d), L * 3 * d, 3 * d, r, L, L, h, 1, 1,
                   ptr(None), key_tok, 0 if pad_idx is None else int(pad_idx), ptr(ctx), d, ptr(None), stream())
         ops._gemm(ctx, lw.w_o, lw.b_o, x, "fp32", resid=x, tag="dec_out_proj")
         # cross-attention over the encoder output
         ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=hbuf)
         ops._gemm(hbuf, lw.w_q2, lw.b_q2, q2, "fp32", tag="dec_q")
         ops._gemm(mem, lw.w_kv2, lw.b_kv2, kv2, "fp32", tag="dec_mem_kv")
-        ops._call("stac_attention_f32", ptr(q2), d, ptr(kv2), _off(kv2, d), 2 * d, r, L, t2, h, r // bm, 0,
+        ops._call("stac_attention_f32", ptr(q2), d, ptr(kv2), _off(kv2, d), t2 * 2 * d, 2 * d, r, L, t2, h, r // bm, 0,
                   ptr(mem_len, torch.int32) if mem_len is not None else ptr(None), ptr(None), 0, ptr(ctx), d,
                   ptr(weights) if last else ptr(None), stream())
         ops._gemm(ctx, lw.w_o2, lw.b_o2, x, "fp32", resid=x, tag="dec_out_proj2")
@@ -197,6 +197,92 @@ def decoder_stack(tgt: torch.Tensor, memory: torch.Tensor, w: DecoderWeights, me
     out = torch.empty(r, L, d, **f32)
     ops._layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=out.view(m, d))
     return out, weights
+
+
+class DecoderCache:
+    """KV-cached incremental decoding: the same arithmetic as ``decoder_stack`` on the growing prefix, one token per
+    call (what a beam searcher's ``forward_step`` needs, mutitask_decoder.py:119-128, without re-running the whole
+    decoder over the whole prefix every step as the reference does).
+
+    * the cross-attention keys / values of every layer are projected ONCE from the encoder output, per utterance (not
+      per hypothesis row: row r reads memory[r // beam]);
+    * the self-attention keys / values of the prefix live in a time-major cache [layer][max_len][rows][2 d], so the
+      projection of step t is written by the GEMM straight into slab t and a beam re-ordering is a row gather;
+    * ``step(tokens)`` returns what ``decode(prefix)[0][:, -1]`` and ``decode(prefix)[1][:, -1]`` return.
+    Same entry points as ``decoder_stack`` (fp32, CUDA cores); no CPU fallback."""
+
+    def __init__(self, w: DecoderWeights, memory: torch.Tensor, rows: int, max_len: int,
+                 mem_len: Optional[torch.Tensor] = None):
+        bm, t2, d = memory.shape
+        if d != w.d_model or rows % bm != 0:
+            raise StacB200Error("encoder_out does not match the decoder (d_model / rows not a multiple of its batch)")
+        if max_len > w.pe.shape[0]:
+            raise StacB200Error(f"{max_len} steps exceed the positional-encoding table ({w.pe.shape[0]})")
+        self.w, self.rows, self.max_len, self.t = w, rows, max_len, 0
+        self.bm, self.t2, self.d = bm, t2, d
+        self.mem_len = mem_len
+        dev = memory.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        mem = memory.float().contiguous().view(bm * t2, d)
+        self.cross_kv = []
+        for lw in w.layers:
+            kv = torch.empty(bm * t2, 2 * d, **f32)
+            ops._gemm(mem, lw.w_kv2, lw.b_kv2, kv, "fp32", tag="dec_mem_kv")
+            self.cross_kv.append(kv)
+        self.self_kv = torch.empty(len(w.layers), max_len, rows, 2 * d, **f32)
+        self.x = torch.empty(rows, d, **f32)
+        self.h = torch.empty(rows, d, **f32)
+        self.q = torch.empty(rows, d, **f32)
+        self.ctx = torch.empty(rows, d, **f32)
+        self.ff = torch.empty(rows, w.layers[0].w_1.shape[0], **f32)
+
+    def step(self, tokens: torch.Tensor):
+        """tokens int64 [rows]: the token at position t of every hypothesis.  Returns (prediction [rows, d],
+        head-averaged cross-attention weights of the last layer [rows, T2]) for that position."""
+        w, r, d, t, t2 = self.w, self.rows, self.d, self.t, self.t2
+        if t >= self.max_len:
+            raise StacB200Error("decoder cache is full")
+        if tokens.shape != (r,):
+            raise StacB200Error("one token per hypothesis row is required")
+        h = w.nhead
+        x = self.x
+        tok = tokens.to(device=x.device, dtype=torch.int64).contiguous()
+        # position t of the table: pe + t * d with a period of one row
+        ops._call("stac_embed_scale_pe", ptr(tok, torch.int64), ptr(w.emb), _off(w.pe, t * d), r, 1, d, w.vocab,
+                  math.sqrt(d), ptr(x), stream())
+        weights = torch.empty(r, t2, device=x.device, dtype=torch.float32)
+        for n, lw in enumerate(w.layers):
+            last = n == len(w.layers) - 1
+            ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_f32=self.h)
+            ops._gemm(self.h, lw.w_qkv[:d], lw.b_qkv[:d], self.q, "fp32", tag="dec_q_self")
+            slab = self.self_kv[n, t]                              # [rows, 2 d]: keys | values of position t
+            ops._gemm(self.h, lw.w_qkv[d:], lw.b_qkv[d:], slab, "fp32", tag="dec_kv_self")
+            cache = self.self_kv[n]
+            ops._call("stac_attention_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, 1, t + 1, h,
+                      1, 0, ptr(None), ptr(None), 0, ptr(self.ctx), d, ptr(None), stream())
+            ops._gemm(self.ctx, lw.w_o, lw.b_o, x, "fp32", resid=x, tag="dec_out_proj")
+            ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=self.h)
+            ops._gemm(self.h, lw.w_q2, lw.b_q2, self.q, "fp32", tag="dec_q")
+            kv = self.cross_kv[n]
+            ops._call("stac_attention_f32", ptr(self.q), d, ptr(kv), _off(kv, d), t2 * 2 * d, 2 * d, r, 1, t2, h,
+                      r // self.bm, 0, ptr(self.mem_len, torch.int32) if self.mem_len is not None else ptr(None),
+                      ptr(None), 0, ptr(self.ctx), d, ptr(weights) if last else ptr(None), stream())
+            ops._gemm(self.ctx, lw.w_o2, lw.b_o2, x, "fp32", resid=x, tag="dec_out_proj2")
+            ops._layernorm(x, lw.ln3_g, lw.ln3_b, 1e-6, out_f32=self.h)
+            ops._gemm(self.h, lw.w_1, lw.b_1, self.ff, "fp32", act=ACT_GELU_ERF, tag="dec_ffn1")
+            ops._gemm(self.ff, lw.w_2, lw.b_2, x, "fp32", resid=x, tag="dec_ffn2")
+        out = torch.empty(r, d, device=x.device, dtype=torch.float32)
+        ops._layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=out)
+        self.t = t + 1
+        return out, weights
+
+    def reorder(self, index: torch.Tensor):
+        """Beam re-ordering (``permute_mem``, mutitask_decoder.py:109-112): hypothesis row i continues row index[i].
+        Data movement only (a row gather of the cached prefix)."""
+        idx = index.to(device=self.self_kv.device, dtype=torch.int64)
+        if idx.shape != (self.rows,):
+            raise StacB200Error("one source row per hypothesis row is required")
+        self.self_kv[:, :self.t] = self.self_kv[:, :self.t].index_select(2, idx)
 
 
 def decoder_params_version(decoder: nn.Module, tgt_module: nn.Module):

@@ -82,13 +82,13 @@ class Emulator:
                 p = np.exp(s - s.max(1, keepdims=True))
                 out[b, :, h] = (p / p.sum(1, keepdims=True)) @ x[b, :nk, 2, h]
 
-    def stac_attention_f32(self, q, ldq, k, v, ldkv, rows, lq, lk, n_head, mem_rows_div, causal, kv_len, key_tokens,
-                           pad_idx, ctx, ldctx, weights, stream):
+    def stac_attention_f32(self, q, ldq, k, v, kv_bs, kv_rs, rows, lq, lk, n_head, mem_rows_div, causal, kv_len,
+                           key_tokens, pad_idx, ctx, ldctx, weights, stream):
         n_mem = (rows + mem_rows_div - 1) // mem_rows_div
         d = n_head * 64
         qq = _arr(q, (rows * lq - 1) * ldq + d)
-        kk = _arr(k, (n_mem * lk - 1) * ldkv + d)
-        vv = _arr(v, (n_mem * lk - 1) * ldkv + d)
+        kk = _arr(k, (n_mem - 1) * kv_bs + (lk - 1) * kv_rs + d)
+        vv = _arr(v, (n_mem - 1) * kv_bs + (lk - 1) * kv_rs + d)
         cc = _arr(ctx, (rows * lq - 1) * ldctx + d)
         kl = _arr(kv_len, rows, np.int32)
         kt = _arr(key_tokens, rows * lk, np.int64)
@@ -107,13 +107,13 @@ class Emulator:
                     for j in range(nk):
                         if kt is not None and kt[r * lk + j] == pad_idx:
                             continue
-                        o = (rb * lk + j) * ldkv + h * 64
+                        o = rb * kv_bs + j * kv_rs + h * 64
                         s[j] = qv @ kk[o:o + 64]
                     p = np.exp(s - s.max())
                     p /= p.sum()
                     acc = np.zeros(64)
                     for j in range(nk):
-                        o = (rb * lk + j) * ldkv + h * 64
+                        o = rb * kv_bs + j * kv_rs + h * 64
                         acc += p[j] * vv[o:o + 64]
                     cc[row * ldctx + h * 64: row * ldctx + h * 64 + 64] = acc.astype(np.float32)
                     wacc += p / n_head

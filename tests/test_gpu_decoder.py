@@ -79,7 +79,8 @@ def test_attention_f32_kernel(rows, lq, lk, h, div, causal):
     qd, kvd, kld, tokd = q.cuda(), kv.cuda(), kv_len.cuda(), tok.cuda()
     ctx = torch.full((rows * lq, d), float("nan"), device="cuda")
     w = torch.full((rows, lq, lk), float("nan"), device="cuda")
-    ops._call("stac_attention_f32", ops.ptr(qd), d, ops.ptr(kvd), dec._off(kvd, d), 2 * d, rows, lq, lk, h, div, causal,
+    ops._call("stac_attention_f32", ops.ptr(qd), d, ops.ptr(kvd), dec._off(kvd, d), lk * 2 * d, 2 * d, rows, lq, lk, h, div,
+              causal,
               ops.ptr(kld), ops.ptr(tokd) if use_tok else ops.ptr(None), 0, ops.ptr(ctx), d, ops.ptr(w), ops.stream())
     torch.cuda.synchronize()
     qq = q.view(rows, lq, h, 64).permute(0, 2, 1, 3).double()
@@ -108,3 +109,20 @@ def test_embed_scale_pe_kernel():
               float(np.sqrt(d)), ops.ptr(out), ops.stream())
     want = emb[tok] * np.float32(np.sqrt(d)) + pe[:L][None]
     assert rel_l2(out.view(rows, L, d), want) < 1e-6
+
+
+def test_kv_cached_steps_equal_full_prefix_decode_on_device():
+    d, state = fixture()
+    tr = build(sb.TransformerMultiTask, state, precision="bf16").cuda()
+    prefix, enc_out = torch.from_numpy(d["prefix"]).cuda(), torch.from_numpy(d["enc_out"]).cuda()
+    beam = 3
+    rows = prefix.repeat_interleave(beam, 0)
+    cache = tr.decoder_cache(enc_out, rows=rows.shape[0], max_len=rows.shape[1])
+    for t in range(rows.shape[1]):
+        out, w = cache.step(rows[:, t].contiguous())
+        if t == 1:
+            cache.reorder(torch.arange(rows.shape[0], device="cuda"))      # identity re-ordering: nothing may change
+    assert rel_l2(out[::beam], torch.from_numpy(d["pred"])[:, -1]) < FP32_TOL
+    assert rel_l2(w[::beam], torch.from_numpy(d["attn"])[:, -1]) < FP32_TOL
+    full, full_w = tr.decode(rows, enc_out.repeat_interleave(beam, 0))
+    assert rel_l2(out, full[:, -1]) < 1e-5 and rel_l2(w, full_w[:, -1]) < 1e-5

@@ -99,3 +99,40 @@ def test_decoder_weights_follow_checkpoint_updates(monkeypatch):
     tr.load_state_dict(sd)                                   # e.g. checkpoint averaging, inference.py:228-233
     b, _ = tr.decode(prefix, enc_out)
     assert rel_l2(b, a) > 1e-3
+
+
+def test_kv_cached_steps_equal_the_full_prefix_decode(monkeypatch):
+    """DecoderCache.step, token by token, against the reference-generated decode() vectors (last position of every
+    prefix) and against the full-prefix device path; then a beam re-ordering."""
+    d, state = fixture()
+    abi_emulator.install(monkeypatch)
+    tr = build(sb.TransformerMultiTask, state, precision="fp32")
+    prefix, enc_out = torch.from_numpy(d["prefix"]), torch.from_numpy(d["enc_out"])
+    b, L = prefix.shape
+    cache = tr.decoder_cache(enc_out, rows=b, max_len=8)
+    for t in range(L):
+        out, w = cache.step(prefix[:, t])
+        full, full_w = tr.decode(prefix[:, :t + 1].contiguous(), enc_out)
+        assert rel_l2(out, full[:, -1]) < 1e-5 and rel_l2(w, full_w[:, -1]) < 1e-5
+        if t == 0:
+            assert rel_l2(out, torch.from_numpy(d["pred1"])[:, 0]) < 1e-5
+    assert rel_l2(out, torch.from_numpy(d["pred"])[:, -1]) < 1e-5
+    assert rel_l2(w, torch.from_numpy(d["attn"])[:, -1]) < 1e-5
+    # with encoder lengths, beam rows over the un-inflated memory, and a re-ordering in the middle
+    beam = 2
+    enc_len = torch.from_numpy(d["enc_len"])
+    rows_prefix = prefix.repeat_interleave(beam, 0).clone()
+    rows_prefix[1::beam, 1:] = (rows_prefix[1::beam, 1:] + 7) % 60 + 1            # the second beam diverges after step 0
+    cache = tr.decoder_cache(enc_out, rows=b * beam, max_len=L, enc_len=enc_len.repeat_interleave(beam, 0))
+    index = torch.tensor([1, 1, 2, 3, 5, 4])                                       # row 0 <- row 1, rows 4 / 5 swapped
+    cur = rows_prefix.clone()
+    for t in range(L):
+        if t == 2:
+            cache.reorder(index)
+            cur = cur[index]
+            cur[:, t:] = rows_prefix[:, t:]
+        out, w = cache.step(cur[:, t].contiguous())
+    want, want_w = tr.decode(cur, enc_out.repeat_interleave(beam, 0), enc_len.repeat_interleave(beam, 0))
+    assert rel_l2(out, want[:, -1]) < 1e-5 and rel_l2(w, want_w[:, -1]) < 1e-5
+    with pytest.raises(sb.StacB200Error, match="full"):
+        cache.step(cur[:, 0].contiguous())

@@ -1,0 +1,55 @@
+"""Times one beam-search decoding step of the S model on the device, both ways (run on a B200):
+  * the reference's way, mutitask_decoder.py:119-128: the whole decoder over the whole prefix (TransformerMultiTask.decode),
+  * KV-cached (decoder.DecoderCache.step): one token per row over cached keys / values.
+  python tools/bench_decoder.py [--batch 64] [--beam 10] [--frames 751] [--prefix 32]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import stac_speech_translation_b200 as sb  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--beam", type=int, default=10)
+ap.add_argument("--frames", type=int, default=751)
+ap.add_argument("--prefix", type=int, default=32)
+a = ap.parse_args()
+torch.manual_seed(0)
+tr = sb.TransformerMultiTask(tgt_vocab=5000, input_size=5120, d_model=256, nhead=4, num_encoder_layers=1,
+                             num_decoder_layers=6, d_ffn=1024, activation=torch.nn.GELU, normalize_before=True,
+                             precision="bf16").eval().cuda()
+rows = a.batch * a.beam
+enc = torch.randn(a.batch, a.frames, 256, device="cuda")
+tok = torch.randint(1, 5000, (rows, a.prefix), device="cuda")
+
+
+def timed(fn, n=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+inflated = enc.repeat_interleave(a.beam, 0)
+ms_full = timed(lambda: tr.decode(tok, inflated))
+cache = tr.decoder_cache(enc, rows=rows, max_len=a.prefix + 8)
+for t in range(a.prefix - 1):
+    cache.step(tok[:, t].contiguous())
+t0 = cache.t
+
+
+def one_step():
+    cache.t = t0
+    cache.step(tok[:, t0].contiguous())
+
+
+ms_step = timed(one_step)
+print(f"rows {rows}  prefix {a.prefix}  frames {a.frames}:  full-prefix decode {ms_full:.3f} ms   cached step {ms_step:.3f} ms")

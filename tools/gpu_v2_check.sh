@@ -16,3 +16,4 @@ timeout 120 python tools/bench_mha.py stac_speech_translation_b200/libstac_b200.
 echo "bench_mha rc $?"; cat gpurun_out/v2_mha_bench.log
 STAC_MHA_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v2_bench.json 2> gpurun_out/v2_bench.err
 echo "bench (STAC_MHA_V2=1) rc $?"; tail -c 1200 gpurun_out/v2_bench.json
+timeout 300 python tools/bench_decoder.py > gpurun_out/v2_decoder_bench.log 2>&1; echo "bench_decoder rc $?"; cat gpurun_out/v2_decoder_bench.log
