@@ -22,6 +22,12 @@ reference's own ``encode()`` / ``forward()`` / ``make_masks()`` / ``EncoderWrapp
 inputs in ``tests/golden/glue_reference.npz``; ``tests/test_oracle.py`` holds the restated
 ``TransformerMultiTask`` to those vectors at 1e-6 and ``tests/test_gpu_glue_reference.py`` holds the
 CUDA encoder to them at the north-star tolerances.
+
+The two consumers right behind the path are pinned the same way: ``tests/golden/make_decoder_golden.py``
+runs the reference's own ``decode()`` / ``forward()`` (decoder half) over the restated TransformerDecoder
+(``tests/golden/decoder_reference.npz``), and ``tests/golden/make_turns_golden.py`` executes the reference's own
+``append_speaker_turns`` body, cut out of inference.py with ``ast`` (``tests/golden/turns_reference.json``), which pins
+``oracle/turns.py`` completely (that function has no SpeechBrain arithmetic in it).
 """
 from .speechbrain_path import (  # noqa: F401
     Fbank,
