@@ -240,6 +240,12 @@ int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float*
                        const int32_t* kv_len, const int64_t* key_tokens, int64_t pad_idx, float* ctx, int64_t ldctx,
                        float* weights, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * host ingest -- in front of a2: replaces shipping the fp32 waveform that librosa.load produced
+ *        (/root/reference/stac-st/inference.py:250-261, batch.to(device) :91).  out[i] = pcm[i] / 32768 (exactly the
+ *        value a 16-bit file decodes to); pcm and out 16-byte aligned. */
+int stac_pcm_i16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream);
+
 /* fp32 -> bf16 conversion (weight packing / activation hand-off) */
 int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);
 

@@ -222,3 +222,32 @@ def test_turn_detection_host_side():
         turns.append_speaker_turns(["a-b-0000100-c"], torch.zeros(1, 4, dtype=torch.int32), 7, 8, [], [])
     with pytest.raises(StacB200Error):
         turns.greedy_ids(torch.zeros(1, 4, 9))
+
+
+def test_ingest_collation_matches_padded_batch_semantics():
+    """ingest.collate against SpeechBrain's PaddedBatch behaviour for ``sig`` (right zero padding, wav_lens = len / max
+    as a double division stored in fp32) and the int16 -> fp32 decode rule (sample / 32768, exact)."""
+    from stac_speech_translation_b200 import ingest
+    from stac_speech_translation_b200._lib import StacB200Error
+    rng = np.random.default_rng(3)
+    turns = [rng.integers(-32768, 32768, n, dtype=np.int16) for n in (1600, 37, 4801)]
+    utt = ingest.concat_turns(turns)
+    assert utt.dtype == np.int16 and utt.shape == (1600 + 37 + 4801,) and np.array_equal(utt[1600:1637], turns[1])
+    batch = [utt, turns[0], turns[2][:4799]]
+    pcm, wl = ingest.collate(batch)
+    assert pcm.dtype == torch.int16 and pcm.shape == (3, utt.shape[0]) and wl.dtype == torch.float32
+    for i, u in enumerate(batch):
+        assert np.array_equal(pcm[i, :len(u)].numpy(), u) and not pcm[i, len(u):].any()
+        assert float(wl[i]) == float(np.float32(len(u) / len(utt)))
+    flat = torch.full((3 * utt.shape[0] + 5,), 9, dtype=torch.int16)
+    pcm2, wl2 = ingest.collate(batch, out=flat)
+    assert torch.equal(pcm2, pcm) and torch.equal(wl2, wl) and pcm2.data_ptr() == flat.data_ptr()
+    # the decode rule the device kernel applies is exact in fp32 and equals what a 16-bit file loads as
+    every = np.arange(-32768, 32768, dtype=np.int16)
+    assert np.array_equal((every.astype(np.float32) * np.float32(1 / 32768)).astype(np.float64), every / 32768.0)
+    with pytest.raises(StacB200Error):
+        ingest.collate([])
+    with pytest.raises(StacB200Error):
+        ingest.collate([np.zeros(4, np.float32)])
+    with pytest.raises(StacB200Error, match="no CPU fallback"):
+        ingest.pcm_to_float(torch.zeros(16, dtype=torch.int16))
