@@ -251,3 +251,23 @@ def test_ingest_collation_matches_padded_batch_semantics():
         ingest.collate([np.zeros(4, np.float32)])
     with pytest.raises(StacB200Error, match="no CPU fallback"):
         ingest.pcm_to_float(torch.zeros(16, dtype=torch.int16))
+
+
+def test_attention_v2_protocol_model_check():
+    """tools/model_check_mha2.py: the barrier protocol of csrc/attention_tc2.cu under random schedules (no deadlock, no
+    parity aliasing, no data hazard), and the checker itself catches the race DESIGN.md section 4 describes (a consumer
+    that jumps over uses of a parity-tracked mbarrier)."""
+    import importlib.util
+    path = os.path.join(ROOT, "tools", "model_check_mha2.py")
+    spec = importlib.util.spec_from_file_location("model_check_mha2", path)
+    mc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mc)
+    assert mc.check(runs=80, seed=11) == 80
+    src = open(path).read()
+    walk = src[src.index("                for _ in range(pc.n_kt):"):src.index("                sc = copy(pc)")]
+    jump = ("                for _ in range(pc.n_kt):\n                    self.kv_empty[pc.stage].arrive()\n"
+            "                    advance(pc)\n                    yield\n")
+    ns = {"__name__": "mutant"}
+    exec(compile(src.replace(walk, jump, 1), "mutant", "exec"), ns)
+    with pytest.raises(AssertionError):
+        ns["check"](200, 7)
