@@ -121,6 +121,34 @@ class Emulator:
                     ww[row * lk:(row + 1) * lk] = wacc.astype(np.float32)
 
 
+    def stac_argmax_rows(self, x, rows, cols, out, stream):
+        _arr(out, rows, np.int32)[:] = _arr(x, rows * cols).reshape(rows, cols).argmax(1)
+
+    def stac_ctc_spikes(self, ids, batch, t2, turn_id, xt_id, row_counts, spikes_turn, spikes_xt, n_out, stream):
+        flat = _arr(ids, batch * t2, np.int32)
+        for k, (tok, dst) in enumerate(((turn_id, spikes_turn), (xt_id, spikes_xt))):
+            pos = np.nonzero(flat == tok)[0]
+            _arr(dst, batch * t2, np.int32)[:len(pos)] = pos
+            _arr(n_out, 2, np.int32)[k] = len(pos)
+            _arr(row_counts, batch * 2, np.int32).reshape(batch, 2)[:, k] = (flat.reshape(batch, t2) == tok).sum(1)
+
+    def stac_pcm_i16_to_f32(self, pcm, n, out, stream):
+        _arr(out, n)[:] = _arr(pcm, n, np.int16).astype(np.float32) * np.float32(1 / 32768)
+
+
+class EmuLib:
+    """Stands in for the ctypes handle (`_lib.lib()`): every entry point returns STAC_OK after the emulator ran."""
+
+    def __init__(self, emu):
+        self._emu = emu
+
+    def __getattr__(self, name):
+        def fn(*args):
+            self._emu.call(name, *args)
+            return 0
+        return fn
+
+
 def cpu_ptr(t, dtype=None):
     """`_lib.ptr` without the is_cuda requirement (same contiguity / dtype checks)."""
     if t is None:
@@ -133,10 +161,12 @@ def cpu_ptr(t, dtype=None):
 
 def install(monkeypatch):
     """Route the host orchestration's kernel calls to the emulator (CPU tensors)."""
-    from stac_speech_translation_b200 import decoder, ops
+    from stac_speech_translation_b200 import decoder, ingest, ops, turns
     emu = Emulator()
-    for mod in (ops, decoder):
+    for mod in (ops, decoder, turns, ingest):
         monkeypatch.setattr(mod, "ptr", cpu_ptr)
         monkeypatch.setattr(mod, "stream", lambda: c_void_p(0))
+    for mod in (turns, ingest):
+        monkeypatch.setattr(mod, "lib", lambda: EmuLib(emu))
     monkeypatch.setattr(ops, "_call", emu.call)
     return emu

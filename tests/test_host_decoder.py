@@ -136,3 +136,21 @@ def test_kv_cached_steps_equal_the_full_prefix_decode(monkeypatch):
     assert rel_l2(out, want[:, -1]) < 1e-5 and rel_l2(w, want_w[:, -1]) < 1e-5
     with pytest.raises(sb.StacB200Error, match="full"):
         cache.step(cur[:, 0].contiguous())
+
+
+def test_turns_and_ingest_host_code_through_the_emulated_abi(monkeypatch):
+    """The Python side of turns.py / ingest.py (argument order, slicing of the compacted spikes, shapes) with the
+    emulator behind the C ABI: same golden lines as the reference function, same decode rule."""
+    import json
+    from stac_speech_translation_b200 import ingest, turns
+    abi_emulator.install(monkeypatch)
+    for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "turns_reference.json"))):
+        ids = torch.tensor(c["ids"], dtype=torch.int32)
+        p = torch.full(ids.shape + (c["vocab"],), -20.0)
+        p.scatter_(2, ids.long()[..., None], -0.1)
+        for x in (ids, p):
+            turn, xt = [], []
+            turns.append_speaker_turns(c["utt"], x, 7, 8, turn, xt)
+            assert turn == c["turn_rttm"] and xt == c["xt_rttm"]
+    pcm = torch.randint(-32768, 32768, (3, 1001), dtype=torch.int16)
+    assert torch.equal(ingest.pcm_to_float(pcm), pcm.float() / 32768.0)
