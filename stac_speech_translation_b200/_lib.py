@@ -7,12 +7,14 @@ device the call raises.  Build the library with ``python -m stac_speech_translat
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 from pathlib import Path
 
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent / "libstac_b200.so"
+# STAC_B200_LIB selects a variant build (python -m stac_speech_translation_b200.build --variant ...) for experiments
+LIB_PATH = Path(os.environ.get("STAC_B200_LIB") or Path(__file__).resolve().parent / "libstac_b200.so")
 
 OK = 0
 ACT_NONE, ACT_GELU_ERF = 0, 1

@@ -43,7 +43,17 @@ constexpr int kOffKV = 131072;                   // [stages] x (K 8 KB + V 8 KB)
 constexpr int kOffX = kOffKV + kKvStages * 16384;      // float [2 groups][2 bufs][2 halves][128 rows]: row-max exchange
 constexpr int kOffLen = kOffX + 2 * 2 * 2 * 128 * 4;   // int [kLenCache]
 constexpr int kOffBar = kOffLen + 128 * 4;
-constexpr int kNumBars = 8 + 2 * kKvStages + 20;
+// MHA_OSTAGED_PER_BUFFER (off in the default build until it has run on a B200): one o_staged barrier per (Q buffer,
+// group) instead of one per group.  tools/model_check_mha1.py shows that with one barrier per group a softmax group
+// that gets two short work items ahead of the store warp completes TWO phases of it before the store warp looks, the
+// parity wait aliases, and the kernel deadlocks (mbarrier time-out trap); a per-buffer barrier cannot run ahead, because
+// the buffer itself is only refilled after the store warp has released it.  DESIGN.md section 9.
+#ifdef MHA_OSTAGED_PER_BUFFER
+constexpr int kNumOStaged = 4;
+#else
+constexpr int kNumOStaged = 2;
+#endif
+constexpr int kNumBars = 8 + 2 * kKvStages + 18 + kNumOStaged;
 #ifdef MHA_TRACE
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024 + 5 * 64 * 8 * 4;
 #else
@@ -138,7 +148,12 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto p_full = [&](int w, int i) { return gb + 8u * (w * 9 + 4 + i); };
   auto p_free = [&](int w, int i) { return gb + 8u * (w * 9 + 6 + i); };
   auto o_free = [&](int w) { return gb + 8u * (w * 9 + 8); };
-  auto o_staged = [&](int w) { return gb + 8u * (18 + w); };     // the group's O tile is staged in smem for the store warp
+  // the group's O tile is staged in smem (in Q buffer `buf`) for the store warp
+#ifdef MHA_OSTAGED_PER_BUFFER
+  auto o_staged = [&](int buf, int w) { return gb + 8u * (18 + buf * 2 + w); };
+#else
+  auto o_staged = [&](int buf, int w) { (void)buf; return gb + 8u * (18 + w); };
+#endif
   const uint32_t tmem_slot = bars + 8u * kNumBars;
 #ifdef MHA_TRACE
   unsigned int* trace_s = reinterpret_cast<unsigned int*>(sptr + kOffBar + kNumBars * 8 + 16);
@@ -164,7 +179,8 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int i = 0; i < 2; ++i) {
         mbar_init(s_full(w, i), 1); mbar_init(s_free(w, i), 8); mbar_init(p_full(w, i), 8); mbar_init(p_free(w, i), 1);
       }
-      mbar_init(o_free(w), 8); mbar_init(o_staged(w), 8);
+      mbar_init(o_free(w), 8);
+      for (int buf = 0; buf < kNumOStaged / 2; ++buf) mbar_init(o_staged(buf, w), 8);
     }
     fence_barrier_init();
   }
@@ -209,14 +225,20 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     __syncwarp();
   } else if (warp == 19) {
     // ============================ output store warp ============================
-    uint32_t cnt[2] = {0, 0};
+    uint32_t st_par = 0;      // bit (barrier index): parity of the uses of that o_staged barrier
     int n_done = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_done) {
       const Item it = decode_item(item, n_done, len_cache, n_qblk, n_head, seq_len, kv_len);
       const int buf = n_done & 1;
       for (int w = 0; w < 2; ++w) {
         if (w == 1 && !it.active1) continue;
-        mbar_wait(o_staged(w), cnt[w]++ & 1);
+#ifdef MHA_OSTAGED_PER_BUFFER
+        const int bit = buf * 2 + w;
+#else
+        const int bit = w;
+#endif
+        mbar_wait(o_staged(buf, w), (st_par >> bit) & 1);
+        st_par ^= 1u << bit;
         if (elect_one()) {
           // rows past the end of the utterance are clipped by the 3-D map
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -498,7 +520,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(o_staged(w));
+        if (lane == 0) mbar_arrive(o_staged(ordinal & 1, w));
       }
       if ((warp & 7) == 0 && lane == 0) TRACE(3 + w, 7, g - 1);
     }

@@ -12,7 +12,11 @@ timeout 300 python -m pytest tests/test_gpu_turns.py tests/test_gpu_wav_ingest.p
 echo "turn-detection tests rc $?"; tail -5 gpurun_out/v2_turn_tests.log
 timeout 600 python -m pytest tests/test_gpu_decoder.py -q -x -m gpu > gpurun_out/v2_decoder_tests.log 2>&1
 echo "decoder tests rc $?"; tail -8 gpurun_out/v2_decoder_tests.log
-timeout 120 python tools/bench_mha.py stac_speech_translation_b200/libstac_b200.so > gpurun_out/v2_mha_bench.log 2>&1
+# the per-buffer o_staged fix of the default attention kernel: same tests on the variant build, then time it
+python -m stac_speech_translation_b200.build --variant ostaged -- -DMHA_OSTAGED_PER_BUFFER > gpurun_out/v2_variant_build.log 2>&1
+STAC_B200_LIB=$PWD/stac_speech_translation_b200/libstac_b200_ostaged.so timeout 600 python -m pytest tests/test_gpu_tc_attention.py tests/test_gpu_bf16_path.py -q -x -m gpu > gpurun_out/v2_ostaged_tests.log 2>&1
+echo "o_staged-per-buffer variant tests rc $?"; tail -3 gpurun_out/v2_ostaged_tests.log
+timeout 120 python tools/bench_mha.py stac_speech_translation_b200/libstac_b200.so stac_speech_translation_b200/libstac_b200_ostaged.so > gpurun_out/v2_mha_bench.log 2>&1
 echo "bench_mha rc $?"; cat gpurun_out/v2_mha_bench.log
 STAC_MHA_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v2_bench.json 2> gpurun_out/v2_bench.err
 echo "bench (STAC_MHA_V2=1) rc $?"; tail -c 1200 gpurun_out/v2_bench.json
