@@ -13,9 +13,13 @@ Mirrors what /root/reference/stac-st/modules/TransformerMultiTask.py builds and 
     feed-forward), final LayerNorm; the head-averaged cross-attention weights of the last layer are returned because
     the beam searcher receives them (``mutitask_decoder.py:126``).
 
-First correct path: fp32 on the CUDA cores in both precision modes (stac_gemm_f32, stac_layernorm, stac_embed_scale_pe,
-stac_attention_f32), the whole prefix per call exactly as the reference's ``forward_step`` asks for it.  None of the
-torch modules' ``forward`` is called; there is no CPU fallback.  Not yet run on a B200 (see csrc/decoder_f32.cu).
+Two drivers over the same entry points (fp32 on the CUDA cores in both precision modes: stac_gemm_f32, stac_layernorm,
+stac_embed_scale_pe, stac_attention_f32):
+  * ``decoder_stack``: the whole prefix per call, exactly what the reference's ``forward_step`` asks for
+    (``decode`` / ``forward`` semantics, pinned by vectors the reference's own code produced);
+  * ``DecoderCache``: KV-cached, one token per call (same results, tested equal), the shape a B200 wants.
+None of the torch modules' ``forward`` is called; there is no CPU fallback.  Not yet run on a B200 (see
+csrc/decoder_f32.cu); the host side is covered on the CPU through tests/abi_emulator.py.
 """
 from __future__ import annotations
 

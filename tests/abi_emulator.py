@@ -9,7 +9,6 @@ import ctypes
 from ctypes import c_void_p
 
 import numpy as np
-import torch
 from scipy.special import erf
 
 from stac_speech_translation_b200 import _lib
