@@ -118,6 +118,21 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+#ifdef MHA2_TRACE    // timing experiment only (tools/trace_mha2.py): CTA 0 logs clock64 per (role, step, event) to global memory
+__device__ unsigned int* g_trace2 = nullptr;
+#define TRACE2(role, ev, step)                                                                                   \
+  do {                                                                                                           \
+    if (blockIdx.x == 0 && g_trace2 != nullptr && (step) < 64)                                                    \
+      g_trace2[((role) * 64 + (step)) * 8 + (ev)] = (unsigned int)clock64();                                     \
+  } while (0)
+#else
+#define TRACE2(role, ev, step) do {} while (0)
+#endif
+// roles: 0 / 1 MMA issuer of group 0 / 1 (0 S-start, 1 operands ready, 2 S issued, 3 PV-start, 4 p_full passed,
+// 5 PV issued), 2 / 3 softmax warp 0 of group 0 / 1 (0 start, 1 s_full passed, 2 scores in registers, 3 maximum done,
+// 4 exponentials + P stores issued, 5 p_full arrived), 4 epilogue (per item: 0 start, 1 l_full, 2 o_full, 3 O read,
+// 4 staged, 5 store issued)
+
 struct Item {
   int b, h, q0, n_keys, n_kt;
   bool active1;      // the second query tile of the block exists
@@ -283,8 +298,10 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (sc.valid && !(w == 1 && sc.virt) && g_s < g_p + 1) {
             // ---- S(g_s) = Q K^T ----
             const int buf = sc.n_done & 1;
+            if (lane == 0) TRACE2(w, 0, g_s);
             mbar_wait(kv_full(sc.stage), sc.phase);
             if (sc.j == 0) mbar_wait(q_full(buf, w), (buf ? q_fill1 : q_fill0) & 1);
+            if (lane == 0) TRACE2(w, 1, g_s);
             tc_fence_after();
             const bool last_of_item = sc.j == sc.n_kt - 1;
             if (elect_one()) {
@@ -297,14 +314,17 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             __syncwarp();
             if (last_of_item) { if (buf) ++q_fill1; else ++q_fill0; }
+            if (lane == 0) TRACE2(w, 2, g_s);
             ++g_s;
             advance(sc);
           }
           // ---- O += P(g_p) V ----
           {
             const int ob = uses & 1;
+            if (lane == 0) TRACE2(w, 3, g_p);
             mbar_wait(p_full(w), (uint32_t)g_p & 1);
             if (pc.j == 0) mbar_wait(o_free(w, ob), ((uses >> 1) & 1) ^ 1);    // the epilogue has drained this O buffer
+            if (lane == 0) TRACE2(w, 4, g_p);
             tc_fence_after();
             const bool last_of_item = pc.j == pc.n_kt - 1;
             if (elect_one()) {
@@ -320,6 +340,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             __syncwarp();
             if (last_of_item) ++uses;
+            if (lane == 0) TRACE2(w, 5, g_p);
             ++g_p;
             advance(pc);
           }
@@ -347,9 +368,13 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int ob = uses[w] & 1;
         const uint32_t ph = (uses[w] >> 1) & 1;
         ++uses[w];
+        const bool tr = warp == 8 && lane == 0;
+        if (tr) TRACE2(4, 0, ordinal * 2 + w);
         mbar_wait(l_full(w, ob), ph);
+        if (tr) TRACE2(4, 1, ordinal * 2 + w);
         const float inv = xch[(w * 2 + ob) * 128 + r];
         mbar_wait(o_full(w, ob), ph);
+        if (tr) TRACE2(4, 2, ordinal * 2 + w);
         tc_fence_after();
         // the previous TMA store out of this group's staging tile must have read it
         if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -373,8 +398,10 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_free(w, ob));     // O buffer and 1 / l slot may be reused
+        if (tr) TRACE2(4, 3, ordinal * 2 + w);
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
+        if (tr) TRACE2(4, 4, ordinal * 2 + w);
         if (warp == 8 && lane == 0) {
           // rows past the end of the utterance are clipped by the 3-D map
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -382,6 +409,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                          "r"(it.h * kHd), "r"(it.q0 + w * kQTile), "r"(it.b) : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (tr) TRACE2(4, 5, ordinal * 2 + w);
       }
     }
     if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -408,12 +436,16 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       constexpr float kRaise = 40.0f;
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < it.n_kt; ++j, ++g) {
+        const bool tr = (warp & 3) == 0 && lane == 0;
+        if (tr) TRACE2(2 + w, 0, g);
         mbar_wait(s_full(w), g & 1);
+        if (tr) TRACE2(2 + w, 1, g);
         tc_fence_after();
         uint32_t v[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, v[c]);
         tmem_ld_wait();
+        if (tr) TRACE2(2 + w, 2, g);
         const int valid = it.n_keys - j * kKTile;      // my columns < valid are real keys
         if (valid < kKTile) {
           // last tile of the utterance only (a real branch: the full tiles must not pay 128 compare / select pairs)
@@ -449,6 +481,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           }
         }
+        if (tr) TRACE2(2 + w, 3, g);
         const float m_scaled = m_ref * kLog2e;
         float2 l0 = make_float2(0.f, 0.f), l1 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -472,10 +505,12 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           tmem_st16(s_tmem + c * 16, pk);
         }
         l_run += (l0.x + l0.y) + (l1.x + l1.y);
+        if (tr && l_run != 123.f) TRACE2(2 + w, 4, g);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full(w));
+        if (tr) TRACE2(2 + w, 5, g);
       }
       // end of the item: hand 1 / l to the epilogue warpgroup.  The slot (and the O buffer) were last used two items of
       // this group ago; o_free says the epilogue is done with both.
@@ -493,6 +528,13 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 }  // namespace
+
+#ifdef MHA2_TRACE
+extern "C" int stac_mha2_trace(unsigned int* buf) {
+  cudaMemcpyToSymbol(g_trace2, &buf, sizeof(buf));
+  return 0;
+}
+#endif
 
 extern "C" int stac_mha_bf16_v2(const uint16_t* qkv, const int32_t* kv_len, int64_t batch, int64_t seq_len,
                                 int64_t d_model, int64_t n_head, uint16_t* ctx, void* stream) {

@@ -21,3 +21,6 @@ echo "bench_mha rc $?"; cat gpurun_out/v2_mha_bench.log
 STAC_MHA_V2=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/v2_bench.json 2> gpurun_out/v2_bench.err
 echo "bench (STAC_MHA_V2=1) rc $?"; tail -c 1200 gpurun_out/v2_bench.json
 timeout 300 python tools/bench_decoder.py > gpurun_out/v2_decoder_bench.log 2>&1; echo "bench_decoder rc $?"; cat gpurun_out/v2_decoder_bench.log
+python -m stac_speech_translation_b200.build --variant mha2trace -- -DMHA2_TRACE > gpurun_out/v2_trace_build.log 2>&1
+timeout 120 python tools/trace_mha2.py stac_speech_translation_b200/libstac_b200_mha2trace.so > gpurun_out/v2_mha2_trace.log 2>&1
+echo "trace_mha2 rc $?"; tail -12 gpurun_out/v2_mha2_trace.log
