@@ -154,3 +154,73 @@ def test_turns_and_ingest_host_code_through_the_emulated_abi(monkeypatch):
             assert turn == c["turn_rttm"] and xt == c["xt_rttm"]
     pcm = torch.randint(-32768, 32768, (3, 1001), dtype=torch.int16)
     assert torch.equal(ingest.pcm_to_float(pcm), pcm.float() / 32768.0)
+
+
+class _StubBeamSearcher:
+    """A minimal beam search with the calling convention of SpeechBrain's S2SBeamSearcher as the reference's subclass
+    sees it (reset_mem -> per step: forward_step, top-k over beam x vocab, permute_mem): enough to drive both
+    forward_step implementations through identical control flow.  NOT a restatement of SpeechBrain's searcher."""
+
+    def __init__(self, model, fc, beam_size, bos_index, prefix, temperature=1.15):
+        self.model, self.fc, self.beam_size, self.bos_index = model, fc, beam_size, bos_index
+        self.decoder_input_tokens, self.temperature = prefix, temperature
+        self.softmax = torch.nn.LogSoftmax(dim=-1)
+
+    def search(self, enc_states, steps):
+        b = enc_states.shape[0]
+        beam = self.beam_size
+        enc = enc_states.repeat_interleave(beam, 0)
+        memory = self.reset_mem(b * beam, enc.device)
+        inp = torch.full((b * beam,), self.bos_index, dtype=torch.long)
+        scores = torch.zeros(b, beam)
+        scores[:, 1:] = -1e9
+        trace = []
+        for _ in range(steps):
+            logp, memory, attn = self.forward_step(inp, memory, enc, None)
+            vocab = logp.shape[-1]
+            cand = (scores.view(b * beam, 1) + logp).view(b, beam * vocab)
+            scores, idx = cand.topk(beam, dim=-1)
+            pred = (idx // vocab + torch.arange(b)[:, None] * beam).view(-1)
+            inp = (idx % vocab).view(-1)
+            memory = self.permute_mem(memory, pred)
+            trace.append((scores.clone(), inp.clone(), pred.clone(), attn[:, -1].clone()))
+        return memory, trace
+
+
+def test_cached_forward_step_drives_the_same_search_as_the_reference_forward_step(monkeypatch):
+    """searcher.CachedStepMixin against the reference's forward_step / permute_mem / reset_mem bodies
+    (mutitask_decoder.py:101-128, restated in the baseline class below) under the same beam-search control flow: same
+    hypotheses, scores and back-pointers at every step."""
+    from stac_speech_translation_b200.searcher import CachedStepMixin, _update_mem
+    d, state = fixture()
+    abi_emulator.install(monkeypatch)
+    tr = build(sb.TransformerMultiTask, state, precision="fp32")
+    torch.manual_seed(5)
+    fc = torch.nn.Linear(tr.d_model, tr.tgt_vocab)
+
+    class ReferenceStep(_StubBeamSearcher):           # mutitask_decoder.py:101-128, verbatim semantics
+        def reset_mem(self, batch_size, device):
+            return torch.tensor([self.decoder_input_tokens] * batch_size).to(device)
+
+        def permute_mem(self, memory, index):
+            return torch.index_select(memory, dim=0, index=index)
+
+        def forward_step(self, inp_tokens, memory, enc_states, enc_lens):
+            if not torch.all(inp_tokens == self.bos_index):
+                memory = _update_mem(inp_tokens, memory)
+            pred, attn = self.model.decode(memory, enc_states)
+            prob_dist = self.softmax(self.fc(pred) / self.temperature)
+            return prob_dist[:, -1, :], memory, attn
+
+    class CachedStep(CachedStepMixin, _StubBeamSearcher):
+        pass
+
+    enc_out = torch.from_numpy(d["enc_out"])
+    args = dict(model=tr, fc=fc, beam_size=3, bos_index=1, prefix=[1, 9, 12])
+    with torch.no_grad():
+        mem_ref, trace_ref = ReferenceStep(**args).search(enc_out, steps=5)
+        mem_new, trace_new = CachedStep(**args).search(enc_out, steps=5)
+    assert torch.equal(mem_ref, mem_new)
+    for (s0, i0, p0, a0), (s1, i1, p1, a1) in zip(trace_ref, trace_new):
+        assert torch.equal(i0, i1) and torch.equal(p0, p1)
+        assert rel_l2(s1, s0) < 1e-5 and rel_l2(a1, a0) < 1e-4
