@@ -37,7 +37,10 @@ namespace {
 using namespace tc;
 
 constexpr int kHd = 64, kQTile = 128, kKTile = 128;
-constexpr int kKvStages = 3;
+#ifndef MHA2_KV_STAGES
+#define MHA2_KV_STAGES 3
+#endif
+constexpr int kKvStages = MHA2_KV_STAGES;            // 32 KB each; 3 is the most that fits beside Q (64 KB) and the staging tiles (32 KB)
 constexpr int kThreads = 512;
 constexpr int kRegsSoftmax = 176, kRegsOther = 80;     // 256 * 176 + 256 * 80 = 512 * 128
 #ifndef MHA2_POLY
@@ -53,6 +56,7 @@ constexpr int kLenCache = 128;
 constexpr int kOffBar = kOffLen + kLenCache * 4;
 constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 8;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
+static_assert(kKvStages >= 2 && kSmemBytes <= 232448, "K/V ring does not fit in shared memory");
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_mufu(float x) {
