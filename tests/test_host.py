@@ -291,3 +291,22 @@ def test_default_attention_protocol_model_check():
             mc.check(runs=300, seed=3, per_buffer=False)
     finally:
         sys.path.remove(sys_path)
+
+
+def test_fused_ffn_protocol_model_check():
+    """tools/model_check_ffn.py: the fused feed-forward kernel as built (one issuer warp) has no deadlock / aliasing /
+    hazard under random schedules with heavy-tailed TMA latencies, and the checker reproduces the race of the earlier
+    two-issuer design that only ever fired on an 8-GPU run."""
+    import importlib.util
+    import sys
+    tools = os.path.join(ROOT, "tools")
+    sys.path.insert(0, tools)
+    try:
+        spec = importlib.util.spec_from_file_location("model_check_ffn", os.path.join(tools, "model_check_ffn.py"))
+        mc = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mc)
+        assert mc.check(runs=100, seed=2) == 100
+        with pytest.raises(AssertionError, match="meant completion|holds unit"):
+            mc.check(runs=400, seed=1, two_issuers=True)
+    finally:
+        sys.path.remove(tools)

@@ -123,7 +123,9 @@ class Sim:
         self.kv_full[s].arrive()
 
     def later(self, action):
-        self.async_events.append([self.rng.randint(0, 6), action])
+        # mostly short, sometimes very long (a congested memory system re-orders completions across many steps)
+        delay = self.rng.randint(0, 6) if self.rng.random() < 0.85 else self.rng.randint(50, 400)
+        self.async_events.append([delay, action])
 
     def issuer(self, w):
         items = self.items
