@@ -310,3 +310,23 @@ def test_fused_ffn_protocol_model_check():
             mc.check(runs=400, seed=1, two_issuers=True)
     finally:
         sys.path.remove(tools)
+
+
+def test_custom_op_layer_registers_and_propagates_shapes():
+    """custom_ops.py: the tensor-in / tensor-out entry points as torch.ops.stac_b200.* with fake-tensor shape functions
+    (what torch.compile / export need); still no CPU implementation."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import stac_speech_translation_b200.custom_ops  # noqa: F401
+    ns = torch.ops.stac_b200
+    with FakeTensorMode():
+        f = ns.fbank(torch.empty(4, 16000), 80.0, True)
+        assert f.shape == (4, 101, 80) and f.dtype == torch.float32
+        assert ns.input_norm(f, torch.empty(80), torch.empty(80)).shape == f.shape
+        y = ns.linear(torch.empty(4, 26, 256), torch.empty(5000, 256), None, "fp32")
+        assert y.shape == (4, 26, 5000) and ns.log_softmax(y).shape == y.shape
+        out, ids = ns.log_softmax_greedy(y)
+        assert out.shape == y.shape and ids.shape == (4, 26) and ids.dtype == torch.int32
+        assert ns.argmax_rows(out).dtype == torch.int32
+        assert ns.pcm_to_float(torch.empty(3, 100, dtype=torch.int16)).dtype == torch.float32
+    with pytest.raises(sb.StacB200Error, match="no CPU fallback"):
+        ns.input_norm(torch.zeros(1, 4, 80), torch.zeros(80), torch.ones(80))
