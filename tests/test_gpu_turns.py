@@ -8,7 +8,10 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# Written after the round-1 GPU budget was spent: not part of the default GPU suite until it has run on a B200 once
+# (STAC_EXPERIMENTAL=1 enables it; tools/gpu_v2_check.sh runs it first thing next round).
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("STAC_EXPERIMENTAL") != "1", reason="not yet run on a B200")]
 
 from oracle import turns as oturns  # noqa: E402
 from stac_speech_translation_b200 import turns  # noqa: E402

@@ -1,10 +1,15 @@
 """int16 PCM ingest on the device (stac_pcm_i16_to_f32, ingest.PcmStager) against the decode rule of a 16-bit file
 (sample / 32768): exact."""
 import numpy as np
+import os
+
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# Written after the round-1 GPU budget was spent: not part of the default GPU suite until it has run on a B200 once
+# (STAC_EXPERIMENTAL=1 enables it; tools/gpu_v2_check.sh runs it first thing next round).
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("STAC_EXPERIMENTAL") != "1", reason="not yet run on a B200")]
 
 from stac_speech_translation_b200 import ingest  # noqa: E402
 
