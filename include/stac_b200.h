@@ -246,6 +246,14 @@ int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float*
  *        value a 16-bit file decodes to); pcm and out 16-byte aligned. */
 int stac_pcm_i16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * training-stage statistics of InputNormalization -- replaces the per-utterance torch.mean / torch.std
+ *        loop of normalize(feats, wav_lens, epoch) in train mode (/root/reference/stac-st/train_multitask.py:60-61):
+ *        mean / unbiased std (floored at eps) of x[b, :round(wav_len[b] * frames), :] per utterance and bin;
+ *        x [batch, frames, dim], wav_len fp32 [batch], mean / std fp32 [batch, dim].  Not yet run on a B200. */
+int stac_utt_mean_std(const float* x, const float* wav_len, int64_t batch, int64_t frames, int64_t dim, float eps,
+                      float* mean, float* std, void* stream);
+
 /* fp32 -> bf16 conversion (weight packing / activation hand-off) */
 int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);
 

@@ -61,8 +61,10 @@ class InputNormalization(nn.Module):
     Eval-mode forward is ``(x - glob_mean) / glob_std`` on the GPU.  The running statistics are
     plain attributes saved/restored through ``_save`` / ``_load`` exactly like SpeechBrain's
     ``normalizer.ckpt`` (dict keys count/glob_mean/glob_std/spk_dict_*).  Updating the statistics
-    (train mode) is outside the accelerated path: ``forward`` raises in training mode;
-    ``calibrate`` computes them once from a batch with SpeechBrain's formula.
+    (train mode, ``train_multitask.py:60-61``): the per-utterance mean / std over the valid frames come from
+    ``stac_utt_mean_std`` on the device, the running-average update of the 80 global values is SpeechBrain's code on the
+    host copies (first device version, not yet run on a B200).  ``calibrate`` computes them once from a batch with
+    SpeechBrain's formula.
     """
 
     def __init__(self, mean_norm=True, std_norm=True, norm_type="global", avg_factor=None,
@@ -84,10 +86,31 @@ class InputNormalization(nn.Module):
     @torch.no_grad()
     def forward(self, x, lengths=None, spk_ids=torch.tensor([]), epoch=0):
         if self.training:
-            raise StacB200Error("stac_b200 InputNormalization is inference-only: call .eval() "
-                                "(statistics come from the checkpoint or from calibrate())")
+            if lengths is None:
+                raise StacB200Error("InputNormalization needs the relative lengths in training mode")
+            self._update_statistics(x, lengths, epoch)
         mean, std = self.device_stats(x.device, x.shape[-1])
         return ops.input_norm(x.float(), mean, std)
+
+    def _update_statistics(self, x, lengths, epoch):
+        """SpeechBrain's train-mode step: per-utterance statistics (device), batch average and running update (host)."""
+        x = x.float().contiguous()
+        b, t, f = x.shape
+        wl = lengths.to(device=x.device, dtype=torch.float32).contiguous()
+        means = torch.empty(b, f, device=x.device, dtype=torch.float32)
+        stds = torch.empty(b, f, device=x.device, dtype=torch.float32)
+        ops._call("stac_utt_mean_std", ops.ptr(x, torch.float32), ops.ptr(wl, torch.float32), b, t, f, float(self.eps),
+                  ops.ptr(means), ops.ptr(stds), ops.stream())
+        current_mean = torch.mean(means.cpu(), dim=0)
+        current_std = torch.mean(stds.cpu(), dim=0)
+        if self.count == 0:
+            self.glob_mean, self.glob_std = current_mean, current_std
+        elif epoch < self.update_until_epoch:
+            self.weight = 1 / (self.count + 1) if self.avg_factor is None else self.avg_factor
+            self.glob_mean = (1 - self.weight) * self.glob_mean.cpu() + self.weight * current_mean
+            self.glob_std = (1 - self.weight) * self.glob_std.cpu() + self.weight * current_std
+        self.count = self.count + 1
+        self._dev_stats = None
 
     def device_stats(self, device, n_mels):
         if self.glob_mean.numel() != n_mels:

@@ -120,6 +120,18 @@ class Emulator:
                     ww[row * lk:(row + 1) * lk] = wacc.astype(np.float32)
 
 
+    def stac_utt_mean_std(self, x, wav_len, batch, frames, dim, eps, mean, std, stream):
+        xx = _arr(x, batch * frames * dim).reshape(batch, frames, dim).astype(np.float64)
+        wl = _arr(wav_len, batch)
+        for b in range(batch):
+            n = int(np.rint(np.float32(wl[b]) * np.float32(frames)))
+            seg = xx[b, :n]
+            _arr(mean, batch * dim).reshape(batch, dim)[b] = seg.mean(0)
+            _arr(std, batch * dim).reshape(batch, dim)[b] = np.maximum(seg.std(0, ddof=1), eps)
+
+    def stac_input_norm(self, x, mean, std, rows, dim, out, stream):
+        _arr(out, rows * dim).reshape(rows, dim)[:] = (_arr(x, rows * dim).reshape(rows, dim) - _arr(mean, dim)) / _arr(std, dim)
+
     def stac_argmax_rows(self, x, rows, cols, out, stream):
         _arr(out, rows, np.int32)[:] = _arr(x, rows * cols).reshape(rows, cols).argmax(1)
 

@@ -224,3 +224,24 @@ def test_cached_forward_step_drives_the_same_search_as_the_reference_forward_ste
     for (s0, i0, p0, a0), (s1, i1, p1, a1) in zip(trace_ref, trace_new):
         assert torch.equal(i0, i1) and torch.equal(p0, p1)
         assert rel_l2(s1, s0) < 1e-5 and rel_l2(a1, a0) < 1e-4
+
+
+def test_train_mode_input_normalization_follows_speechbrain_updates(monkeypatch):
+    """features.InputNormalization in training mode (device statistics through the emulated ABI + SpeechBrain's running
+    update on the host) against the oracle's restatement over several steps, epochs and the eval call that follows."""
+    from oracle.speechbrain_path import InputNormalization as OracleNorm
+    abi_emulator.install(monkeypatch)
+    g = torch.Generator().manual_seed(4)
+    ours = sb.InputNormalization(norm_type="global", update_until_epoch=2).train()
+    ref = OracleNorm(norm_type="global", update_until_epoch=2).train()
+    for step, epoch in enumerate([0, 0, 1, 2, 3]):
+        x = torch.randn(3, 50, 80, generator=g) * (1 + step) + step
+        wl = torch.tensor([1.0, 0.73, 0.41])
+        got, want = ours(x, wl, epoch=epoch), ref(x, wl, epoch=epoch)
+        assert rel_l2(got, want) < 1e-5, (step, epoch)
+        assert ours.count == ref.count and rel_l2(ours.glob_mean, ref.glob_mean) < 1e-6
+        assert rel_l2(ours.glob_std, ref.glob_std) < 1e-6
+    ours.eval(), ref.eval()
+    x = torch.randn(2, 30, 80, generator=g)
+    assert rel_l2(ours(x, torch.ones(2)), ref(x, torch.ones(2))) < 1e-5
+    assert ours.count == ref.count == 5

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 export STAC_EXPERIMENTAL=1
 timeout 300 python -m pytest tests/test_gpu_tc_attention.py -q -x -m gpu -k v2 > gpurun_out/v2_mha_tests.log 2>&1
 echo "attention v2 tests rc $?"; tail -5 gpurun_out/v2_mha_tests.log
-timeout 300 python -m pytest tests/test_gpu_turns.py tests/test_gpu_wav_ingest.py tests/test_gpu_xcustom_ops.py -q -m gpu > gpurun_out/v2_turn_tests.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_turns.py tests/test_gpu_wav_ingest.py tests/test_gpu_xcustom_ops.py tests/test_gpu_ytrain_norm.py -q -m gpu > gpurun_out/v2_turn_tests.log 2>&1
 echo "turn-detection tests rc $?"; tail -5 gpurun_out/v2_turn_tests.log
 timeout 600 python -m pytest tests/test_gpu_decoder.py -q -x -m gpu > gpurun_out/v2_decoder_tests.log 2>&1
 echo "decoder tests rc $?"; tail -8 gpurun_out/v2_decoder_tests.log
