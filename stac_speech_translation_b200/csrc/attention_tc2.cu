@@ -24,6 +24,11 @@
 // Budget per 128-key step of one CTA (2 x 128 query rows): MUFU 2 x 128 x 128 / 16 = 2048 clk, tensor pipe
 // 2 x (256 + 256) = 1024 clk; the first kernel needs 2 x 1950 = 3900 clk for the same work.
 //
+// The TMEM conventions this relies on - thread = lane = query row for 32x32b loads / stores, P as packed bf16 pairs
+// (keys 2c, 2c+1 in 32-bit column c, even key in the low half) on top of its own scores, 8 columns per K = 16 step of
+// the TS-form MMA - are the ones the public CUTLASS CuTeDSL Blackwell FMHA example uses (St32x32b of the score
+// registers recast to the 16-bit type; P.V fragments taken from TMEM); read for the conventions only, no code shared.
+//
 // TMEM (512 columns): S/P group 0 at 0, group 1 at 128 (128 fp32 score columns; P = 64 columns of packed bf16 pairs
 // on top of the first 64); O[group][buffer] at 256 + (group * 2 + buffer) * 64.
 // Threads (512): warps 0-3 softmax group 0, 4-7 softmax group 1 (warp & 3 = TMEM lane quarter), 8-11 epilogue
