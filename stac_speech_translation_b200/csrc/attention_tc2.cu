@@ -59,7 +59,16 @@ constexpr int kOffX = kOffKV + kKvStages * 32768;      // float [2 groups][2 O b
 constexpr int kOffLen = kOffX + 2 * 2 * 128 * 4;       // int [kLenCache]
 constexpr int kLenCache = 128;
 constexpr int kOffBar = kOffLen + kLenCache * 4;
-constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 8;
+// -DMHA2_SEQUENCE (experiment, default off): the two softmax groups take strict turns in their exponential phase
+// (group 0 step g, group 1 step g, group 0 step g+1, ...) through two more barriers, so that each group's TMEM load /
+// maximum / P store falls into the other group's exponentials instead of competing with them for the MUFU.  Group 1
+// walks the sequence as virtual steps through items in which it has no query tile.
+#ifdef MHA2_SEQUENCE
+constexpr int kNumSeqBars = 2;
+#else
+constexpr int kNumSeqBars = 0;
+#endif
+constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 8 + kNumSeqBars;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 static_assert(kKvStages >= 2 && kSmemBytes <= 232448, "K/V ring does not fit in shared memory");
 constexpr float kLog2e = 1.4426950408889634f;
@@ -182,6 +191,9 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   auto o_full = [&](int w, int ob) { return gb + 8u * (w * 8 + 2 + ob); };   // MMA commit: last P.V of the item retired
   auto l_full = [&](int w, int ob) { return gb + 8u * (w * 8 + 4 + ob); };   // 4 softmax warps: 1 / l is in smem
   auto o_free = [&](int w, int ob) { return gb + 8u * (w * 8 + 6 + ob); };   // 4 epilogue warps: O and 1 / l were read
+#ifdef MHA2_SEQUENCE
+  auto seq_done = [&](int w) { return gb + 8u * (16 + w); };      // 4 softmax warps of group w: exponentials of a step issued
+#endif
   const uint32_t tmem_slot = bars + 8u * kNumBars;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,6 +212,9 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(s_full(w), 1);
       mbar_init(p_full(w), 4);
       for (int ob = 0; ob < 2; ++ob) { mbar_init(o_full(w, ob), 1); mbar_init(l_full(w, ob), 4); mbar_init(o_free(w, ob), 4); }
+#ifdef MHA2_SEQUENCE
+      mbar_init(seq_done(w), 4);
+#endif
     }
     fence_barrier_init();
   }
@@ -434,9 +449,24 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint32_t g = 0;                                // per-group step index
     uint32_t uses = 0;
     int ordinal = 0;
+#ifdef MHA2_SEQUENCE
+    uint32_t gs = 0;                               // position in the exponential sequence (virtual steps included)
+#endif
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
       const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
+#ifdef MHA2_SEQUENCE
+      if (w == 1 && !it.active1) {
+        // no query tile for this group: keep the turn-taking going, one virtual step per key tile
+        for (int j = 0; j < it.n_kt; ++j, ++gs) {
+          mbar_wait(seq_done(0), gs & 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(seq_done(1));
+        }
+        continue;
+      }
+#else
       if (w == 1 && !it.active1) continue;
+#endif
       const int ob = uses & 1;
       const uint32_t o_tmem = tmem_base + 256 + (w * 2 + ob) * kHd + lane_off;
       // m_ref: the maximum the exponents are taken against.  It is only raised (and O / l rescaled) when the running
@@ -491,6 +521,10 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         if (tr) TRACE2(2 + w, 3, g);
+#ifdef MHA2_SEQUENCE
+        if (w == 0) { if (gs > 0) mbar_wait(seq_done(1), (gs - 1) & 1); }     // group 1 is through step gs - 1
+        else mbar_wait(seq_done(0), gs & 1);                                   // group 0 is through step gs
+#endif
         const float m_scaled = m_ref * kLog2e;
         float2 l0 = make_float2(0.f, 0.f), l1 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -515,6 +549,11 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         l_run += (l0.x + l0.y) + (l1.x + l1.y);
         if (tr && l_run != 123.f) TRACE2(2 + w, 4, g);
+#ifdef MHA2_SEQUENCE
+        __syncwarp();
+        if (lane == 0) mbar_arrive(seq_done(w));
+        ++gs;
+#endif
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

@@ -263,6 +263,8 @@ def test_attention_v2_protocol_model_check():
     mc = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mc)
     assert mc.check(runs=80, seed=11) == 80
+    assert mc.check(runs=80, seed=12, sequence=True) == 80          # -DMHA2_SEQUENCE variant
+    mc.SEQUENCE = False
     src = open(path).read()
     walk = src[src.index("                for _ in range(pc.n_kt):"):src.index("                sc = copy(pc)")]
     jump = ("                for _ in range(pc.n_kt):\n                    self.kv_empty[pc.stage].arrive()\n"

@@ -24,8 +24,8 @@ timeout 300 python tools/bench_decoder.py > gpurun_out/v2_decoder_bench.log 2>&1
 python -m stac_speech_translation_b200.build --variant mha2trace -- -DMHA2_TRACE > gpurun_out/v2_trace_build.log 2>&1
 timeout 120 python tools/trace_mha2.py stac_speech_translation_b200/libstac_b200_mha2trace.so > gpurun_out/v2_mha2_trace.log 2>&1
 echo "trace_mha2 rc $?"; tail -12 gpurun_out/v2_mha2_trace.log
-# attention v2 knobs: share of exponentials on the FMA pipe, depth of the K/V ring (3 is the most that fits; each variant: its own build, timed alone)
-for v in "poly2:-DMHA2_POLY=2" "poly4:-DMHA2_POLY=4" "kv2:-DMHA2_KV_STAGES=2"; do
+# attention v2 knobs: share of exponentials on the FMA pipe, depth of the K/V ring, softmax groups taking turns (3 is the most that fits; each variant: its own build, timed alone)
+for v in "poly2:-DMHA2_POLY=2" "poly4:-DMHA2_POLY=4" "kv2:-DMHA2_KV_STAGES=2" "seq:-DMHA2_SEQUENCE"; do
   name=${v%%:*}; flag=${v#*:}
   python -m stac_speech_translation_b200.build --variant $name -- $flag > gpurun_out/v2_build_$name.log 2>&1
   timeout 120 python tools/bench_mha.py stac_speech_translation_b200/libstac_b200_$name.so > gpurun_out/v2_mha_bench_$name.log 2>&1

@@ -22,6 +22,7 @@ import random
 import sys
 
 KV_STAGES = 3
+SEQUENCE = False        # -DMHA2_SEQUENCE: the two softmax groups take strict turns in their exponential phase
 
 
 class Hazard(AssertionError):
@@ -65,6 +66,8 @@ class Sim:
         self.o_full = [[MBar(f"o_full[{w}][{o}]", 1) for o in range(2)] for w in range(2)]
         self.l_full = [[MBar(f"l_full[{w}][{o}]", 4) for o in range(2)] for w in range(2)]
         self.o_free = [[MBar(f"o_free[{w}][{o}]", 4) for o in range(2)] for w in range(2)]
+        self.seq_done = [MBar(f"seq_done[{w}]", 4) for w in range(2)]
+        self.exp_turns = []                            # (group, sequence step) in the order the exponential phases ran
         # asynchronous completions: list of [delay, action]; the MMA streams are FIFOs (in-order per issuer)
         self.async_events = []
         self.mma_fifo = [[], []]
@@ -234,9 +237,15 @@ class Sim:
 
     def softmax(self, w, warp):
         """One of the four warps of softmax group w (the barrier counts are per warp)."""
-        g = uses = 0
+        g = uses = gs = 0
         for n_kt, active1 in self.items:
             if w == 1 and not active1:
+                if SEQUENCE:
+                    for _ in range(n_kt):
+                        yield from wait(self.seq_done[0], gs & 1, gs)
+                        self.seq_done[1].arrive()
+                        gs += 1
+                        yield
                 continue
             ob = uses & 1
             for j in range(n_kt):
@@ -247,6 +256,17 @@ class Sim:
                     if self.pv_done[w] != g:
                         raise Hazard("O rescaled while an earlier P.V was still in flight")
                 yield
+                if SEQUENCE:
+                    if w == 0:
+                        if gs > 0:
+                            yield from wait(self.seq_done[1], (gs - 1) & 1, gs - 1)
+                    else:
+                        yield from wait(self.seq_done[0], gs & 1, gs)
+                    if warp == 0:
+                        self.exp_turns.append((w, gs))
+                    yield
+                    self.seq_done[w].arrive()
+                    gs += 1
                 if self.s_version[w] != g:
                     raise Hazard("S overwritten while the softmax was still reading it")
                 if warp == 0:
@@ -322,14 +342,18 @@ class Sim:
         want = [(n, w) for n, (_, a1) in enumerate(self.items) for w in range(2) if w == 0 or a1]
         if sorted(self.outputs) != want:
             raise Hazard("not every (item, group) tile was written exactly once")
+        if SEQUENCE and self.exp_turns != sorted(self.exp_turns, key=lambda t: (t[1], t[0])):
+            raise Hazard("the exponential phases did not run in turn order")
 
     def snapshot(self):
         bars = [b for row in (self.q_full + self.q_empty + self.o_full + self.l_full + self.o_free) for b in row]
-        bars += self.kv_full + self.kv_empty + self.s_full + self.p_full
+        bars += self.kv_full + self.kv_empty + self.s_full + self.p_full + self.seq_done
         return tuple((b.phase, b.pending) for b in bars) + (len(self.outputs),)
 
 
-def check(runs=200, seed=0):
+def check(runs=200, seed=0, sequence=False):
+    global SEQUENCE
+    SEQUENCE = sequence
     rng = random.Random(seed)
     for r in range(runs):
         n_items = rng.randint(1, 7)
@@ -341,4 +365,6 @@ def check(runs=200, seed=0):
 if __name__ == "__main__":
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    print("ok:", check(runs, seed), "random schedules, no deadlock, no parity aliasing, no data hazard")
+    sequence = "--sequence" in sys.argv
+    print("ok:", check(runs, seed, sequence), "random schedules, no deadlock, no parity aliasing, no data hazard",
+          "(softmax groups take turns: -DMHA2_SEQUENCE)" if sequence else "")
