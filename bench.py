@@ -121,6 +121,7 @@ def work_table(size_cfg, batch, n_samples, kv_len_sum_sq_like):
         "stac_layernorm": ("hbm", m * d * (4 + 2), 2 * layers + 1),
         "stac_gemm_bf16:qkv": ("tensor", 2 * d * 3 * d * m, layers),
         "stac_mha_bf16": ("tensor", 4 * d * kv_len_sum_sq_like, layers),
+        "stac_mha_bf16_v2": ("tensor", 4 * d * kv_len_sum_sq_like, layers),     # STAC_MHA_V2=1 (experimental kernel)
         "stac_gemm_bf16:out_proj": ("tensor", 2 * d * d * m, layers),
         "stac_gemm_bf16:ffn1": ("tensor", 2 * d * dffn * m, layers),
         "stac_gemm_bf16:ffn2": ("tensor", 2 * d * dffn * m, layers),
