@@ -332,3 +332,22 @@ def test_custom_op_layer_registers_and_propagates_shapes():
         assert ns.pcm_to_float(torch.empty(3, 100, dtype=torch.int16)).dtype == torch.float32
     with pytest.raises(sb.StacB200Error, match="no CPU fallback"):
         ns.input_norm(torch.zeros(1, 4, 80), torch.zeros(80), torch.ones(80))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): one JSON line on stdout with the contract's
+    keys, its own cpu_baseline description and an e2e object without device copies."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-batch", "1", "--seconds", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("encoder audio-sec/sec") and d["unit"] == "audio-s/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
