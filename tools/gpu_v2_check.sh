@@ -6,6 +6,8 @@
 # a hang), then times attention v2 against the default kernel and the whole path with STAC_MHA_V2=1.
 mkdir -p gpurun_out
 export STAC_EXPERIMENTAL=1
+# tensor-memory conventions attention v2 relies on (exact integer test of the TS-form MMA under three layouts of P)
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 --expt-relaxed-constexpr -o /tmp/probe_ts_mma tools/probe_ts_mma.cu > gpurun_out/v2_probe_build.log 2>&1 && timeout 60 /tmp/probe_ts_mma > gpurun_out/v2_probe_ts_mma.log 2>&1; echo "probe_ts_mma rc $?"; cat gpurun_out/v2_probe_ts_mma.log
 timeout 300 python -m pytest tests/test_gpu_tc_attention.py -q -x -m gpu -k v2 > gpurun_out/v2_mha_tests.log 2>&1
 echo "attention v2 tests rc $?"; tail -5 gpurun_out/v2_mha_tests.log
 timeout 300 python -m pytest tests/test_gpu_turns.py tests/test_gpu_wav_ingest.py tests/test_gpu_xcustom_ops.py tests/test_gpu_ytrain_norm.py -q -m gpu > gpurun_out/v2_turn_tests.log 2>&1
