@@ -120,6 +120,87 @@ class Emulator:
                     ww[row * lk:(row + 1) * lk] = wacc.astype(np.float32)
 
 
+    # ---- a2 - a4, a8: the fp32 front-end and CTC head, from the C-ABI documentation (include/stac_b200.h) ----
+    def stac_fbank_logmel(self, pcm, batch, n_samples, row_stride, tables, logmel_db, utt_max_ordered, stream):
+        tab = _arr(tables, 2692)
+        window = tab[:400].astype(np.float64)
+        start, count = tab[1252:1332].astype(int), tab[1332:1412].astype(int)
+        weights = tab[1412:].reshape(80, 16).astype(np.float64)
+        frames = 1 + n_samples // 160
+        x = _arr(pcm, (batch - 1) * row_stride + n_samples)
+        db = _arr(logmel_db, batch * frames * 80).reshape(batch, frames, 80)
+        umax = _arr(utt_max_ordered, batch, np.uint32)
+        for b in range(batch):
+            sig = np.concatenate([np.zeros(200), x[b * row_stride: b * row_stride + n_samples].astype(np.float64),
+                                  np.zeros(200)])                                   # centre = True, zero padding
+            idx = np.arange(frames)[:, None] * 160 + np.arange(400)[None, :]
+            spec = np.fft.rfft(sig[idx] * window, axis=1)
+            power = spec.real ** 2 + spec.imag ** 2                                   # [T, 201]
+            mel = np.stack([(power[:, start[m]: start[m] + count[m]] * weights[m, :count[m]]).sum(1)
+                            for m in range(80)], 1)
+            db[b] = (10.0 * np.log10(np.maximum(mel, 1e-10))).astype(np.float32)
+            u = np.float32(db[b].max()).view(np.uint32)
+            umax[b] = (~u & 0xffffffff) if (u & 0x80000000) else (u | 0x80000000)      # order-preserving key
+
+    def stac_fbank_topdb_norm(self, logmel_db, utt_max_ordered, per_utterance, top_db, mean, std, batch, frames, n_mels,
+                              out, stream):
+        x = _arr(logmel_db, batch * frames * n_mels).reshape(batch, frames, n_mels).copy()
+        keys = _arr(utt_max_ordered, batch, np.uint32)
+        mx = np.array([np.uint32((k & 0x7fffffff) if (k & 0x80000000) else (~k & 0xffffffff)).view(np.float32)
+                       for k in keys])
+        if not per_utterance:
+            mx[:] = mx.max()
+        y = np.maximum(x, (mx - np.float32(top_db))[:, None, None])
+        if mean:
+            y = (y - _arr(mean, n_mels)) / _arr(std, n_mels)
+        _arr(out, batch * frames * n_mels).reshape(batch, frames, n_mels)[:] = y
+
+    @staticmethod
+    def _conv_block(x_btfc, weight_oifk, bias, stride=2):
+        """[B, T, F, C_in] -> [B, T', F', C_out]: reflect pad 1 in time and frequency, 3 x 3 conv, kernel [kf][kt]."""
+        import torch
+        import torch.nn.functional as F
+        x = torch.from_numpy(np.ascontiguousarray(x_btfc)).double().permute(0, 3, 2, 1)      # [B, C, F, T]
+        x = F.pad(x, (1, 1, 1, 1), mode="reflect")
+        y = F.conv2d(x, torch.from_numpy(weight_oifk).double(), torch.from_numpy(bias).double(), stride=stride)
+        return y.permute(0, 3, 2, 1).numpy()                                                  # [B, T', F', C_out]
+
+    @staticmethod
+    def _ln_lrelu(x, gamma, beta, eps, slope):
+        mu = x.mean(-1, keepdims=True)
+        var = x.var(-1, keepdims=True)
+        y = (x - mu) / np.sqrt(var + eps) * gamma + beta
+        return np.where(y >= 0, y, y * slope)
+
+    def stac_conv0_ln_lrelu(self, feats, w0, b0, ln_g, ln_b, batch, frames, out, out_mode, stream):
+        assert out_mode == _lib.DT_F32, "emulator: fp32 layout only"
+        t1 = (frames - 1) // 2 + 1
+        x = _arr(feats, batch * frames * 80).reshape(batch, frames, 80, 1)
+        w = _arr(w0, 256 * 9).reshape(256, 1, 3, 3).astype(np.float64)
+        y = self._conv_block(x, w, _arr(b0, 256).astype(np.float64)).reshape(batch, t1, 40 * 256)
+        y = self._ln_lrelu(y, _arr(ln_g, 40 * 256), _arr(ln_b, 40 * 256), 1e-5, 0.01)
+        _arr(out, batch * t1 * 40 * 256).reshape(batch, t1, 40 * 256)[:] = y
+
+    def stac_conv1_f32(self, x, w1, b1, batch, t1, out, stream):
+        t2 = (t1 - 1) // 2 + 1
+        xx = _arr(x, batch * t1 * 40 * 256).reshape(batch, t1, 40, 256)
+        w = _arr(w1, 256 * 9 * 256).reshape(256, 3, 3, 256).transpose(0, 3, 1, 2).astype(np.float64)   # [out][in][kf][kt]
+        y = self._conv_block(xx, np.ascontiguousarray(w), _arr(b1, 256).astype(np.float64))
+        _arr(out, batch * t2 * 20 * 256).reshape(batch, t2, 20, 256)[:] = y
+
+    def stac_group_ln_lrelu(self, x, rows, dim, gamma, beta, eps, slope, out, out_dtype, stream):
+        assert out_dtype == _lib.DT_F32, "emulator: fp32 output only"
+        y = self._ln_lrelu(_arr(x, rows * dim).reshape(rows, dim).astype(np.float64), _arr(gamma, dim), _arr(beta, dim),
+                           eps, slope)
+        _arr(out, rows * dim).reshape(rows, dim)[:] = y
+
+    def stac_log_softmax(self, logits, rows, vocab, out, argmax, stream):
+        x = _arr(logits, rows * vocab).reshape(rows, vocab).astype(np.float64)
+        m = x.max(1, keepdims=True)
+        _arr(out, rows * vocab).reshape(rows, vocab)[:] = x - (m + np.log(np.exp(x - m).sum(1, keepdims=True)))
+        if argmax:
+            _arr(argmax, rows, np.int32)[:] = x.argmax(1)
+
     def stac_utt_mean_std(self, x, wav_len, batch, frames, dim, eps, mean, std, stream):
         xx = _arr(x, batch * frames * dim).reshape(batch, frames, dim).astype(np.float64)
         wl = _arr(wav_len, batch)

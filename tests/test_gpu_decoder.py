@@ -2,7 +2,7 @@
 forward() produced (tests/golden/decoder_reference.npz) and against the oracle at S-model width.  fp32 path: 1e-4.
 
 These kernels were written after the round-1 GPU budget was spent; they compile for sm_100a and their host side is
-covered on the CPU (tests/test_host_decoder.py), but they have not run on a B200 yet, so the file is not part of the
+covered on the CPU (tests/test_host_emulated.py), but they have not run on a B200 yet, so the file is not part of the
 default GPU suite: STAC_EXPERIMENTAL=1 enables it (tools/gpu_v2_check.sh)."""
 import os
 
@@ -16,7 +16,7 @@ pytestmark = [pytest.mark.gpu,
 import stac_speech_translation_b200 as sb  # noqa: E402
 from oracle import speechbrain_path as sp  # noqa: E402
 from stac_speech_translation_b200 import decoder as dec, ops  # noqa: E402
-from test_host_decoder import build, fixture  # noqa: E402
+from test_host_emulated import build, fixture  # noqa: E402
 from util import FP32_TOL, rel_l2  # noqa: E402
 
 

@@ -245,3 +245,28 @@ def test_train_mode_input_normalization_follows_speechbrain_updates(monkeypatch)
     x = torch.randn(2, 30, 80, generator=g)
     assert rel_l2(ours(x, torch.ones(2)), ref(x, torch.ones(2))) < 1e-5
     assert ours.count == ref.count == 5
+
+
+def test_fp32_path_host_orchestration_against_the_oracle(monkeypatch):
+    """The whole six-call sequence (pipeline.compute_forward: Fbank, InputNormalization, ConvolutionFrontEnd, encode,
+    ctc_lin, log_softmax) in fp32 mode on the CPU, with the emulated C ABI standing in for the kernels, against the
+    oracle at every stage boundary: weight packing, table layouts, shapes, strides, mask rules and call order of the host
+    side are exercised without a GPU (the kernels themselves: tests/test_gpu_fp32_path.py)."""
+    import oracle
+    from stac_speech_translation_b200 import synth
+    from util import TINY, oracle_modules, product_from_oracle
+    abi_emulator.install(monkeypatch)
+    omods = oracle_modules(TINY, vocab=64)
+    mods = product_from_oracle(omods, "fp32", device="cpu")
+    wavs, wl = synth.synth_batch([0.9, 0.62], seed=31)
+    for train_mask in (False, True):
+        with torch.no_grad():
+            want = oracle.reference_compute_forward(omods, wavs, wl, train_mask=train_mask)
+        got = sb.compute_forward(mods, wavs, wl, train_mask=train_mask)
+        for key in ("fbank", "feats", "cnn", "enc_out", "logits", "p_ctc"):
+            assert got[key].shape == want[key].shape, key
+            assert rel_l2(got[key], want[key]) < 1e-4, (key, train_mask, rel_l2(got[key], want[key]))
+        # the fused call (what bench.py and the multi-GPU driver use): same results, plus the greedy ids
+        res = sb.EncoderPipeline(mods, train_mask=train_mask)(wavs, wl)
+        assert rel_l2(res["enc_out"], want["enc_out"]) < 1e-4 and rel_l2(res["p_ctc"], want["p_ctc"]) < 1e-4
+        assert torch.equal(res["greedy"].long(), want["p_ctc"].argmax(-1))
