@@ -9,6 +9,7 @@ import ctypes
 from ctypes import c_void_p
 
 import numpy as np
+import torch
 from scipy.special import erf
 
 from stac_speech_translation_b200 import _lib
@@ -19,6 +20,18 @@ def _arr(addr, n, dtype=np.float32):
         return None
     nbytes = int(n) * np.dtype(dtype).itemsize
     return np.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=dtype)
+
+
+def _tarr(addr, n, dtype):
+    """torch view of raw memory (for bf16 / fp16, which numpy does not have)."""
+    if not addr:
+        return None
+    nbytes = int(n) * torch.empty(0, dtype=dtype).element_size()
+    return torch.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=dtype)
+
+
+def _gelu(y):
+    return 0.5 * y * (1.0 + erf(y / np.sqrt(2.0)))
 
 
 class Emulator:
@@ -50,12 +63,14 @@ class Emulator:
         o[:] = e[tok] * np.float32(scale) + p[np.arange(rows) % seq_len]
 
     def stac_layernorm(self, x, rows, dim, gamma, beta, eps, out_f32, out_bf16, stream):
-        assert out_bf16 == 0, "emulator: fp32 output only"
         xx = _arr(x, rows * dim).reshape(rows, dim).astype(np.float64)
         mu = xx.mean(1, keepdims=True)
         var = xx.var(1, keepdims=True)
         y = (xx - mu) / np.sqrt(var + eps) * _arr(gamma, dim) + _arr(beta, dim)
-        _arr(out_f32, rows * dim).reshape(rows, dim)[:] = y.astype(np.float32)
+        if out_f32:
+            _arr(out_f32, rows * dim).reshape(rows, dim)[:] = y.astype(np.float32)
+        if out_bf16:
+            _tarr(out_bf16, rows * dim, torch.bfloat16)[:] = torch.from_numpy(y).to(torch.bfloat16).flatten()
 
     def stac_gemm_f32(self, a, w, bias, resid, resid_period, act, c, m, n, k, stream):
         y = _arr(a, m * k).reshape(m, k).astype(np.float64) @ _arr(w, n * k).reshape(n, k).astype(np.float64).T
@@ -120,6 +135,113 @@ class Emulator:
                     ww[row * lk:(row + 1) * lk] = wacc.astype(np.float32)
 
 
+    # ---- bf16 mode (the benchmark path): same arithmetic with bf16 roundings at the documented hand-offs ----
+    def stac_cast_bf16(self, x, n, out, stream):
+        _tarr(out, n, torch.bfloat16)[:] = torch.from_numpy(_arr(x, n).copy()).to(torch.bfloat16)
+
+    def stac_gemm_bf16(self, a, w, bias, resid, resid_period, act, c, c_dtype, m, n, k, vt_out, vt_cols, seq_len, t_pad,
+                       stream):
+        assert vt_out == 0, "emulator: no transposed V output"
+        y = _tarr(a, m * k, torch.bfloat16).double().view(m, k).numpy() @ \
+            _tarr(w, n * k, torch.bfloat16).double().view(n, k).numpy().T
+        if bias:
+            y = y + _arr(bias, n)
+        if act == _lib.ACT_GELU_ERF:
+            y = _gelu(y)
+        if resid:
+            if resid_period:
+                y = y + _arr(resid, resid_period * n).reshape(resid_period, n)[np.arange(m) % resid_period]
+            else:
+                y = y + _arr(resid, m * n).reshape(m, n)
+        if c_dtype == _lib.DT_BF16:
+            _tarr(c, m * n, torch.bfloat16)[:] = torch.from_numpy(y).to(torch.bfloat16).flatten()
+        else:
+            _arr(c, m * n).reshape(m, n)[:] = y.astype(np.float32)
+
+    def stac_ffn_fused_bf16(self, h, w1, b1, w2, b2, x, m, d_model, d_ffn, stream):
+        hh = _tarr(h, m * d_model, torch.bfloat16).double().view(m, d_model).numpy()
+        hid = _gelu(hh @ _tarr(w1, d_ffn * d_model, torch.bfloat16).double().view(d_ffn, d_model).numpy().T
+                    + _arr(b1, d_ffn))
+        hid = torch.from_numpy(hid).to(torch.bfloat16).double().numpy()          # P is bf16 in shared memory
+        y = hid @ _tarr(w2, d_model * d_ffn, torch.bfloat16).double().view(d_model, d_ffn).numpy().T + _arr(b2, d_model)
+        xx = _arr(x, m * d_model).reshape(m, d_model)
+        xx[:] = (xx + y).astype(np.float32)
+
+    def _mha_bf16(self, qkv, kv_len, batch, seq_len, d_model, n_head, ctx):
+        x = _tarr(qkv, batch * seq_len * 3 * d_model, torch.bfloat16).double().view(batch, seq_len, 3, n_head, 64).numpy()
+        n = _arr(kv_len, batch, np.int32)
+        out = np.zeros((batch, seq_len, n_head, 64))
+        for b in range(batch):
+            nk = min(max(int(n[b]), 1), seq_len)
+            for h in range(n_head):
+                s = x[b, :, 0, h] @ x[b, :nk, 1, h].T
+                p = np.exp(s - s.max(1, keepdims=True))
+                out[b, :, h] = (p / p.sum(1, keepdims=True)) @ x[b, :nk, 2, h]
+        _tarr(ctx, batch * seq_len * d_model, torch.bfloat16)[:] = torch.from_numpy(out).to(torch.bfloat16).flatten()
+
+    def stac_mha_bf16(self, qkv, v_t, kv_len, batch, seq_len, t_pad, d_model, n_head, ctx, stream):
+        assert v_t == 0 and t_pad >= seq_len
+        self._mha_bf16(qkv, kv_len, batch, seq_len, d_model, n_head, ctx)
+
+    def stac_mha_bf16_v2(self, qkv, kv_len, batch, seq_len, d_model, n_head, ctx, stream):
+        self._mha_bf16(qkv, kv_len, batch, seq_len, d_model, n_head, ctx)
+
+    def stac_ctc_head_bf16(self, enc, w, bias, m, vocab, d_model, workspace, log_probs, out_dtype, argmax, stream):
+        assert workspace
+        x = _tarr(enc, m * d_model, torch.bfloat16).double().view(m, d_model).numpy() @ \
+            _tarr(w, vocab * d_model, torch.bfloat16).double().view(vocab, d_model).numpy().T
+        if bias:
+            x = x + _arr(bias, vocab)
+        mx = x.max(1, keepdims=True)
+        y = x - (mx + np.log(np.exp(x - mx).sum(1, keepdims=True)))
+        if out_dtype == _lib.DT_BF16:
+            _tarr(log_probs, m * vocab, torch.bfloat16)[:] = torch.from_numpy(y).to(torch.bfloat16).flatten()
+        else:
+            _arr(log_probs, m * vocab).reshape(m, vocab)[:] = y.astype(np.float32)
+        if argmax:
+            _arr(argmax, m, np.int32)[:] = x.argmax(1)
+
+    def stac_fbank_logmel_tc(self, pcm, batch, n_samples, row_stride, tables, twiddles, logmel_db, utt_max_ordered,
+                             stream):
+        from stac_speech_translation_b200 import ops
+        tab = _arr(tables, 400 + 208 * 2)
+        window, wbin = tab[:400].astype(np.float64), tab[400:].reshape(208, 2).astype(np.float64)
+        assert _tarr(twiddles, 2 * 208 * 256, torch.float16).abs().max() <= 1.0
+        fb = ops.mel_filter_matrix().numpy()                      # only its sparsity structure is used (compiled into the
+        frames = 1 + n_samples // 160                             # kernel); the weights come from the table
+        x = _arr(pcm, (batch - 1) * row_stride + n_samples)
+        db = _arr(logmel_db, batch * frames * 80).reshape(batch, frames, 80)
+        umax = _arr(utt_max_ordered, batch, np.uint32)
+        for b in range(batch):
+            sig = np.concatenate([np.zeros(200), x[b * row_stride: b * row_stride + n_samples].astype(np.float64),
+                                  np.zeros(200)])
+            idx = np.arange(frames)[:, None] * 160 + np.arange(400)[None, :]
+            spec = np.fft.rfft(sig[idx] * window, axis=1)
+            power = spec.real ** 2 + spec.imag ** 2
+            mel = np.zeros((frames, 80))
+            for k in range(201):
+                for j, m in enumerate(np.nonzero(fb[:, k] > 0)[0]):
+                    mel[:, m] += power[:, k] * wbin[k, j]
+            db[b] = (10.0 * np.log10(np.maximum(mel, 1e-10))).astype(np.float32)
+            u = np.float32(db[b].max()).view(np.uint32)
+            umax[b] = (~u & 0xffffffff) if (u & 0x80000000) else (u | 0x80000000)
+
+    def stac_conv1_bf16(self, xpad, w1, b1, ln_g, ln_b, batch, t1, out, stream):
+        t2, tp2 = (t1 - 1) // 2 + 1, (t1 + 3) // 2
+        planes = _tarr(xpad, batch * 4 * tp2 * 21 * 256, torch.bfloat16).double().view(batch, 4, tp2, 21, 256).numpy()
+        pad = np.zeros((batch, 2 * tp2, 42, 256))                 # padded coordinates tp = t1 + 1, fp = f1 + 1
+        for par in range(4):
+            pad[:, (par >> 1)::2, (par & 1)::2] = planes[:, par]
+        w = _tarr(w1, 9 * 256 * 256, torch.bfloat16).double().view(3, 3, 256, 256).numpy()      # [kf][kt][out][in]
+        y = np.zeros((batch, t2, 20, 256))
+        for kf in range(3):
+            for kt in range(3):
+                patch = pad[:, kt: kt + 2 * t2: 2, kf: kf + 40: 2]                                   # [B, T2, 20, in]
+                y += patch @ w[kf, kt].T
+        y = (y + _arr(b1, 256)).reshape(batch, t2, 20 * 256)
+        y = self._ln_lrelu(y, _arr(ln_g, 20 * 256), _arr(ln_b, 20 * 256), 1e-5, 0.01)
+        _tarr(out, batch * t2 * 5120, torch.bfloat16)[:] = torch.from_numpy(y).to(torch.bfloat16).flatten()
+
     # ---- a2 - a4, a8: the fp32 front-end and CTC head, from the C-ABI documentation (include/stac_b200.h) ----
     def stac_fbank_logmel(self, pcm, batch, n_samples, row_stride, tables, logmel_db, utt_max_ordered, stream):
         tab = _arr(tables, 2692)
@@ -173,13 +295,26 @@ class Emulator:
         return np.where(y >= 0, y, y * slope)
 
     def stac_conv0_ln_lrelu(self, feats, w0, b0, ln_g, ln_b, batch, frames, out, out_mode, stream):
-        assert out_mode == _lib.DT_F32, "emulator: fp32 layout only"
         t1 = (frames - 1) // 2 + 1
         x = _arr(feats, batch * frames * 80).reshape(batch, frames, 80, 1)
         w = _arr(w0, 256 * 9).reshape(256, 1, 3, 3).astype(np.float64)
         y = self._conv_block(x, w, _arr(b0, 256).astype(np.float64)).reshape(batch, t1, 40 * 256)
         y = self._ln_lrelu(y, _arr(ln_g, 40 * 256), _arr(ln_b, 40 * 256), 1e-5, 0.01)
-        _arr(out, batch * t1 * 40 * 256).reshape(batch, t1, 40 * 256)[:] = y
+        if out_mode == _lib.DT_F32:
+            _arr(out, batch * t1 * 40 * 256).reshape(batch, t1, 40 * 256)[:] = y
+            return
+        # bf16: reflect-padded, parity-split planes [B][4 = (tp & 1) * 2 + (fp & 1)][Tp2][21][256], tp = t1 + 1, fp = f1 + 1
+        tp2 = (t1 + 3) // 2
+        y = y.reshape(batch, t1, 40, 256)
+        tidx = np.abs(np.arange(-1, t1 + 1))
+        tidx = np.where(tidx >= t1, 2 * (t1 - 1) - tidx, tidx)
+        fidx = np.abs(np.arange(-1, 41))
+        fidx = np.where(fidx >= 40, 2 * 39 - fidx, fidx)
+        pad = np.zeros((batch, 2 * tp2, 42, 256))
+        pad[:, : t1 + 2] = y[:, tidx][:, :, fidx]
+        planes = _tarr(out, batch * 4 * tp2 * 21 * 256, torch.bfloat16).view(batch, 4, tp2, 21, 256)
+        for par in range(4):
+            planes[:, par] = torch.from_numpy(np.ascontiguousarray(pad[:, (par >> 1)::2, (par & 1)::2])).to(torch.bfloat16)
 
     def stac_conv1_f32(self, x, w1, b1, batch, t1, out, stream):
         t2 = (t1 - 1) // 2 + 1
