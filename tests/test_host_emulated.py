@@ -272,18 +272,20 @@ def test_fp32_path_host_orchestration_against_the_oracle(monkeypatch):
         assert torch.equal(res["greedy"].long(), want["p_ctc"].argmax(-1))
 
 
-@pytest.mark.parametrize("mha_v2", [False, True])
-def test_bf16_path_host_orchestration_against_the_oracle(monkeypatch, mha_v2):
+@pytest.mark.parametrize("mha_v2,tiny", [(False, False), (True, False), (False, True)])
+def test_bf16_path_host_orchestration_against_the_oracle(monkeypatch, mha_v2, tiny):
     """The benchmark path's host side (fused EncoderPipeline in bf16 mode: tensor-core Fbank tables, padded parity-split
     conv0 layout, packed conv1 / projection weights with the pre-scaled q rows, fused FFN and CTC head calls, greedy
     ids) on the CPU through the emulated C ABI, against the fp32 oracle at the bf16 tolerance; S width so that the fused
-    feed-forward call is taken.  mha_v2: the STAC_MHA_V2=1 branch of ops.encoder_stack."""
+    feed-forward call is taken (tiny: d_model 128, the two-GEMM feed-forward that the M / L sizes use).
+    mha_v2: the STAC_MHA_V2=1 branch of ops.encoder_stack."""
     import oracle
     from stac_speech_translation_b200 import ops, synth
     from util import BF16_TOL, oracle_modules, product_from_oracle
     emu = abi_emulator.install(monkeypatch)
     monkeypatch.setattr(ops, "MHA_V2", mha_v2)
-    omods = oracle_modules("S", num_encoder_layers=2, vocab=64)
+    from util import TINY
+    omods = oracle_modules(TINY, vocab=64) if tiny else oracle_modules("S", num_encoder_layers=2, vocab=64)
     mods = product_from_oracle(omods, "bf16", device="cpu")
     wavs, wl = synth.synth_batch([0.7, 0.45], seed=32)
     with torch.no_grad():
@@ -293,7 +295,8 @@ def test_bf16_path_host_orchestration_against_the_oracle(monkeypatch, mha_v2):
     assert rel_l2(res["enc_out"], want["enc_out"]) < BF16_TOL and rel_l2(res["p_ctc"], want["p_ctc"]) < BF16_TOL
     assert (res["greedy"].long() == res["p_ctc"].argmax(-1)).all()
     assert ("stac_mha_bf16_v2" if mha_v2 else "stac_mha_bf16") in emu.calls
-    assert {"stac_fbank_logmel_tc", "stac_conv1_bf16", "stac_ffn_fused_bf16", "stac_ctc_head_bf16"} <= set(emu.calls)
+    assert {"stac_fbank_logmel_tc", "stac_conv1_bf16", "stac_ctc_head_bf16"} <= set(emu.calls)
+    assert ("stac_ffn_fused_bf16" in emu.calls) == (not tiny)
     # the six-call sequence in bf16 mode (fp32 tensors at every stage boundary, as the reference's callers expect)
     got = sb.compute_forward(mods, wavs, wl)
     assert all(got[k].dtype == torch.float32 for k in ("fbank", "feats", "cnn", "enc_out", "logits", "p_ctc"))
