@@ -18,10 +18,16 @@ the graph at a ctypes call.  Each op is a thin wrapper: argument checks and allo
 | ``log_softmax_greedy(logits)``             | the same + ``.argmax(-1)`` inference.py:58                      | stac_log_softmax |
 | ``argmax_rows(x)``                         | ``model_ctc_outputs.argmax(-1)`` inference.py:58                | stac_argmax_rows |
 | ``pcm_to_float(pcm)``                      | fp32 decode of 16-bit PCM in front of ``batch.to(device)`` :91  | stac_pcm_i16_to_f32 |
+| ``conv_frontend(feats, weights, precision)`` | ``CNN(feats)`` inference.py:99                                 | stac_conv0_ln_lrelu, stac_conv1_* |
+| ``encoder(src, kv_len, weights, ...)``     | ``Transformer.encode`` after the mask rule, :100               | stac_gemm_*, stac_layernorm, stac_mha_*, stac_ffn_fused_bf16 |
+| ``ctc_head(enc_bf16, weight, bias)``       | ``log_softmax(ctc_lin(enc_out))`` + arg-max, :105-106 / :58    | stac_ctc_head_bf16 |
+
+The three structured ops take the packed weights as flat tensor lists (``frontend_weight_list`` /
+``encoder_weight_list`` turn the packed dataclasses of ``ops.py`` into them).
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -105,3 +111,57 @@ def pcm_to_float(pcm: torch.Tensor) -> torch.Tensor:
 @pcm_to_float.register_fake
 def _(pcm):
     return torch.empty_like(pcm, dtype=torch.float32, memory_format=torch.contiguous_format)
+
+
+# ---- structured stages: packed weights travel as flat tensor lists ----
+def frontend_weight_list(w: ops.FrontendWeights) -> List[torch.Tensor]:
+    return [w.w0, w.b0, w.g0, w.be0, w.w1, w.b1, w.g1, w.be1]
+
+
+def encoder_weight_list(w: ops.EncoderWeights) -> List[torch.Tensor]:
+    """[w_src, b_src, pe, lnf_g, lnf_b] + 12 tensors per layer in LayerWeights field order."""
+    out = [w.w_src, w.b_src, w.pe, w.lnf_g, w.lnf_b]
+    for L in w.layers:
+        out += [L.ln1_g, L.ln1_b, L.w_qkv, L.b_qkv, L.w_o, L.b_o, L.ln2_g, L.ln2_b, L.w_1, L.b_1, L.w_2, L.b_2]
+    return out
+
+
+@torch.library.custom_op("stac_b200::conv_frontend", mutates_args=())
+def conv_frontend(feats: torch.Tensor, weights: Sequence[torch.Tensor], precision: str, out_bf16: bool) -> torch.Tensor:
+    w = ops.FrontendWeights(precision, *weights)
+    return ops.conv_frontend(feats, w, torch.bfloat16 if out_bf16 else torch.float32)
+
+
+@conv_frontend.register_fake
+def _(feats, weights, precision, out_bf16):
+    t2 = ops.frames_of((feats.shape[1] - 1) * ops.HOP)[2]
+    return feats.new_empty(feats.shape[0], t2, ops.F2 * ops.CNN_CH, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+
+
+@torch.library.custom_op("stac_b200::encoder", mutates_args=())
+def encoder(src: torch.Tensor, kv_len: torch.Tensor, weights: Sequence[torch.Tensor], d_model: int, nhead: int,
+            precision: str) -> torch.Tensor:
+    ws = list(weights)
+    if (len(ws) - 5) % 12 != 0:
+        raise ops._lib.StacB200Error("encoder weight list: 5 tensors + 12 per layer expected")
+    w = ops.EncoderWeights(precision, d_model, nhead, ws[0], ws[1], ws[2],
+                           [ops.LayerWeights(*ws[i:i + 12]) for i in range(5, len(ws), 12)], ws[3], ws[4])
+    return ops.encoder_stack(src, w, kv_len)
+
+
+@encoder.register_fake
+def _(src, kv_len, weights, d_model, nhead, precision):
+    return src.new_empty(src.shape[0], src.shape[1], d_model, dtype=torch.float32)
+
+
+@torch.library.custom_op("stac_b200::ctc_head", mutates_args=())
+def ctc_head(enc_bf16: torch.Tensor, weight_bf16: torch.Tensor, bias: Optional[torch.Tensor]
+             ) -> Tuple[torch.Tensor, torch.Tensor]:
+    p, ids = ops.ctc_head_bf16(enc_bf16, weight_bf16, bias)
+    return p, ids
+
+
+@ctc_head.register_fake
+def _(enc_bf16, weight_bf16, bias):
+    return (enc_bf16.new_empty(*enc_bf16.shape[:-1], weight_bf16.shape[0], dtype=torch.float32),
+            enc_bf16.new_empty(enc_bf16.shape[:-1], dtype=torch.int32))

@@ -330,6 +330,12 @@ def test_custom_op_layer_registers_and_propagates_shapes():
         assert out.shape == y.shape and ids.shape == (4, 26) and ids.dtype == torch.int32
         assert ns.argmax_rows(out).dtype == torch.int32
         assert ns.pcm_to_float(torch.empty(3, 100, dtype=torch.int16)).dtype == torch.float32
+        src = ns.conv_frontend(f, [torch.empty(1)] * 8, "bf16", True)
+        assert src.shape == (4, 26, 5120) and src.dtype == torch.bfloat16
+        enc = ns.encoder(src, torch.empty(4, dtype=torch.int32), [torch.empty(1)] * 29, 256, 4, "bf16")
+        assert enc.shape == (4, 26, 256) and enc.dtype == torch.float32
+        p, ids = ns.ctc_head(enc.to(torch.bfloat16), torch.empty(5000, 256, dtype=torch.bfloat16), None)
+        assert p.shape == (4, 26, 5000) and ids.shape == (4, 26)
     with pytest.raises(sb.StacB200Error, match="no CPU fallback"):
         ns.input_norm(torch.zeros(1, 4, 80), torch.zeros(80), torch.ones(80))
 

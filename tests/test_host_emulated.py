@@ -302,3 +302,28 @@ def test_bf16_path_host_orchestration_against_the_oracle(monkeypatch, mha_v2, ti
     assert all(got[k].dtype == torch.float32 for k in ("fbank", "feats", "cnn", "enc_out", "logits", "p_ctc"))
     assert rel_l2(got["cnn"], want["cnn"]) < BF16_TOL and rel_l2(got["enc_out"], want["enc_out"]) < BF16_TOL
     assert rel_l2(got["p_ctc"], want["p_ctc"]) < BF16_TOL
+
+
+def test_structured_custom_ops_equal_the_pipeline(monkeypatch):
+    """torch.ops.stac_b200.{fbank-free front-end, encoder, ctc_head} with flat weight lists give what the fused
+    EncoderPipeline gives (bf16 mode, emulated ABI), i.e. the custom-op layer is a faithful view of the same calls."""
+    import stac_speech_translation_b200.custom_ops as co
+    from stac_speech_translation_b200 import ops, synth
+    from util import oracle_modules, product_from_oracle
+    abi_emulator.install(monkeypatch)
+    omods = oracle_modules("S", num_encoder_layers=1, vocab=64)
+    mods = product_from_oracle(omods, "bf16", device="cpu")
+    wavs, wl = synth.synth_batch([0.5, 0.33], seed=33)
+    pipe = sb.EncoderPipeline(mods)
+    res = pipe(wavs, wl)
+    ns = torch.ops.stac_b200
+    fb, norm = mods["compute_features"], mods["normalize"]
+    mean, std = norm.device_stats(wavs.device, 80)
+    feats = ops.fbank_tc(wavs, fb.tc_tables(wavs.device), fb.top_db, fb.top_db_per_utterance, mean, std)
+    src = ns.conv_frontend(feats, co.frontend_weight_list(mods["CNN"].packed()), "bf16", True)
+    tr = mods["Transformer"]
+    enc = ns.encoder(src, res["kv_len"], co.encoder_weight_list(tr.packed()), tr.d_model, tr.nhead, "bf16")
+    assert torch.equal(enc, res["enc_out"])
+    ctc = mods["ctc_lin"]
+    p, ids = ns.ctc_head(enc.to(torch.bfloat16), ctc.packed_weight(), ctc.w.bias.detach().float().contiguous())
+    assert rel_l2(p, res["p_ctc"]) < 2e-2 and p.shape == res["p_ctc"].shape and ids.shape == res["greedy"].shape
