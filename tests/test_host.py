@@ -357,3 +357,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_custom_ops_survive_torch_export():
+    """What the custom-op layer is for: a module written over torch.ops.stac_b200.* exports to one graph whose nodes are
+    those ops (fake tensors, no kernel runs)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import stac_speech_translation_b200.custom_ops  # noqa: F401
+
+    class M(torch.nn.Module):
+        def forward(self, feats, mean, std, w, b):
+            x = torch.ops.stac_b200.input_norm(feats, mean, std)
+            y = torch.ops.stac_b200.linear(x, w, b, "fp32")
+            return torch.ops.stac_b200.log_softmax_greedy(y)
+
+    with FakeTensorMode(allow_non_fake_inputs=True):
+        args = (torch.empty(2, 50, 80), torch.empty(80), torch.empty(80), torch.empty(64, 80), torch.empty(64))
+        ep = torch.export.export(M(), args)
+    targets = [str(n.target) for n in ep.graph.nodes if n.op == "call_function"]
+    assert [t for t in targets if t.startswith("stac_b200.")] == [
+        "stac_b200.input_norm.default", "stac_b200.linear.default", "stac_b200.log_softmax_greedy.default"]
