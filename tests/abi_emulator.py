@@ -397,3 +397,26 @@ def install(monkeypatch):
         monkeypatch.setattr(mod, "lib", lambda: EmuLib(emu))
     monkeypatch.setattr(ops, "_call", emu.call)
     return emu
+
+
+def install_simt(monkeypatch, simt_lib):
+    """Like install(), but every entry point the CPU build of the SIMT kernels exports (tests/simt_cpu) runs THAT - the
+    kernel source itself under the CPU emulation of the CUDA execution model - instead of the numpy stand-in."""
+    emu = install(monkeypatch)
+    from stac_speech_translation_b200 import ops
+    routed = []
+
+    def call(name, *args):
+        fn = getattr(simt_lib, name, None)
+        if fn is None:
+            return emu.call(name, *args)
+        res, sig = _lib._SIGNATURES[name]
+        fn.restype, fn.argtypes = res, sig
+        emu.calls.append(name)
+        routed.append(name)
+        rc = fn(*args)
+        assert rc == 0, (name, rc)
+
+    monkeypatch.setattr(ops, "_call", call)
+    emu.routed = routed
+    return emu

@@ -1,0 +1,226 @@
+"""The library's plain SIMT kernels, compiled from their real source for a CPU emulation of the CUDA execution model
+(tests/simt_cpu: blocks one after another, threads of a block as OS threads, barriers for __syncthreads and the
+warp-synchronous primitives), driven through the same extern "C" entry points on host memory.
+
+This is how the kernels that were written after the round's GPU budget was spent (turn detection, decoder building
+blocks, PCM ingest, train-mode normalisation statistics) have been EXECUTED so far; their first run on a B200 is
+tests/test_gpu_{turns,decoder,wav_ingest,ytrain_norm}.py.  Test infrastructure: nothing of it ships."""
+import ctypes
+import json
+import os
+import sys
+from ctypes import c_float, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "simt_cpu"))
+import build as simt_build  # noqa: E402
+
+from stac_speech_translation_b200 import _lib  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def simt():
+    lib = ctypes.CDLL(str(simt_build.build()))
+    for name in ("stac_argmax_rows", "stac_ctc_spikes", "stac_embed_scale_pe", "stac_attention_f32",
+                 "stac_pcm_i16_to_f32", "stac_utt_mean_std", "stac_layernorm", "stac_mha_f32", "stac_log_softmax",
+                 "stac_kv_lengths", "stac_cast_bf16", "stac_gemm_f32"):
+        res, args = _lib._SIGNATURES[name]
+        getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
+    return lib
+
+
+def P(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def test_turn_detection_kernels(simt):
+    for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "turns_reference.json"))):
+        ids = torch.tensor(c["ids"], dtype=torch.int32)
+        b, t2 = ids.shape
+        counts = torch.empty(b, 2, dtype=torch.int32)
+        spikes = torch.full((2, b * t2), -1, dtype=torch.int32)
+        n_out = torch.empty(2, dtype=torch.int32)
+        assert simt.stac_ctc_spikes(P(ids), b, t2, 7, 8, P(counts), P(spikes[0]), P(spikes[1]), P(n_out), None) == 0
+        flat = ids.reshape(-1).numpy()
+        for k, tok in enumerate((7, 8)):
+            want = np.nonzero(flat == tok)[0]
+            assert int(n_out[k]) == len(want) and np.array_equal(spikes[k, :len(want)].numpy(), want)
+            assert (spikes[k, len(want):] == -1).all()                      # nothing written past the count
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(70, 300, generator=g)
+    x[7, 100] = x[7, 250] = 50.0                                            # tie: the first index wins
+    x[9, 299] = 60.0
+    out = torch.empty(70, dtype=torch.int32)
+    assert simt.stac_argmax_rows(P(x), 70, 300, P(out), None) == 0
+    assert torch.equal(out.long(), x.argmax(-1)) and int(out[7]) == 100
+    small = torch.randn(5, 3, generator=g)                                  # fewer columns than threads
+    out = torch.empty(5, dtype=torch.int32)
+    assert simt.stac_argmax_rows(P(small), 5, 3, P(out), None) == 0 and torch.equal(out.long(), small.argmax(-1))
+
+
+def test_spike_compaction_across_many_rows(simt):
+    g = torch.Generator().manual_seed(2)
+    b, t2 = 300, 70                                                         # row offsets need more than one pass of 256
+    ids = torch.randint(9, 50, (b, t2), generator=g, dtype=torch.int32)
+    r = torch.rand(b, t2, generator=g)
+    ids[r < 0.1] = 7
+    ids[(r >= 0.1) & (r < 0.2)] = 8
+    counts, n_out = torch.empty(b, 2, dtype=torch.int32), torch.empty(2, dtype=torch.int32)
+    spikes = torch.empty(2, b * t2, dtype=torch.int32)
+    assert simt.stac_ctc_spikes(P(ids), b, t2, 7, 8, P(counts), P(spikes[0]), P(spikes[1]), P(n_out), None) == 0
+    flat = ids.reshape(-1).numpy()
+    assert np.array_equal(spikes[0, :int(n_out[0])].numpy(), np.nonzero(flat == 7)[0])
+    assert np.array_equal(spikes[1, :int(n_out[1])].numpy(), np.nonzero(flat == 8)[0])
+
+
+@pytest.mark.parametrize("rows,lq,lk,h,div,causal", [(1, 1, 1, 1, 1, 0), (3, 4, 4, 2, 1, 1), (4, 2, 37, 2, 2, 0),
+                                                     (2, 1, 300, 1, 1, 0)])
+def test_attention_f32_kernel(simt, rows, lq, lk, h, div, causal):
+    g = torch.Generator().manual_seed(rows * 100 + lk)
+    d = 64 * h
+    n_mem = rows // div
+    q = torch.randn(rows * lq, d, generator=g)
+    kv = torch.randn(n_mem * lk, 2 * d, generator=g)
+    kv_len = torch.randint(1, lk + 1, (rows,), generator=g, dtype=torch.int32)
+    tok = torch.randint(0, 3, (rows, lk), generator=g)
+    tok[:, 0] = 1
+    use_tok = causal == 1
+    ctx = torch.full((rows * lq, d), float("nan"))
+    w = torch.full((rows, lq, lk), float("nan"))
+    rc = simt.stac_attention_f32(P(q), d, P(kv), c_void_p(kv.data_ptr() + 4 * d), lk * 2 * d, 2 * d, rows, lq, lk, h, div,
+                                 causal, P(kv_len), P(tok) if use_tok else None, 0, P(ctx), d, P(w), None)
+    assert rc == 0
+    qq = q.view(rows, lq, h, 64).permute(0, 2, 1, 3).double()
+    k = kv[:, :d].reshape(n_mem, lk, h, 64).permute(0, 2, 1, 3).double().repeat_interleave(div, 0)
+    v = kv[:, d:].reshape(n_mem, lk, h, 64).permute(0, 2, 1, 3).double().repeat_interleave(div, 0)
+    mask = torch.arange(lk)[None, None, :] >= kv_len[:, None, None]
+    if causal:
+        mask = mask | (torch.arange(lk)[None, None, :] > torch.arange(lq)[None, :, None])
+    if use_tok:
+        mask = mask | (tok == 0)[:, None, :]
+    p = torch.softmax((qq @ k.transpose(-1, -2)).masked_fill(mask[:, None], float("-inf")), -1)
+    want = (p @ v).permute(0, 2, 1, 3).reshape(rows * lq, d)
+    assert (ctx.double() - want).norm() / want.norm() < 1e-5
+    assert (w.double() - p.mean(1)).norm() / p.mean(1).norm() < 1e-5
+
+
+def test_attention_time_major_cache_and_embedding(simt):
+    """The addressing DecoderCache uses: keys / values in a time-major cache [lk][rows][2 d]; and the embedding kernel
+    with a position offset into the table."""
+    g = torch.Generator().manual_seed(9)
+    rows, lk, h = 3, 5, 2
+    d = 64 * h
+    q = torch.randn(rows, d, generator=g)
+    cache = torch.randn(8, rows, 2 * d, generator=g)                        # max_len 8, only lk rows are valid
+    ctx = torch.empty(rows, d)
+    rc = simt.stac_attention_f32(P(q), d, P(cache), c_void_p(cache.data_ptr() + 4 * d), 2 * d, rows * 2 * d, rows, 1, lk,
+                                 h, 1, 0, None, None, 0, P(ctx), d, None, None)
+    assert rc == 0
+    kk = cache[:lk, :, :d].permute(1, 0, 2).reshape(rows, lk, h, 64).permute(0, 2, 1, 3).double()
+    vv = cache[:lk, :, d:].permute(1, 0, 2).reshape(rows, lk, h, 64).permute(0, 2, 1, 3).double()
+    p = torch.softmax(q.view(rows, 1, h, 64).permute(0, 2, 1, 3).double() @ kk.transpose(-1, -2), -1)
+    want = (p @ vv).permute(0, 2, 1, 3).reshape(rows, d)
+    assert (ctx.double() - want).norm() / want.norm() < 1e-5
+    vocab, L, r = 97, 5, 4
+    emb, pe = torch.randn(vocab, d, generator=g), torch.randn(40, d, generator=g)
+    tok = torch.randint(0, vocab, (r, L), generator=g)
+    out = torch.empty(r * L, d)
+    assert simt.stac_embed_scale_pe(P(tok), P(emb), P(pe), r * L, L, d, vocab, float(np.sqrt(d)), P(out), None) == 0
+    assert torch.allclose(out.view(r, L, d), emb[tok] * np.float32(np.sqrt(d)) + pe[:L][None], atol=1e-5)
+    out1 = torch.empty(r, d)                                                # one position (t = 3) for every row
+    tok3 = tok[:, 3].contiguous()                                           # (kept alive across the call)
+    rc = simt.stac_embed_scale_pe(P(tok3), P(emb), c_void_p(pe.data_ptr() + 3 * d * 4), r, 1, d, vocab,
+                                  float(np.sqrt(d)), P(out1), None)
+    assert rc == 0 and torch.allclose(out1, out.view(r, L, d)[:, 3], atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 4099])
+def test_pcm_to_float(simt, n):
+    pcm = torch.randint(-32768, 32768, (n,), dtype=torch.int16)
+    if n >= 4:
+        pcm[:4] = torch.tensor([-32768, 32767, 0, -1], dtype=torch.int16)
+    out = torch.full((n + 8,), 3.0)
+    assert simt.stac_pcm_i16_to_f32(P(pcm), n, P(out), None) == 0
+    assert torch.equal(out[:n], pcm.float() / 32768.0) and (out[n:] == 3.0).all()
+
+
+def test_utt_mean_std(simt):
+    g = torch.Generator().manual_seed(4)
+    b, t, f = 4, 57, 80
+    x = torch.randn(b, t, f, generator=g) * 3 + 1
+    wl = torch.tensor([1.0, 0.73, 0.41, 0.5])
+    mean, std = torch.empty(b, f), torch.empty(b, f)
+    assert simt.stac_utt_mean_std(P(x), P(wl), b, t, f, 1e-10, P(mean), P(std), None) == 0
+    for i in range(b):
+        n = int(torch.round(wl[i] * t))
+        assert torch.allclose(mean[i], x[i, :n].mean(0), atol=1e-5)
+        assert torch.allclose(std[i], x[i, :n].std(0), atol=1e-5)
+
+
+def test_fp32_encoder_kernels(simt):
+    """The fp32-mode encoder kernels (already parity-green on the B200) under the same CPU emulation: a regression net
+    for sessions without a GPU, and a check of the emulation itself against kernels whose behaviour is known."""
+    g = torch.Generator().manual_seed(1)
+    rows, dim = 37, 256
+    x, gam, bet = torch.randn(rows, dim, generator=g) * 2 + 1, torch.rand(dim, generator=g) + 0.5, torch.randn(dim, generator=g)
+    out = torch.empty(rows, dim)
+    outb = torch.empty(rows, dim, dtype=torch.bfloat16)
+    assert simt.stac_layernorm(P(x), rows, dim, P(gam), P(bet), 1e-6, P(out), P(outb), None) == 0
+    want = torch.nn.functional.layer_norm(x, (dim,), gam, bet, 1e-6)
+    assert torch.allclose(out, want, atol=2e-5) and torch.allclose(outb.float(), want, atol=4e-2, rtol=1e-2)
+    # attention over a packed qkv projection with key padding by length
+    b, t, h = 2, 70, 2
+    d = 64 * h
+    qkv = torch.randn(b * t, 3 * d, generator=g)
+    kv_len = torch.tensor([70, 33], dtype=torch.int32)
+    ctx = torch.empty(b * t, d)
+    assert simt.stac_mha_f32(P(qkv), P(kv_len), b, t, d, h, P(ctx), None) == 0
+    q, k, v = (z.view(b, t, h, 64).transpose(1, 2).double() for z in qkv.split(d, dim=-1))
+    mask = torch.arange(t)[None, :] >= kv_len[:, None]
+    p = torch.softmax((q @ k.transpose(-1, -2)).masked_fill(mask[:, None, None, :], float("-inf")), -1)
+    want = (p @ v).transpose(1, 2).reshape(b * t, d)
+    assert (ctx.double() - want).norm() / want.norm() < 1e-5
+    # log-softmax with the greedy id
+    logits = torch.randn(9, 501, generator=g)
+    lp, ids = torch.empty(9, 501), torch.empty(9, dtype=torch.int32)
+    assert simt.stac_log_softmax(P(logits), 9, 501, P(lp), P(ids), None) == 0
+    assert torch.allclose(lp, torch.log_softmax(logits, -1), atol=1e-5) and torch.equal(ids.long(), logits.argmax(-1))
+    # valid-length rules of encode() / forward() in fp32 (TransformerMultiTask.py:289-294 / :225-226)
+    wl = torch.tensor([1.0, 0.7304, 0.5, 0.013])
+    for rule, fn in ((0, lambda z: torch.floor(z) + 1), (1, torch.round)):
+        n = torch.empty(4, dtype=torch.int32)
+        assert simt.stac_kv_lengths(P(wl), 4, 37, rule, P(n), None) == 0
+        assert torch.equal(n.long(), fn(wl * 37).clamp(1, 37).long())
+    # the CUDA-core GEMM with bias, exact-erf GELU and a periodic residual
+    m, n_, k_ = 45, 24, 64
+    a, w, bias = torch.randn(m, k_, generator=g), torch.randn(n_, k_, generator=g), torch.randn(n_, generator=g)
+    res, c = torch.randn(9, n_, generator=g), torch.empty(m, n_)
+    assert simt.stac_gemm_f32(P(a), P(w), P(bias), P(res), 9, _lib.ACT_GELU_ERF, P(c), m, n_, k_, None) == 0
+    want = torch.nn.functional.gelu(a @ w.T + bias) + res[torch.arange(m) % 9]
+    assert torch.allclose(c, want, atol=1e-4)
+
+
+def test_fp32_path_on_the_emulated_kernels(simt, monkeypatch):
+    """The whole fp32 path - Fbank (FFT kernel), normalisation, both convolution blocks, encoder, CTC head - with every
+    kernel running from its real source under the CPU emulation, against the oracle at the fp32 tolerance."""
+    import abi_emulator
+    import oracle
+    import stac_speech_translation_b200 as sb
+    from stac_speech_translation_b200 import synth
+    from util import FP32_TOL, TINY, oracle_modules, product_from_oracle, rel_l2
+    emu = abi_emulator.install_simt(monkeypatch, simt)
+    omods = oracle_modules(TINY, vocab=64, num_encoder_layers=1)
+    mods = product_from_oracle(omods, "fp32", device="cpu")
+    wavs, wl = synth.synth_batch([0.33, 0.2], seed=35)
+    with torch.no_grad():
+        want = oracle.reference_compute_forward(omods, wavs, wl)
+    got = sb.compute_forward(mods, wavs, wl)
+    for key in ("fbank", "feats", "cnn", "enc_out", "logits", "p_ctc"):
+        assert rel_l2(got[key], want[key]) < FP32_TOL, (key, rel_l2(got[key], want[key]))
+    assert set(emu.routed) >= {"stac_fbank_logmel", "stac_fbank_topdb_norm", "stac_input_norm", "stac_conv0_ln_lrelu",
+                               "stac_conv1_f32", "stac_group_ln_lrelu", "stac_gemm_f32", "stac_layernorm", "stac_mha_f32",
+                               "stac_log_softmax"}
+    assert set(emu.calls) == set(emu.routed)                  # nothing fell back to the numpy stand-ins
