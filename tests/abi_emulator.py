@@ -418,5 +418,13 @@ def install_simt(monkeypatch, simt_lib):
         assert rc == 0, (name, rc)
 
     monkeypatch.setattr(ops, "_call", call)
+    # turns.py / ingest.py call the handle directly: give them the CPU build with the ctypes signatures applied
+    from stac_speech_translation_b200 import ingest, turns
+    for name, (res, sig) in _lib._SIGNATURES.items():
+        fn = getattr(simt_lib, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = res, sig
+    for mod in (turns, ingest):
+        monkeypatch.setattr(mod, "lib", lambda: simt_lib)
     emu.routed = routed
     return emu

@@ -224,3 +224,55 @@ def test_fp32_path_on_the_emulated_kernels(simt, monkeypatch):
                                "stac_conv1_f32", "stac_group_ln_lrelu", "stac_gemm_f32", "stac_layernorm", "stac_mha_f32",
                                "stac_log_softmax"}
     assert set(emu.calls) == set(emu.routed)                  # nothing fell back to the numpy stand-ins
+
+
+def test_decoder_on_the_emulated_kernels_against_reference_vectors(simt, monkeypatch):
+    """TransformerMultiTask.decode() and the KV-cached step with every kernel running from its real source under the CPU
+    emulation, against the vectors the REFERENCE'S OWN decode() produced (tests/golden/decoder_reference.npz)."""
+    import abi_emulator
+    import stac_speech_translation_b200 as sb
+    from test_host_emulated import build, fixture
+    from util import FP32_TOL, rel_l2
+    d, state = fixture()
+    emu = abi_emulator.install_simt(monkeypatch, simt)
+    tr = build(sb.TransformerMultiTask, state, precision="fp32")
+    prefix, enc_out = torch.from_numpy(d["prefix"]), torch.from_numpy(d["enc_out"])
+    pred, attn = tr.decode(prefix, enc_out)
+    assert rel_l2(pred, torch.from_numpy(d["pred"])) < FP32_TOL and rel_l2(attn, torch.from_numpy(d["attn"])) < FP32_TOL
+    pred_len, attn_len = tr.decode(prefix, enc_out, torch.from_numpy(d["enc_len"]))
+    assert rel_l2(pred_len, torch.from_numpy(d["pred_len"])) < FP32_TOL
+    assert rel_l2(attn_len, torch.from_numpy(d["attn_len"])) < FP32_TOL
+    cache = tr.decoder_cache(enc_out, rows=prefix.shape[0], max_len=6)
+    for t in range(prefix.shape[1]):
+        out, w = cache.step(prefix[:, t].contiguous())
+    assert rel_l2(out, torch.from_numpy(d["pred"])[:, -1]) < FP32_TOL
+    assert rel_l2(w, torch.from_numpy(d["attn"])[:, -1]) < FP32_TOL
+    assert set(emu.calls) == set(emu.routed) >= {"stac_embed_scale_pe", "stac_attention_f32", "stac_gemm_f32"}
+
+
+def test_turns_ingest_and_train_norm_drop_ins_on_the_emulated_kernels(simt, monkeypatch):
+    """The three small drop-ins end to end (Python side + kernels from source under the CPU emulation): RTTM lines equal
+    to the reference function's, the PCM decode rule, SpeechBrain's train-mode normalisation updates."""
+    import abi_emulator
+    import stac_speech_translation_b200 as sb
+    from oracle.speechbrain_path import InputNormalization as OracleNorm
+    from stac_speech_translation_b200 import ingest, turns
+    from util import rel_l2
+    abi_emulator.install_simt(monkeypatch, simt)
+    for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "turns_reference.json")))[:3]:
+        ids = torch.tensor(c["ids"], dtype=torch.int32)
+        p = torch.full(ids.shape + (min(c["vocab"], 60),), -20.0)
+        p.scatter_(2, ids.long().clamp(max=p.shape[-1] - 1)[..., None], -0.1)
+        for x in ((ids, p) if c["vocab"] <= 60 else (ids,)):
+            turn, xt = [], []
+            turns.append_speaker_turns(c["utt"], x, 7, 8, turn, xt)
+            assert turn == c["turn_rttm"] and xt == c["xt_rttm"]
+    pcm = torch.randint(-32768, 32768, (3, 1001), dtype=torch.int16)
+    assert torch.equal(ingest.pcm_to_float(pcm), pcm.float() / 32768.0)
+    g = torch.Generator().manual_seed(4)
+    ours, ref = sb.InputNormalization(update_until_epoch=2).train(), OracleNorm(update_until_epoch=2).train()
+    for step, epoch in enumerate([0, 0, 1, 2]):
+        x = torch.randn(3, 50, 80, generator=g) * (1 + step) + step
+        wl = torch.tensor([1.0, 0.73, 0.41])
+        assert rel_l2(ours(x, wl, epoch=epoch), ref(x, wl, epoch=epoch)) < 1e-5
+        assert rel_l2(ours.glob_mean, ref.glob_mean) < 1e-5 and rel_l2(ours.glob_std, ref.glob_std) < 1e-5
