@@ -195,18 +195,33 @@ def run_reference(args, rank, world):
     emit(line)
 
 
-def cpu_baseline(args):
+def cpu_baseline(args, mods=None, wavs=None, wl=None):
+    """The oracle port timed on the host cores on a bounded sample of the workload.  When the product's module graph
+    and the timed batch are given, the oracle is loaded with the PRODUCT's weights and normaliser statistics (through
+    state_dict, as a checkpoint would be) and run on the first utterances of that very batch, and what it returns is
+    handed back as the parity reference for the timed outputs (the oracle is the checker here, nothing else)."""
     import oracle
     from stac_speech_translation_b200 import synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     omods = oracle.build_reference_modules(args.size)
     b = max(1, min(args.cpu_batch, args.batch))
-    wavs, wl = synth.fast_synth_batch(b, args.seconds, seed=1234)
-    norm = omods["normalize"]
-    norm.train(); norm(omods["compute_features"](wavs[:, :32000]), wl); norm.eval()
+    if mods is not None:
+        for k in ("CNN", "Transformer", "ctc_lin"):
+            sd = {k_: v.detach().float().cpu() for k_, v in mods[k].state_dict().items()}
+            res = omods[k].load_state_dict(sd, strict=True)
+            assert not res.missing_keys and not res.unexpected_keys
+        st = mods["normalize"]._statistics_dict()
+        omods["normalize"]._load_statistics_dict(
+            {k_: (v.detach().float().cpu() if torch.is_tensor(v) else v) for k_, v in st.items()})
+        omods["normalize"].eval()
+        wavs, wl = wavs[:b].contiguous(), wl[:b].contiguous()
+    else:
+        wavs, wl = synth.fast_synth_batch(b, args.seconds, seed=1234)
+        norm = omods["normalize"]
+        norm.train(); norm(omods["compute_features"](wavs[:, :32000]), wl); norm.eval()
     t0 = time.perf_counter()
-    oracle.reference_compute_forward(omods, wavs, wl)
+    ref = oracle.reference_compute_forward(omods, wavs, wl)
     warm = time.perf_counter() - t0
     reps = max(3, min(20, int(12.0 / max(warm, 1e-3))))          # about 10-15 s of CPU work
     t0 = time.perf_counter()
@@ -215,7 +230,42 @@ def cpu_baseline(args):
     dt = (time.perf_counter() - t0) / reps
     return {"value": round(b * args.seconds / dt, 2), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{b} x {args.seconds:g} s utterances, {reps} timed passes after 1 warm-up, torch fp32, "
-                      f"{cores} threads"}
+                      f"{cores} threads"}, ref
+
+
+PARITY_TOL = {"bf16": 2e-2, "fp32": 1e-4}      # north_star: relative tolerance on encoder states / posteriors
+
+
+def parity_block(res, ref, n, precision):
+    """The timed batch's outputs (first n utterances) against the oracle's on the same audio and weights."""
+    from stac_speech_translation_b200.pipeline import ctc_greedy_collapse
+
+    def rel(a, b_):
+        a, b_ = a.detach().double().cpu(), b_.detach().double().cpu()
+        return float((a - b_).norm() / b_.norm().clamp_min(1e-30))
+
+    enc, p = res["enc_out"][:n].float().cpu(), res["p_ctc"][:n].float().cpu()
+    ids = res["greedy"][:n].cpu().long()
+    ref_ids = ref["p_ctc"].argmax(-1)
+    t2 = ids.shape[1]
+    seq = ctc_greedy_collapse(ids, [t2] * n)
+    ref_seq = ctc_greedy_collapse(ref_ids, [t2] * n)
+    top2 = ref["p_ctc"].topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1])
+    flipped = ids != ref_ids
+    tol = PARITY_TOL[precision]
+    out = {"utterances": n, "enc_rel_l2": round(rel(enc, ref["enc_out"]), 6),
+           "pctc_rel_l2": round(rel(p, ref["p_ctc"]), 6),
+           "pctc_max_abs": round(float((p - ref["p_ctc"]).abs().max()), 5),
+           "greedy_frame": round(float((~flipped).float().mean()), 5),
+           "greedy_seq": round(sum(a == b_ for a, b_ in zip(seq, ref_seq)) / n, 4),
+           "max_margin_of_flipped_frame": round(float(margin[flipped].max()) if flipped.any() else 0.0, 5),
+           "tolerance": tol,
+           "note": "oracle (fp32 CPU restatement, product's weights) vs the timed batch; synthetic weights are untrained, "
+                   "so greedy ids flip wherever the oracle's own top-2 margin is below the posterior error "
+                   "(the trained-weight criterion is tests/test_gpu_ctc_peaky.py)"}
+    out["ok"] = bool(out["enc_rel_l2"] <= tol and out["pctc_rel_l2"] <= tol)
+    return out
 
 
 def kernel_table(trace, n_steps, wt, pk):
@@ -495,7 +545,12 @@ def run_ours(args, rank, world, local_rank):
         os.makedirs(os.path.dirname(os.path.abspath(args.trace_out)), exist_ok=True)
         json.dump({"table": table, "traced_step_ms": round(step_sum, 3)}, open(args.trace_out, "w"), indent=1)
 
-    cpu = None if args.no_cpu_baseline else cpu_baseline(args)
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
+        cpu, ref = cpu_baseline(args, mods, wavs_cpu, wl_cpu)
+        res = pipe(wavs, wl)                       # the batch every timed step ran on, same kernels
+        torch.cuda.synchronize()
+        parity = parity_block(res, ref, ref["enc_out"].shape[0], args.precision)
     total_audio = audio_s * world
     line = {
         "metric": METRIC, "value": round(total_audio / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
@@ -513,9 +568,13 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks.summary(),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "kernels": [{k: v for k, v in r.items() if k != "work_per_launch"} for r in table[:8]],
     }
     emit(line)
+    if parity is not None and not parity["ok"]:
+        print(f"bench: PARITY FAILURE against the oracle: {parity}", file=sys.stderr)
+        sys.exit(3)
 
 
 _RESULT_FD = None

@@ -256,6 +256,9 @@ int stac_utt_mean_std(const float* x, const float* wav_len, int64_t batch, int64
 
 /* fp32 -> bf16 conversion (weight packing / activation hand-off) */
 int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);
+/* bf16 -> fp32 (exact): the staged drop-in CNN returns fp32 as the reference's does (inference.py:99) while conv1's
+ *        epilogue produces bf16 */
+int stac_cast_f32(const uint16_t* x, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

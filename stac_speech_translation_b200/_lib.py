@@ -57,6 +57,7 @@ _SIGNATURES = {
     "stac_pcm_i16_to_f32": (c_int, [_P, c_int64, _P, _P]),
     "stac_utt_mean_std": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
     "stac_cast_bf16": (c_int, [_P, c_int64, _P, _P]),
+    "stac_cast_f32": (c_int, [_P, c_int64, _P, _P]),
 }
 
 _lib = None
@@ -94,6 +95,9 @@ def check(code: int, what: str = "") -> None:
 
 
 def stream() -> c_void_p:
+    """Current stream of the CURRENT device.  The library is one-device-per-process (one process per GPU, as the
+    multi-GPU path launches it): ptr() refuses tensors that live on another device, so a kernel can never be enqueued
+    on one GPU with pointers of another."""
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -103,6 +107,9 @@ def ptr(t, dtype=None):
         return c_void_p(0)
     if not t.is_cuda:
         raise StacB200Error("stac_b200 kernels need CUDA tensors; there is no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        raise StacB200Error(f"tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}"
+                            " (stac_b200 is one device per process: torch.cuda.set_device first)")
     if not t.is_contiguous():
         raise StacB200Error("stac_b200 kernels need contiguous tensors")
     if dtype is not None and t.dtype != dtype:

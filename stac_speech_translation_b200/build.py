@@ -28,7 +28,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", extra_f
     """Default: libstac_b200.so.  `variant` + `extra_flags` build libstac_b200_<variant>.so next to it with additional
     nvcc flags (timing experiments, e.g. -DMHA_OSTAGED_PER_BUFFER); load it with STAC_B200_LIB=<path>."""
     srcs = sorted(CSRC.glob("*.cu"))
-    hdrs = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "stac_b200.h"]
+    hdrs = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [PKG.parent / "include" / "stac_b200.h"]
     objdir = CSRC / ("build_" + variant if variant else "build")
     objdir.mkdir(exist_ok=True)
     lib_path = PKG / f"libstac_b200_{variant}.so" if variant else LIB

@@ -43,16 +43,12 @@ constexpr int kOffKV = 131072;                   // [stages] x (K 8 KB + V 8 KB)
 constexpr int kOffX = kOffKV + kKvStages * 16384;      // float [2 groups][2 bufs][2 halves][128 rows]: row-max exchange
 constexpr int kOffLen = kOffX + 2 * 2 * 2 * 128 * 4;   // int [kLenCache]
 constexpr int kOffBar = kOffLen + 128 * 4;
-// MHA_OSTAGED_PER_BUFFER (off in the default build until it has run on a B200): one o_staged barrier per (Q buffer,
-// group) instead of one per group.  tools/model_check_mha1.py shows that with one barrier per group a softmax group
-// that gets two short work items ahead of the store warp completes TWO phases of it before the store warp looks, the
-// parity wait aliases, and the kernel deadlocks (mbarrier time-out trap); a per-buffer barrier cannot run ahead, because
-// the buffer itself is only refilled after the store warp has released it.  DESIGN.md section 9.
-#ifdef MHA_OSTAGED_PER_BUFFER
+// One o_staged barrier per (Q buffer, group), not one per group: tools/model_check_mha1.py shows that with one barrier
+// per group a softmax group that gets two short work items ahead of the store warp completes TWO phases of it before the
+// store warp looks, the parity wait aliases, and the kernel deadlocks (mbarrier time-out trap); a per-buffer barrier
+// cannot run ahead, because the buffer itself is only refilled after the store warp has released it.  Verified on a
+// B200 (round 2: parity suite + the many-short-items stress shape, 86.1 us vs 87.4 us).  DESIGN.md section 9.
 constexpr int kNumOStaged = 4;
-#else
-constexpr int kNumOStaged = 2;
-#endif
 constexpr int kNumBars = 8 + 2 * kKvStages + 18 + kNumOStaged;
 #ifdef MHA_TRACE
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024 + 5 * 64 * 8 * 4;
@@ -149,11 +145,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto p_free = [&](int w, int i) { return gb + 8u * (w * 9 + 6 + i); };
   auto o_free = [&](int w) { return gb + 8u * (w * 9 + 8); };
   // the group's O tile is staged in smem (in Q buffer `buf`) for the store warp
-#ifdef MHA_OSTAGED_PER_BUFFER
   auto o_staged = [&](int buf, int w) { return gb + 8u * (18 + buf * 2 + w); };
-#else
-  auto o_staged = [&](int buf, int w) { (void)buf; return gb + 8u * (18 + w); };
-#endif
   const uint32_t tmem_slot = bars + 8u * kNumBars;
 #ifdef MHA_TRACE
   unsigned int* trace_s = reinterpret_cast<unsigned int*>(sptr + kOffBar + kNumBars * 8 + 16);
@@ -232,11 +224,7 @@ mha_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int buf = n_done & 1;
       for (int w = 0; w < 2; ++w) {
         if (w == 1 && !it.active1) continue;
-#ifdef MHA_OSTAGED_PER_BUFFER
         const int bit = buf * 2 + w;
-#else
-        const int bit = w;
-#endif
         mbar_wait(o_staged(buf, w), (st_par >> bit) & 1);
         st_par ^= 1u << bit;
         if (elect_one()) {

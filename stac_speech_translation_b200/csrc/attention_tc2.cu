@@ -1,36 +1,34 @@
-// EXPERIMENTAL second decomposition of the tcgen05 flash attention (stac_mha_bf16_v2).  NOT on the default path:
-// ops.py calls it only when STAC_MHA_V2=1.  It compiles for sm_100a (ptxas accepts every instruction form used), but it
-// was written after the round's GPU budget was spent and HAS NOT RUN ON A B200 YET; its parity test
-// (tests/test_gpu_tc_attention.py::test_mha_bf16_v2) is skipped unless STAC_EXPERIMENTAL=1.
+// Second decomposition of the tcgen05 flash attention (stac_mha_bf16_v2): P in tensor memory, one thread per query row,
+// scores DOUBLE-BUFFERED per query group so that the softmax warps never wait for the tensor pipe.
 //
 // Reference behaviour replaced: the same as attention_tc.cu (torch.nn.MultiheadAttention slow path with a -inf
 // key-padding mask, reached from /root/reference/stac-st/modules/TransformerMultiTask.py:304-308).
 //
-// Why a second decomposition ("Attention, what the trace says now"): the first kernel balances two halves
-// that are both too slow - two threads per row over 64-key tiles with P going through shared memory cost a softmax
-// step ~1950 clk per 64 keys (MUFU floor 512), and its MMA issue loop costs ~1150 clk per step.  This one is the layout
-// FlashAttention-4 / CUTLASS' sm100 FMHA use:
-//   * 128-key tiles: half as many steps, barriers, commits and MMA blocks per key;
-//   * ONE thread per query row (no row-max exchange between warps, no named barrier in the step);
-//   * P never touches shared memory: the bf16 probabilities are written back into TMEM over the scores they came from
-//     (tcgen05.st) and P.V takes its A operand from TMEM (tcgen05.mma [d], [a_tmem], b_desc) - no st.shared, no
-//     fence.proxy.async, and 32 KB of shared memory per stage set free for 128-key K/V tiles;
-//   * S is single-buffered per query group (P aliases it), the two query groups of a work item alternate on the
-//     tensor pipe: while one group runs its exponentials the other group's P.V and next Q.K^T execute;
-//   * O is double-buffered in TMEM and the item epilogue (O / l -> bf16 -> smem -> TMA store) belongs to its own
-//     warpgroup, so the softmax warps go straight on to the next item;
-//   * an optional share of the exponentials is evaluated on the FMA pipe (Cody-Waite split + cubic), -DMHA2_POLY=n
-//     (n of every 8 columns), default 0, to get under the MUFU floor once the rest of the chain is tight.
-// Budget per 128-key step of one CTA (2 x 128 query rows): MUFU 2 x 128 x 128 / 16 = 2048 clk, tensor pipe
-// 2 x (256 + 256) = 1024 clk; the first kernel needs 2 x 1950 = 3900 clk for the same work.
+// History.  The first kernel (attention_tc.cu: two threads per row, 64-key tiles, P through shared
+// memory) balances two halves that are both too slow.  The first version of this file (round 2, first GPU call: parity
+// green, 83 us against 87 us) moved to the FlashAttention-4 layout - 128-key tiles, thread = row, P written back into
+// TMEM over its own scores and taken from there as the A operand of P.V - but kept ONE score buffer per query group.
+// Its clock trace (profiles/r3/r3a_mha2_trace.log) shows what that costs: per 128-key step a group spends ~2000 clk in
+// its exponentials and then ~1850 clk waiting for P.V(g) and S(g+1) to come back from the tensor pipe (both groups end
+// up in phase, so they also share the MUFU while they compute and leave it idle while they wait): 4980 clk per step
+// against a MUFU floor of 2048.  This version removes the wait instead of shortening it:
+//   * 96-key tiles, so that TWO score buffers per group fit in tensor memory next to O (4 x 96 + 2 x 64 = 512 columns);
+//     S(g+1) and S(g+2) are issued while softmax(g) runs, and the softmax warps go from one tile straight to the next;
+//   * O is single-buffered (one item boundary per 8 steps; the epilogue warpgroup drains it in a few hundred clocks);
+//   * everything else as before: ONE thread per query row (no row-max exchange), P never touches shared memory
+//     (tcgen05.st over the scores, TS-form tcgen05.mma), lazy rescaling (O is only touched by the CUDA cores when a row
+//     maximum rises by more than 2^40 - then behind a wait for the P.V in flight), O / l -> bf16 -> smem -> TMA store by
+//     its own warpgroup, optional share of the exponentials on the FMA pipe (-DMHA2_POLY=n, default 0: measured slower).
+// Budget per 96-key step of one CTA (2 x 128 query rows): MUFU 2 x 128 x 96 / 16 = 1536 clk, tensor pipe
+// 2 x (192 + 192) = 768 clk.
 //
-// The TMEM conventions this relies on - thread = lane = query row for 32x32b loads / stores, P as packed bf16 pairs
-// (keys 2c, 2c+1 in 32-bit column c, even key in the low half) on top of its own scores, 8 columns per K = 16 step of
-// the TS-form MMA - are the ones the public CUTLASS CuTeDSL Blackwell FMHA example uses (St32x32b of the score
-// registers recast to the 16-bit type; P.V fragments taken from TMEM); read for the conventions only, no code shared.
+// The TMEM conventions this relies on were probed with exact integer data on a B200 (tools/probe_ts_mma.cu,
+// profiles/r3/r3a_first_call_verification.log): thread = lane = query row for 32x32b loads / stores, P as packed bf16
+// pairs (keys 2c, 2c+1 in 32-bit column c, even key in the LOW half) on top of its own scores, 8 columns per K = 16 step
+// of the TS-form MMA.
 //
-// TMEM (512 columns): S/P group 0 at 0, group 1 at 128 (128 fp32 score columns; P = 64 columns of packed bf16 pairs
-// on top of the first 64); O[group][buffer] at 256 + (group * 2 + buffer) * 64.
+// TMEM (512 columns): S/P buffer (group w, buffer sb) at (w * 2 + sb) * 96 (96 fp32 score columns; P = 48 columns of
+// packed bf16 pairs on top of the first 48); O[group] at 384 + group * 64.
 // Threads (512): warps 0-3 softmax group 0, 4-7 softmax group 1 (warp & 3 = TMEM lane quarter), 8-11 epilogue
 // warpgroup, 12/13 MMA issuers of group 0/1, 14 TMA producer, 15 idle.  setmaxnreg: 176 / 80 / 80.
 #include <algorithm>
@@ -41,11 +39,15 @@ namespace {
 
 using namespace tc;
 
-constexpr int kHd = 64, kQTile = 128, kKTile = 128;
+constexpr int kHd = 64, kQTile = 128, kKTile = 96;
 #ifndef MHA2_KV_STAGES
-#define MHA2_KV_STAGES 3
+#define MHA2_KV_STAGES 4
 #endif
-constexpr int kKvStages = MHA2_KV_STAGES;            // 32 KB each; 3 is the most that fits beside Q (64 KB) and the staging tiles (32 KB)
+constexpr int kKvStages = MHA2_KV_STAGES;            // 24 KB each (K 12 KB + V 12 KB); S runs two tiles ahead of P.V: >= 3
+constexpr int kKBytes = kKTile * kHd * 2;             // one K (or V) tile
+constexpr int kStageBytes = 2 * kKBytes;
+constexpr int kSCols = kKTile;                         // fp32 score columns of one S buffer
+constexpr int kOCol = 4 * kSCols;                      // first O column
 constexpr int kThreads = 512;
 constexpr int kRegsSoftmax = 176, kRegsOther = 80;     // 256 * 176 + 256 * 80 = 512 * 128
 #ifndef MHA2_POLY
@@ -55,22 +57,14 @@ constexpr int kRegsSoftmax = 176, kRegsOther = 80;     // 256 * 176 + 256 * 80 =
 constexpr int kOffQ = 0;                               // [2 bufs][2 groups] x 16 KB
 constexpr int kOffOut = 65536;                         // [2 groups] x 16 KB: normalised bf16 O tile for the TMA store
 constexpr int kOffKV = 98304;                          // [stages] x (K 16 KB + V 16 KB)
-constexpr int kOffX = kOffKV + kKvStages * 32768;      // float [2 groups][2 O buffers][128 rows]: 1 / row sum
-constexpr int kOffLen = kOffX + 2 * 2 * 128 * 4;       // int [kLenCache]
+constexpr int kOffX = kOffKV + kKvStages * kStageBytes; // float [2 groups][128 rows]: 1 / row sum
+constexpr int kOffLen = kOffX + 2 * 128 * 4;           // int [kLenCache]
 constexpr int kLenCache = 128;
 constexpr int kOffBar = kOffLen + kLenCache * 4;
-// -DMHA2_SEQUENCE (experiment, default off): the two softmax groups take strict turns in their exponential phase
-// (group 0 step g, group 1 step g, group 0 step g+1, ...) through two more barriers, so that each group's TMEM load /
-// maximum / P store falls into the other group's exponentials instead of competing with them for the MUFU.  Group 1
-// walks the sequence as virtual steps through items in which it has no query tile.
-#ifdef MHA2_SEQUENCE
-constexpr int kNumSeqBars = 2;
-#else
-constexpr int kNumSeqBars = 0;
-#endif
-constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 8 + kNumSeqBars;
+constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 9;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
-static_assert(kKvStages >= 2 && kSmemBytes <= 232448, "K/V ring does not fit in shared memory");
+static_assert(kKvStages >= 3 && kSmemBytes <= 232448, "K/V ring does not fit in shared memory");
+static_assert(kOCol + 2 * kHd <= 512 && kKTile % 32 == 0 && kKBytes % 1024 == 0, "tensor-memory / tile layout");
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_mufu(float x) {
@@ -182,18 +176,17 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   auto q_empty = [&](int buf, int w) { return bars + 8u * (4 + buf * 2 + w); };
   auto kv_full = [&](int s) { return bars + 8u * (8 + s); };
   auto kv_empty = [&](int s) { return bars + 8u * (8 + kKvStages + s); };
-  // per group (8 each).  One phase of s_full / p_full per key-tile step of the group (parity = step & 1); one phase of
-  // o_full / l_full / o_free per use of an O buffer (parity = (use >> 1) & 1, use = ordinal of the item among the
-  // items in which the group has a query tile).
+  // Per group (9 each).  s_full / p_full / pv_done exist per score buffer sb = step & 1; use number (step >> 1) of a buffer
+  // has parity (step >> 1) & 1.  Per-buffer barriers cannot run ahead of their waiter: S(g + 2) is only issued behind
+  // P.V(g), i.e. after the issuer has passed p_full(g), i.e. after the softmax group has consumed s_full(g).
+  // o_full / l_full / o_free: one phase per work item in which the group has a query tile (parity = use & 1).
   const uint32_t gb = bars + 8u * (8 + 2 * kKvStages);
-  auto s_full = [&](int w) { return gb + 8u * (w * 8); };              // MMA commit: S(step) is in TMEM
-  auto p_full = [&](int w) { return gb + 8u * (w * 8 + 1); };          // 4 softmax warps: P(step) is in TMEM
-  auto o_full = [&](int w, int ob) { return gb + 8u * (w * 8 + 2 + ob); };   // MMA commit: last P.V of the item retired
-  auto l_full = [&](int w, int ob) { return gb + 8u * (w * 8 + 4 + ob); };   // 4 softmax warps: 1 / l is in smem
-  auto o_free = [&](int w, int ob) { return gb + 8u * (w * 8 + 6 + ob); };   // 4 epilogue warps: O and 1 / l were read
-#ifdef MHA2_SEQUENCE
-  auto seq_done = [&](int w) { return gb + 8u * (16 + w); };      // 4 softmax warps of group w: exponentials of a step issued
-#endif
+  auto s_full = [&](int w, int sb) { return gb + 8u * (w * 9 + sb); };        // MMA commit: S(step) is in TMEM
+  auto p_full = [&](int w, int sb) { return gb + 8u * (w * 9 + 2 + sb); };    // 4 softmax warps: P(step) is in TMEM
+  auto pv_done = [&](int w, int sb) { return gb + 8u * (w * 9 + 4 + sb); };   // MMA commit: P.V(step) has retired
+  auto o_full = [&](int w) { return gb + 8u * (w * 9 + 6); };                 // MMA commit: last P.V of the item retired
+  auto l_full = [&](int w) { return gb + 8u * (w * 9 + 7); };                 // 4 softmax warps: 1 / l is in smem
+  auto o_free = [&](int w) { return gb + 8u * (w * 9 + 8); };                 // 4 epilogue warps: O and 1 / l were read
   const uint32_t tmem_slot = bars + 8u * kNumBars;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -209,12 +202,10 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int i = 0; i < 4; ++i) { mbar_init(q_full(i >> 1, i & 1), 1); mbar_init(q_empty(i >> 1, i & 1), 1); }
     for (int s = 0; s < kKvStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }
     for (int w = 0; w < 2; ++w) {
-      mbar_init(s_full(w), 1);
-      mbar_init(p_full(w), 4);
-      for (int ob = 0; ob < 2; ++ob) { mbar_init(o_full(w, ob), 1); mbar_init(l_full(w, ob), 4); mbar_init(o_free(w, ob), 4); }
-#ifdef MHA2_SEQUENCE
-      mbar_init(seq_done(w), 4);
-#endif
+      for (int sb = 0; sb < 2; ++sb) { mbar_init(s_full(w, sb), 1); mbar_init(p_full(w, sb), 4); mbar_init(pv_done(w, sb), 1); }
+      mbar_init(o_full(w), 1);
+      mbar_init(l_full(w), 4);
+      mbar_init(o_free(w), 4);
     }
     fence_barrier_init();
   }
@@ -251,11 +242,11 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
           for (int j = 0; j < it.n_kt; ++j) {
             mbar_wait(kv_empty(stage), kv_phase ^ 1);
-            const uint32_t kdst = sbase + kOffKV + stage * 32768;
-            mbar_arrive_expect_tx(kv_full(stage), 32768);
+            const uint32_t kdst = sbase + kOffKV + stage * kStageBytes;
+            mbar_arrive_expect_tx(kv_full(stage), kStageBytes);
             // rows past the utterance (or past the batch: zero fill) carry finite values and meet P = 0
             tma_load_2d(kdst, &tmap_kv, kv_full(stage), d_model + it.h * kHd, row_base + j * kKTile);
-            tma_load_2d(kdst + 16384, &tmap_kv, kv_full(stage), 2 * d_model + it.h * kHd, row_base + j * kKTile);
+            tma_load_2d(kdst + kKBytes, &tmap_kv, kv_full(stage), 2 * d_model + it.h * kHd, row_base + j * kKTile);
             if (++stage == kKvStages) { stage = 0; kv_phase ^= 1; }
           }
         }
@@ -263,9 +254,10 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __syncwarp();
     } else if (warp < 14) {
       // ============================ MMA issuers: warp 12 -> group 0, warp 13 -> group 1 ============================
-      // Order per group: S(0) | P.V(0) S(1) | P.V(1) S(2) | ...  P(g) lives on top of S(g), so S(g+1) is issued right
-      // behind P.V(g): tcgen05.mma of one thread execute in issue order, which is what keeps S(g+1) from overwriting
-      // P(g) before P.V(g) has read it.  p_full(g) also says that every softmax thread has pulled S(g) out of TMEM.
+      // Order per group: S(0) S(1) | P.V(0) S(2) | P.V(1) S(3) | ...  S(g + 2) lands in the buffer P(g) lives in, so it
+      // is issued behind P.V(g): the tcgen05.mma of one thread execute in issue order, which is what keeps S(g + 2) from
+      // overwriting P(g) before P.V(g) has read it.  p_full(g) also says that every softmax thread has pulled S(g) out of
+      // TMEM.
       auto issuer = [&](auto group) {
         constexpr int w = decltype(group)::value;
         constexpr uint32_t idesc_s = make_idesc_bf16(128, kKTile);
@@ -302,13 +294,14 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         Cursor pc = sc;
         int g_s = 0, g_p = 0;                 // per-group step indices of the next S and the next P.V
         uint32_t q_fill0 = 0, q_fill1 = 0;    // consumed fills of Q buffers 0 / 1 of this group
-        uint32_t uses = 0;                    // items of this group whose P.V sequence has started
+        uint32_t uses = 0;                    // items of this group whose P.V sequence has finished being issued
         const uint32_t q_base = sbase + kOffQ + w * 16384;
-        const uint32_t s_tmem = tmem_base + w * 128;
+        const uint32_t o_tmem = tmem_base + kOCol + w * kHd;
         while (pc.valid) {
           if (w == 1 && pc.virt) {
             // an item without a query tile for this group: every K/V stage of it is still observed and handed back in
-            // order (a consumer that jumps over uses of a parity-tracked mbarrier can alias a pending phase)
+            // order (a consumer that jumps over uses of a parity-tracked mbarrier can alias a pending phase).
+            // The S cursor never passes a virtual item, so it stands at the start of this one.
             const int n = pc.n_kt;
             for (int k = 0; k < n; ++k) {
               mbar_wait(kv_full(pc.stage), pc.phase);
@@ -319,9 +312,13 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             sc = pc;
             continue;
           }
-          if (sc.valid && !(w == 1 && sc.virt) && g_s < g_p + 1) {
-            // ---- S(g_s) = Q K^T ----
+          // ---- S(g_s) = Q K^T, up to two tiles ahead of the P.V sequence ----
+          // (g_s == g_p: nothing else can make progress, wait for the tile; otherwise take it only if it has landed,
+          // so that a late K/V tile never delays a P.V whose probabilities are ready)
+          if (sc.valid && !(w == 1 && sc.virt) && g_s < g_p + 2 &&
+              (g_s == g_p || mbar_test_wait(kv_full(sc.stage), sc.phase))) {
             const int buf = sc.n_done & 1;
+            const int sb = g_s & 1;
             if (lane == 0) TRACE2(w, 0, g_s);
             mbar_wait(kv_full(sc.stage), sc.phase);
             if (sc.j == 0) mbar_wait(q_full(buf, w), (buf ? q_fill1 : q_fill0) & 1);
@@ -329,11 +326,12 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tc_fence_after();
             const bool last_of_item = sc.j == sc.n_kt - 1;
             if (elect_one()) {
+              const uint32_t s_tmem = tmem_base + (w * 2 + sb) * kSCols;
               const uint64_t qd = make_smem_desc_sw128(q_base + buf * 32768);
-              const uint64_t kd = make_smem_desc_sw128(sbase + kOffKV + sc.stage * 32768);
+              const uint64_t kd = make_smem_desc_sw128(sbase + kOffKV + sc.stage * kStageBytes);
 #pragma unroll
               for (int k = 0; k < kHd / 16; ++k) umma_bf16(s_tmem, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-              umma_commit(s_full(w));
+              umma_commit(s_full(w, sb));
               if (last_of_item) umma_commit(q_empty(buf, w));
             }
             __syncwarp();
@@ -341,26 +339,28 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) TRACE2(w, 2, g_s);
             ++g_s;
             advance(sc);
+            continue;
           }
           // ---- O += P(g_p) V ----
           {
-            const int ob = uses & 1;
+            const int sb = g_p & 1;
             if (lane == 0) TRACE2(w, 3, g_p);
-            mbar_wait(p_full(w), (uint32_t)g_p & 1);
-            if (pc.j == 0) mbar_wait(o_free(w, ob), ((uses >> 1) & 1) ^ 1);    // the epilogue has drained this O buffer
+            mbar_wait(p_full(w, sb), (uint32_t)(g_p >> 1) & 1);
+            if (pc.j == 0) mbar_wait(o_free(w), (uses & 1) ^ 1);      // the epilogue has drained the previous item's O
             if (lane == 0) TRACE2(w, 4, g_p);
             tc_fence_after();
             const bool last_of_item = pc.j == pc.n_kt - 1;
             if (elect_one()) {
-              const uint32_t o_tmem = tmem_base + 256 + (w * 2 + ob) * kHd;
-              const uint64_t vd = make_smem_desc_sw128(sbase + kOffKV + pc.stage * 32768 + 16384);
+              const uint32_t p_tmem = tmem_base + (w * 2 + sb) * kSCols;
+              const uint64_t vd = make_smem_desc_sw128(sbase + kOffKV + pc.stage * kStageBytes + kKBytes);
 #pragma unroll
               for (int k = 0; k < kKTile / 16; ++k) {
                 // A: 16 keys = 8 TMEM columns of bf16 pairs; B: 16 keys = 16 rows of 128 bytes of the MN-major V tile
-                umma_bf16_ts(o_tmem, s_tmem + 8 * k, vd + 128 * k, idesc_o, (k | pc.j) != 0);
+                umma_bf16_ts(o_tmem, p_tmem + 8 * k, vd + 128 * k, idesc_o, (k | pc.j) != 0);
               }
               umma_commit(kv_empty(pc.stage));                 // the second arrival comes from the other group's issuer
-              if (last_of_item) umma_commit(o_full(w, ob));
+              umma_commit(pv_done(w, sb));
+              if (last_of_item) umma_commit(o_full(w));
             }
             __syncwarp();
             if (last_of_item) ++uses;
@@ -389,15 +389,14 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         if (w == 1 && !it.active1) continue;
-        const int ob = uses[w] & 1;
-        const uint32_t ph = (uses[w] >> 1) & 1;
+        const uint32_t ph = uses[w] & 1;
         ++uses[w];
         const bool tr = warp == 8 && lane == 0;
         if (tr) TRACE2(4, 0, ordinal * 2 + w);
-        mbar_wait(l_full(w, ob), ph);
+        mbar_wait(l_full(w), ph);
         if (tr) TRACE2(4, 1, ordinal * 2 + w);
-        const float inv = xch[(w * 2 + ob) * 128 + r];
-        mbar_wait(o_full(w, ob), ph);
+        const float inv = xch[w * 128 + r];
+        mbar_wait(o_full(w), ph);
         if (tr) TRACE2(4, 2, ordinal * 2 + w);
         tc_fence_after();
         // the previous TMA store out of this group's staging tile must have read it
@@ -407,7 +406,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t o[32];
-          tmem_ld32(tmem_base + 256 + (w * 2 + ob) * kHd + half * 32 + lane_off, o);
+          tmem_ld32(tmem_base + kOCol + w * kHd + half * 32 + lane_off, o);
           tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -421,7 +420,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(o_free(w, ob));     // O buffer and 1 / l slot may be reused
+        if (lane == 0) mbar_arrive(o_free(w));         // O and the 1 / l slot may be reused
         if (tr) TRACE2(4, 3, ordinal * 2 + w);
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
@@ -444,31 +443,14 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;             // row inside the tile = TMEM lane
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t s_tmem = tmem_base + w * 128 + lane_off;
+    const uint32_t o_tmem = tmem_base + kOCol + w * kHd + lane_off;
     float* xch = reinterpret_cast<float*>(sptr + kOffX);
     uint32_t g = 0;                                // per-group step index
     uint32_t uses = 0;
     int ordinal = 0;
-#ifdef MHA2_SEQUENCE
-    uint32_t gs = 0;                               // position in the exponential sequence (virtual steps included)
-#endif
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
       const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
-#ifdef MHA2_SEQUENCE
-      if (w == 1 && !it.active1) {
-        // no query tile for this group: keep the turn-taking going, one virtual step per key tile
-        for (int j = 0; j < it.n_kt; ++j, ++gs) {
-          mbar_wait(seq_done(0), gs & 1);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(seq_done(1));
-        }
-        continue;
-      }
-#else
       if (w == 1 && !it.active1) continue;
-#endif
-      const int ob = uses & 1;
-      const uint32_t o_tmem = tmem_base + 256 + (w * 2 + ob) * kHd + lane_off;
       // m_ref: the maximum the exponents are taken against.  It is only raised (and O / l rescaled) when the running
       // maximum exceeds it by more than 2^kRaise: P <= 2^kRaise stays far inside bf16 / fp32 range, and O in TMEM is
       // touched by the CUDA cores only on those rare steps.
@@ -476,25 +458,27 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < it.n_kt; ++j, ++g) {
         const bool tr = (warp & 3) == 0 && lane == 0;
+        const int sb = g & 1;
+        const uint32_t s_tmem = tmem_base + (w * 2 + sb) * kSCols + lane_off;
         if (tr) TRACE2(2 + w, 0, g);
-        mbar_wait(s_full(w), g & 1);
+        mbar_wait(s_full(w, sb), (g >> 1) & 1);
         if (tr) TRACE2(2 + w, 1, g);
         tc_fence_after();
-        uint32_t v[4][32];
+        uint32_t v[kKTile / 32][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, v[c]);
+        for (int c = 0; c < kKTile / 32; ++c) tmem_ld32(s_tmem + c * 32, v[c]);
         tmem_ld_wait();
         if (tr) TRACE2(2 + w, 2, g);
         const int valid = it.n_keys - j * kKTile;      // my columns < valid are real keys
         if (valid < kKTile) {
-          // last tile of the utterance only (a real branch: the full tiles must not pay 128 compare / select pairs)
+          // last tile of the utterance only (a real branch: the full tiles must not pay the compare / select pairs)
 #pragma unroll
-          for (int c = 0; c < 128; ++c)
+          for (int c = 0; c < kKTile; ++c)
             if (c >= valid) v[c >> 5][c & 31] = 0xff800000u;        // -inf: exp2 gives exactly 0
         }
         float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 128; c += 4) {
+        for (int c = 0; c < kKTile; c += 4) {
           tm0 = max3(tm0, __uint_as_float(v[c >> 5][c & 31]), __uint_as_float(v[c >> 5][(c & 31) + 1]));
           tm1 = max3(tm1, __uint_as_float(v[c >> 5][(c & 31) + 2]), __uint_as_float(v[c >> 5][(c & 31) + 3]));
         }
@@ -504,11 +488,17 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         } else {
           const bool raise = (tile_max - m_ref) * kLog2e > kRaise;
           if (__any_sync(0xffffffffu, raise)) {
-            // s_full(g) was committed behind P.V(g - 1): O holds every earlier step and no MMA is in flight on it
+            // O must hold every earlier step of the item and nothing may be in flight on it: P.V(g - 1) is the last one
+            // issued (P.V(g) needs the probabilities this thread has yet to write).  Its barrier is the other buffer's
+            // pv_done; completion number (g - 1) >> 1 of it is either the current phase or the one just finished
+            // (P.V(g + 1) cannot be issued before this step is over, P.V(g - 3) retired before S(g) did), so this
+            // occasional wait cannot alias even though the steps in between never look at the barrier.
+            mbar_wait(pv_done(w, sb ^ 1), ((g - 1) >> 1) & 1);
+            tc_fence_after();
             const float factor = raise ? ex2_mufu((m_ref - tile_max) * kLog2e) : 1.0f;
             if (raise) m_ref = tile_max;
             l_run *= factor;
-            // (rare path: 8 columns at a time so that the 128 live scores are not spilled around it)
+            // (rare path: 8 columns at a time so that the live scores are not spilled around it)
 #pragma unroll 1
             for (int c = 0; c < kHd; c += 8) {
               uint32_t o[8];
@@ -521,14 +511,10 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         if (tr) TRACE2(2 + w, 3, g);
-#ifdef MHA2_SEQUENCE
-        if (w == 0) { if (gs > 0) mbar_wait(seq_done(1), (gs - 1) & 1); }     // group 1 is through step gs - 1
-        else mbar_wait(seq_done(0), gs & 1);                                   // group 0 is through step gs
-#endif
         const float m_scaled = m_ref * kLog2e;
         float2 l0 = make_float2(0.f, 0.f), l1 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kKTile / 32; ++c) {
           // P columns 16 c .. 16 c + 15 cover score columns that are already in registers (16 c + 15 < 32 (c + 1))
           uint32_t pk[16];
 #pragma unroll
@@ -549,23 +535,18 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         l_run += (l0.x + l0.y) + (l1.x + l1.y);
         if (tr && l_run != 123.f) TRACE2(2 + w, 4, g);
-#ifdef MHA2_SEQUENCE
-        __syncwarp();
-        if (lane == 0) mbar_arrive(seq_done(w));
-        ++gs;
-#endif
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(w));
+        if (lane == 0) mbar_arrive(p_full(w, sb));
         if (tr) TRACE2(2 + w, 5, g);
       }
-      // end of the item: hand 1 / l to the epilogue warpgroup.  The slot (and the O buffer) were last used two items of
-      // this group ago; o_free says the epilogue is done with both.
-      mbar_wait(o_free(w, ob), ((uses >> 1) & 1) ^ 1);
-      xch[(w * 2 + ob) * 128 + r] = 1.0f / l_run;
+      // end of the item: hand 1 / l to the epilogue warpgroup.  The slot was last used one item of this group ago;
+      // o_free says the epilogue is done with it.
+      mbar_wait(o_free(w), (uses & 1) ^ 1);
+      xch[w * 128 + r] = 1.0f / l_run;
       __syncwarp();
-      if (lane == 0) mbar_arrive(l_full(w, ob));
+      if (lane == 0) mbar_arrive(l_full(w));
       ++uses;
     }
   }

@@ -1,6 +1,5 @@
 // Decoder-side building blocks (the consumer right behind the encoder path): first correct CUDA path,
-// fp32 on the CUDA cores.  Written after the round-1 GPU budget was spent: compiles for sm_100a, NOT YET RUN ON A B200
-// (tests/test_gpu_decoder.py is skipped unless STAC_EXPERIMENTAL=1).
+// fp32 on the CUDA cores (parity on a B200: tests/test_gpu_decoder.py, first run round 2).
 //
 // Reference behaviour replaced: TransformerMultiTask.decode(), /root/reference/stac-st/modules/TransformerMultiTask.py
 // :234-271, and the decoder half of forward() :185-209 - NormalizedEmbedding + positional encoding, then SpeechBrain's

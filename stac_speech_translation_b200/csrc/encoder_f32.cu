@@ -121,7 +121,7 @@ mha_f32_kernel(const float* __restrict__ qkv, const int* __restrict__ kv_len, in
 
 // ---- log-softmax over the vocabulary (+ greedy argmax): one CTA per row ----------------------
 __global__ void __launch_bounds__(256)
-log_softmax_kernel(const float* __restrict__ logits, int vocab, float* __restrict__ out,
+log_softmax_kernel(const float* logits, int vocab, float* out,      // in-place calls alias logits and out
                    int* __restrict__ argmax) {
   __shared__ float red[40];
   __shared__ int red_i[8];
@@ -180,6 +180,20 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bf
   }
 }
 
+__global__ void cast_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float* __restrict__ out) {
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (int64_t)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const uint2 v = *reinterpret_cast<const uint2*>(x + i);
+      *reinterpret_cast<float4*>(out + i) = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                                                        __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+    } else {
+      for (int64_t j = i; j < n; ++j)
+        out[j] = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(x)[j] << 16);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int stac_layernorm(const float* x, int64_t rows, int64_t dim, const float* gamma,
@@ -233,6 +247,13 @@ extern "C" int stac_kv_lengths(const float* wav_len, int64_t batch, int64_t t2, 
   STAC_REQUIRE(out && batch > 0 && batch < (1 << 30) && t2 > 0 && t2 < (1 << 24));
   kv_lengths_kernel<<<(unsigned)ceil_div64(batch, 128), 128, 0, as_stream(stream)>>>(wav_len, (int)batch, (int)t2,
                                                                                     round_rule, out);
+  STAC_LAUNCH_CHECK();
+}
+
+extern "C" int stac_cast_f32(const uint16_t* x, int64_t n, float* out, void* stream) {
+  STAC_REQUIRE(x && out && n > 0);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(n, 256 * 4), 148 * 32);
+  cast_f32_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), n, out);
   STAC_LAUNCH_CHECK();
 }
 

@@ -187,10 +187,11 @@ fbank_logmel_kernel(const float* __restrict__ pcm, int64_t n_samples, int64_t ro
   if (tid == 0 && vmax > -INFINITY) atomicMax(utt_max + b, float_to_ordered(vmax));
 }
 
-__global__ void topdb_norm_kernel(const float* __restrict__ x, const unsigned int* __restrict__ utt_max,
+// (x and out may be the same buffer - the in-place call of ops.fbank - so neither is __restrict__)
+__global__ void topdb_norm_kernel(const float* x, const unsigned int* __restrict__ utt_max,
                                   int per_utt, float top_db, const float* __restrict__ mean,
                                   const float* __restrict__ stdv, int64_t batch, int64_t per_row,
-                                  int n_mels, float* __restrict__ out) {
+                                  int n_mels, float* out) {
   // one CTA-row of work per (b, chunk); per_row = frames * n_mels
   const int b = blockIdx.y;
   float mx;

@@ -257,7 +257,11 @@ def conv_frontend(feats: torch.Tensor, w: FrontendWeights, out_dtype: Optional[t
     out = torch.empty(b, t2, F2 * CNN_CH, device=dev, dtype=torch.bfloat16)
     _call("stac_conv1_bf16", ptr(x0), ptr(w.w1, torch.bfloat16), ptr(w.b1), ptr(w.g1), ptr(w.be1), b, t1, ptr(out),
           stream())
-    return out if out_dtype == torch.bfloat16 else out.float()
+    if out_dtype == torch.bfloat16:
+        return out
+    out32 = torch.empty(out.shape, device=dev, dtype=torch.float32)
+    _call("stac_cast_f32", ptr(out, torch.bfloat16), out.numel(), ptr(out32), stream())
+    return out32
 
 
 # --------------------------------------------------------------------------

@@ -36,9 +36,15 @@ def _update_mem(inp_tokens, memory):
 class CachedStepMixin:
     """Mix in front of the reference's ``S2SMultiTaskTransformerBeamSearch`` (see the module docstring).  Expects the
     attributes that class has: ``model`` (this package's TransformerMultiTask), ``fc``, ``softmax``, ``temperature``,
-    ``bos_index``, ``decoder_input_tokens``, ``beam_size``; ``max_decode_steps_hint`` bounds the cache (default 512)."""
+    ``bos_index``, ``decoder_input_tokens``, ``beam_size``, ``max_decode_ratio``.  The cache is sized from the search
+    itself: SpeechBrain's searcher runs at most ``int(enc_states.shape[1] * max_decode_ratio)`` steps (the reference yamls
+    set max_decode_ratio 1.0, i.e. up to 750 steps for a 30 s segment), bounded by the positional-encoding table."""
 
-    max_decode_steps_hint = 512
+    def _cache_len(self, prefix_len: int, enc_frames: int) -> int:
+        ratio = float(getattr(self, "max_decode_ratio", 1.0))
+        want = prefix_len + int(enc_frames * ratio) + 1
+        pe = getattr(getattr(self.model, "positional_encoding", None), "pe", None)
+        return min(want, int(pe.shape[1])) if pe is not None else want
 
     def reset_mem(self, batch_size, device):
         self._kv_cache = None
@@ -60,7 +66,7 @@ class CachedStepMixin:
                 raise StacB200Error("forward_step expects encoder states inflated to one row per hypothesis")
             # the searcher inflated the encoder states x beam (repeat_interleave): keep one copy per utterance
             cache = self.model.decoder_cache(enc_states[::beam].contiguous(), rows=rows,
-                                             max_len=memory.shape[1] + int(self.max_decode_steps_hint))
+                                             max_len=self._cache_len(memory.shape[1], enc_states.shape[1]))
             self._kv_cache = cache
             for t in range(memory.shape[1]):              # the [bos, source_lang, target_lang] prefix
                 pred, attn = cache.step(memory[:, t].contiguous())

@@ -158,13 +158,14 @@ class TransformerMultiTask(nn.Module):
         b, t2, _ = src.shape
         kv_len = ops.kv_lengths(wav_len, b, t2, src.device, train_mask)
         src = src.contiguous()
+        # the reference hands fp32 CNN features to encode(); the fused pipeline hands bf16 in bf16 mode.  Anything else
+        # would need a torch cast on the product path: refuse it.
+        if src.dtype not in (torch.float32, torch.bfloat16) or (self.precision == "fp32" and src.dtype != torch.float32):
+            raise StacB200Error(f"{self.precision} encoder expects fp32 CNN features (got {src.dtype})")
         if self.precision == "bf16" and src.dtype != torch.bfloat16:
             srcb = torch.empty_like(src, dtype=torch.bfloat16)
-            src32 = src.float()
-            ops._call("stac_cast_bf16", ops.ptr(src32), src.numel(), ops.ptr(srcb), ops.stream())
+            ops._call("stac_cast_bf16", ops.ptr(src), src.numel(), ops.ptr(srcb), ops.stream())
             src = srcb
-        elif self.precision == "fp32":
-            src = src.float()
         return ops.encoder_stack(src, w, kv_len)
 
     @torch.no_grad()

@@ -139,6 +139,9 @@ class Emulator:
     def stac_cast_bf16(self, x, n, out, stream):
         _tarr(out, n, torch.bfloat16)[:] = torch.from_numpy(_arr(x, n).copy()).to(torch.bfloat16)
 
+    def stac_cast_f32(self, x, n, out, stream):
+        _arr(out, n)[:] = _tarr(x, n, torch.bfloat16).float().numpy()
+
     def stac_gemm_bf16(self, a, w, bias, resid, resid_period, act, c, c_dtype, m, n, k, vt_out, vt_cols, seq_len, t_pad,
                        stream):
         assert vt_out == 0, "emulator: no transposed V output"

@@ -1,17 +1,15 @@
 """Decoder side on the device (csrc/decoder_f32.cu + decoder.py) against the vectors the REFERENCE'S OWN decode() /
 forward() produced (tests/golden/decoder_reference.npz) and against the oracle at S-model width.  fp32 path: 1e-4.
 
-These kernels were written after the round-1 GPU budget was spent; they compile for sm_100a and their host side is
-covered on the CPU (tests/test_host_emulated.py), but they have not run on a B200 yet, so the file is not part of the
-default GPU suite: STAC_EXPERIMENTAL=1 enables it (tools/gpu_v2_check.sh)."""
+Host side also covered on the CPU (tests/test_host_emulated.py).  First run on a B200 in round 2
+(profiles/r3/r3a_first_call_verification.log); part of the default GPU suite since."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STAC_EXPERIMENTAL") != "1", reason="decoder path not yet run on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 import stac_speech_translation_b200 as sb  # noqa: E402
 from oracle import speechbrain_path as sp  # noqa: E402

@@ -37,10 +37,7 @@ def test_mha_bf16(t, lens, d, h, use_vt):
     assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
 
 
-# stac_mha_bf16_v2 (csrc/attention_tc2.cu) was written after the round-1 GPU budget was spent: it compiles for sm_100a but
-# has not run on a B200 yet, so it is not part of the default GPU suite.  STAC_EXPERIMENTAL=1 enables it
-# (tools/gpu_v2_check.sh runs it under a time limit, then times it against stac_mha_bf16).
-@pytest.mark.skipif(os.environ.get("STAC_EXPERIMENTAL") != "1", reason="attention v2 not yet run on a B200")
+# stac_mha_bf16_v2 (csrc/attention_tc2.cu): P in TMEM, one thread per query row, 128-key tiles.
 @pytest.mark.parametrize("t,lens,d,h", [(128, [128], 64, 1), (256, [256], 64, 1), (251, [251, 100, 1], 256, 4),
                                          (64, [64, 33], 128, 2), (130, [129, 130, 5], 256, 4),
                                          (751, [751, 400], 256, 4), (300, [300, 299], 512, 8),
@@ -68,9 +65,8 @@ def test_mha_bf16_v2(t, lens, d, h):
 
 # Stress shape for the finding in DESIGN.md section 9: many consecutive one-tile work items per CTA in which both query
 # groups are active (short utterances in a batch padded beyond 128 frames), which is what lets one softmax group run
-# two items ahead of the store warp.  tools/gpu_v2_check.sh runs it in its own process on the per-buffer variant build
-# and then on the default build (where a deadlock shows as the bounded mbarrier wait trapping).
-@pytest.mark.skipif(os.environ.get("STAC_EXPERIMENTAL") != "1", reason="stress test of a latent race: run explicitly")
+# two items ahead of the store warp.  The kernel now has one o_staged barrier per (Q buffer, group), which cannot run
+# ahead (tools/model_check_mha1.py); a regression would show as the bounded mbarrier wait trapping.
 def test_mha_bf16_many_short_items_per_cta():
     g = torch.Generator().manual_seed(7)
     b, t, d, h = 600, 300, 256, 4

@@ -4,10 +4,8 @@ import os
 import pytest
 import torch
 
-# Written after the round-1 GPU budget was spent: not part of the default GPU suite until it has run on a B200 once
-# (STAC_EXPERIMENTAL=1 enables it; tools/gpu_v2_check.sh runs it first thing next round).
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STAC_EXPERIMENTAL") != "1", reason="not yet run on a B200")]
+# First run on a B200 in round 2 (profiles/r3/r3a_first_call_verification.log): part of the default GPU suite since.
+pytestmark = [pytest.mark.gpu]
 
 import stac_speech_translation_b200.custom_ops  # noqa: E402,F401
 from stac_speech_translation_b200 import ingest, ops, turns  # noqa: E402

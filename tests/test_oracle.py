@@ -235,3 +235,25 @@ def test_turn_detection_oracle_matches_the_reference_function():
             turn, xt = [], []
             oturns.append_speaker_turns(c["utt"], x, 7, 8, turn, xt)
             assert turn == c["turn_rttm"] and xt == c["xt_rttm"]
+
+
+def test_ctc_peaky_fixture_decodes():
+    """tests/golden/ctc_peaky.npz (make_ctc_peaky_fixture.py): loaded into the oracle, the fitted CTC head decodes the
+    tone-coded utterances to the symbols they encode, with posteriors that are peaky (clear top-2 margins) - the
+    precondition of the >= 99.5 % greedy-sequence criterion tested on the GPU (tests/test_gpu_ctc_peaky.py)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_ctc_peaky_fixture import load_peaky, synth_tone_batches, SYMBOLS
+    from stac_speech_translation_b200.pipeline import ctc_greedy_collapse
+    from util import oracle_modules
+    omods = load_peaky(oracle_modules("S"))
+    wavs, wl, targets, _ = synth_tone_batches()[0]                  # the batch of the 24 shortest utterances
+    ref = oracle.reference_compute_forward(omods, wavs, wl)
+    t2 = ref["p_ctc"].shape[1]
+    n_valid = (torch.floor(wl * t2) + 1).clamp(max=t2).long().tolist()
+    ids = ref["p_ctc"].argmax(-1)
+    assert ctc_greedy_collapse(ids, n_valid) == targets
+    assert set(ids.unique().tolist()) <= set(SYMBOLS)
+    top2 = ref["p_ctc"].topk(2, dim=-1).values
+    margin = torch.cat([(top2[i, :n, 0] - top2[i, :n, 1]) for i, n in enumerate(n_valid)])
+    assert float((margin > 1.0).float().mean()) > 0.9          # peaky: nine frames in ten decided by > 1 nat

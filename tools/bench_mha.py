@@ -17,7 +17,7 @@ for path in sys.argv[1:]:
     torch.cuda.synchronize()
     assert rc == 0, rc
     calls = {"stac_mha_bf16": call}
-    if hasattr(lib, "stac_mha_bf16_v2") and os.environ.get("STAC_EXPERIMENTAL") == "1":
+    if hasattr(lib, "stac_mha_bf16_v2"):
         f2 = lib.stac_mha_bf16_v2
         f2.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p]
         calls["stac_mha_bf16_v2"] = lambda: f2(qkv.data_ptr(), kv.data_ptr(), b, t, d, h, ctx.data_ptr(), st)

@@ -13,16 +13,17 @@ A random scheduler interleaves the roles.  Checked on every run:
   * no deadlock;
   * every wait passes on exactly the completion it was written for;
   * data hazards: a K/V stage or Q buffer is refilled only after every MMA reading it has completed, and consumed only
-    with the fill it expects; S is read by the softmax only when that step's Q.K^T has completed, P.V issues only on that
-    step's P, the O rescale sees every earlier P.V completed; an O buffer / 1/l slot is reused only after the epilogue
-    has drained its previous use, and the epilogue reads a complete item.
+    with the fill it expects; S is read by the softmax only when that step's Q.K^T has completed (scores are double-
+    buffered per group: S runs up to two tiles ahead of P.V), P.V issues only on that step's P and executes before the
+    S that reuses its buffer, the occasional O rescale (which waits on a barrier the other steps never look at) sees
+    every earlier P.V completed; O / the 1/l slot are reused only after the epilogue has drained the previous item, and
+    the epilogue reads a complete item.
 Usage:  python tools/model_check_mha2.py [runs] [seed]      (also run by tests/test_host.py with a small budget)
 """
 import random
 import sys
 
-KV_STAGES = 3
-SEQUENCE = False        # -DMHA2_SEQUENCE: the two softmax groups take strict turns in their exponential phase
+KV_STAGES = 4
 
 
 class Hazard(AssertionError):
@@ -61,13 +62,12 @@ class Sim:
         self.q_empty = [[MBar(f"q_empty[{b}][{w}]", 1) for w in range(2)] for b in range(2)]
         self.kv_full = [MBar(f"kv_full[{s}]", 1) for s in range(KV_STAGES)]
         self.kv_empty = [MBar(f"kv_empty[{s}]", 2) for s in range(KV_STAGES)]
-        self.s_full = [MBar(f"s_full[{w}]", 1) for w in range(2)]
-        self.p_full = [MBar(f"p_full[{w}]", 4) for w in range(2)]
-        self.o_full = [[MBar(f"o_full[{w}][{o}]", 1) for o in range(2)] for w in range(2)]
-        self.l_full = [[MBar(f"l_full[{w}][{o}]", 4) for o in range(2)] for w in range(2)]
-        self.o_free = [[MBar(f"o_free[{w}][{o}]", 4) for o in range(2)] for w in range(2)]
-        self.seq_done = [MBar(f"seq_done[{w}]", 4) for w in range(2)]
-        self.exp_turns = []                            # (group, sequence step) in the order the exponential phases ran
+        self.s_full = [[MBar(f"s_full[{w}][{b}]", 1) for b in range(2)] for w in range(2)]
+        self.p_full = [[MBar(f"p_full[{w}][{b}]", 4) for b in range(2)] for w in range(2)]
+        self.pv_bar = [[MBar(f"pv_done[{w}][{b}]", 1) for b in range(2)] for w in range(2)]
+        self.o_full = [MBar(f"o_full[{w}]", 1) for w in range(2)]
+        self.l_full = [MBar(f"l_full[{w}]", 4) for w in range(2)]
+        self.o_free = [MBar(f"o_free[{w}]", 4) for w in range(2)]
         # asynchronous completions: list of [delay, action]; the MMA streams are FIFOs (in-order per issuer)
         self.async_events = []
         self.mma_fifo = [[], []]
@@ -76,12 +76,13 @@ class Sim:
         self.stage_reads = [0] * KV_STAGES             # MMA blocks in flight that read the stage
         self.q_fill = [[None, None], [None, None]]     # item ordinal held by Q buffer (buf, w)
         self.q_reads = [[0, 0], [0, 0]]
-        self.s_version = [-1, -1]                      # step whose scores are complete in S_w
-        self.p_version = [-1, -1]                      # step whose probabilities are in P_w
+        self.s_version = [[-1, -1], [-1, -1]]          # step whose scores are complete in S[w][buffer]
+        self.p_version = [[-1, -1], [-1, -1]]          # step whose probabilities are in P[w][buffer]
+        self.s_reading = [[0, 0], [0, 0]]              # softmax warps currently between "S read" and "P written"
         self.pv_done = [0, 0]                          # P.V blocks completed per group
-        self.o_use = [[None, None], [None, None]]      # (use, accumulated P.V blocks) per O buffer
-        self.o_drained = [[-1, -1], [-1, -1]]          # last use the epilogue has read out
-        self.l_slot = [[None, None], [None, None]]
+        self.o_use = [None, None]                      # (use, accumulated P.V blocks) of the group's O
+        self.o_drained = [-1, -1]                      # last use the epilogue has read out
+        self.l_slot = [None, None]
         self.outputs = []
 
     # ---------------- roles ----------------
@@ -179,8 +180,9 @@ class Sim:
                     yield
                 sc = copy(pc)
                 continue
-            if sc.valid and not (w == 1 and sc.virt) and g_s < g_p + 1:
-                buf = sc.n_done & 1
+            if (sc.valid and not (w == 1 and sc.virt) and g_s < g_p + 2
+                    and (g_s == g_p or self.kv_full[sc.stage].passes(sc.phase))):
+                buf, sb = sc.n_done & 1, g_s & 1
                 yield from wait(self.kv_full[sc.stage], sc.phase, sc.tile // KV_STAGES)
                 if sc.j == 0:
                     yield from wait(self.q_full[buf][w], q_fill[buf] & 1, q_fill[buf])
@@ -191,27 +193,28 @@ class Sim:
                 last = sc.j == sc.n_kt - 1
                 self.stage_reads[sc.stage] += 1
                 self.q_reads[buf][w] += 1
-                commits = [self.s_full[w]] + ([self.q_empty[buf][w]] if last else [])
+                commits = [self.s_full[w][sb]] + ([self.q_empty[buf][w]] if last else [])
                 self.mma_fifo[w].append(("S", g_s, sc.stage, (buf, w), commits))
                 if last:
                     q_fill[buf] += 1
                 g_s += 1
                 advance(sc)
                 yield
-            ob = uses & 1
-            yield from wait(self.p_full[w], g_p & 1, g_p)
+                continue
+            sb = g_p & 1
+            yield from wait(self.p_full[w][sb], (g_p >> 1) & 1, g_p >> 1)
             if pc.j == 0:
-                yield from wait(self.o_free[w][ob], ((uses >> 1) & 1) ^ 1, uses // 2 - 1)
-                if self.o_drained[w][ob] != uses - 2 and uses >= 2:
-                    raise Hazard("first P.V of an item issued into an O buffer the epilogue has not drained")
-            if self.p_version[w] != g_p:
-                raise Hazard(f"P.V({g_p}) issued on P of step {self.p_version[w]}")
+                yield from wait(self.o_free[w], (uses & 1) ^ 1, uses - 1)
+                if uses >= 1 and self.o_drained[w] != uses - 1:
+                    raise Hazard("first P.V of an item issued into an O the epilogue has not drained")
+            if self.p_version[w][sb] != g_p:
+                raise Hazard(f"P.V({g_p}) issued on P of step {self.p_version[w][sb]}")
             if self.stage_fill[pc.stage] != pc.tile:
                 raise Hazard("P.V: stage holds another tile")
             last = pc.j == pc.n_kt - 1
             self.stage_reads[pc.stage] += 1
-            commits = [self.kv_empty[pc.stage]] + ([self.o_full[w][ob]] if last else [])
-            self.mma_fifo[w].append(("PV", g_p, pc.stage, (ob, uses, pc.j, pc.n_kt), commits))
+            commits = [self.kv_empty[pc.stage], self.pv_bar[w][sb]] + ([self.o_full[w]] if last else [])
+            self.mma_fifo[w].append(("PV", g_p, pc.stage, (uses, pc.j, pc.n_kt), commits))
             if last:
                 uses += 1
             g_p += 1
@@ -221,65 +224,55 @@ class Sim:
     def mma_complete(self, w):
         kind, g, stage, info, commits = self.mma_fifo[w].pop(0)
         self.stage_reads[stage] -= 1
+        sb = g & 1
         if kind == "S":
             buf, ww = info
             self.q_reads[buf][ww] -= 1
-            self.s_version[w] = g
-            self.p_version[w] = -1             # S(g) overwrites the columns P(g - 1) lived in
+            if self.s_reading[w][sb]:
+                raise Hazard("S overwrote a score buffer a softmax warp was still working on")
+            self.s_version[w][sb] = g
+            self.p_version[w][sb] = -1         # S(g) overwrites the columns P(g - 2) lived in
         else:
-            ob, use, j, n_kt = info
-            if self.p_version[w] != g:
+            use, j, n_kt = info
+            if self.p_version[w][sb] != g:
                 raise Hazard("P.V executed after its P was overwritten")
             self.pv_done[w] += 1
-            self.o_use[w][ob] = (use, 1) if j == 0 else (use, self.o_use[w][ob][1] + 1)
+            self.o_use[w] = (use, 1) if j == 0 else (use, self.o_use[w][1] + 1)
         for b in commits:
             b.arrive()
 
     def softmax(self, w, warp):
         """One of the four warps of softmax group w (the barrier counts are per warp)."""
-        g = uses = gs = 0
+        g = uses = 0
         for n_kt, active1 in self.items:
             if w == 1 and not active1:
-                if SEQUENCE:
-                    for _ in range(n_kt):
-                        yield from wait(self.seq_done[0], gs & 1, gs)
-                        self.seq_done[1].arrive()
-                        gs += 1
-                        yield
                 continue
-            ob = uses & 1
             for j in range(n_kt):
-                yield from wait(self.s_full[w], g & 1, g)
-                if self.s_version[w] != g:
-                    raise Hazard(f"softmax read S of step {self.s_version[w]}, expected {g}")
-                if j > 0 and self.rng.random() < 0.3:          # lazy rescale of O
+                sb = g & 1
+                yield from wait(self.s_full[w][sb], (g >> 1) & 1, g >> 1)
+                if self.s_version[w][sb] != g:
+                    raise Hazard(f"softmax read S of step {self.s_version[w][sb]}, expected {g}")
+                self.s_reading[w][sb] += 1
+                yield
+                if j > 0 and self.rng.random() < 0.3:          # lazy rescale of O: the occasional waiter of pv_done
+                    yield from wait(self.pv_bar[w][sb ^ 1], ((g - 1) >> 1) & 1, (g - 1) >> 1)
                     if self.pv_done[w] != g:
                         raise Hazard("O rescaled while an earlier P.V was still in flight")
-                yield
-                if SEQUENCE:
-                    if w == 0:
-                        if gs > 0:
-                            yield from wait(self.seq_done[1], (gs - 1) & 1, gs - 1)
-                    else:
-                        yield from wait(self.seq_done[0], gs & 1, gs)
-                    if warp == 0:
-                        self.exp_turns.append((w, gs))
                     yield
-                    self.seq_done[w].arrive()
-                    gs += 1
-                if self.s_version[w] != g:
+                if self.s_version[w][sb] != g:
                     raise Hazard("S overwritten while the softmax was still reading it")
+                self.s_reading[w][sb] -= 1
                 if warp == 0:
-                    self.p_version[w] = g
-                self.p_full[w].arrive()
+                    self.p_version[w][sb] = g
+                self.p_full[w][sb].arrive()
                 g += 1
                 yield
-            yield from wait(self.o_free[w][ob], ((uses >> 1) & 1) ^ 1, uses // 2 - 1)
-            if uses >= 2 and self.o_drained[w][ob] != uses - 2:
+            yield from wait(self.o_free[w], (uses & 1) ^ 1, uses - 1)
+            if uses >= 1 and self.o_drained[w] != uses - 1:
                 raise Hazard("1/l slot overwritten before the epilogue read it")
             if warp == 0:
-                self.l_slot[w][ob] = uses
-            self.l_full[w][ob].arrive()
+                self.l_slot[w] = uses
+            self.l_full[w].arrive()
             uses += 1
             yield
 
@@ -289,22 +282,22 @@ class Sim:
             for w in range(2):
                 if w == 1 and not active1:
                     continue
-                ob, use = uses[w] & 1, uses[w]
-                ph = (uses[w] >> 1) & 1
+                use = uses[w]
+                ph = uses[w] & 1
                 uses[w] += 1
-                yield from wait(self.l_full[w][ob], ph, use // 2)
-                if self.l_slot[w][ob] != use:
+                yield from wait(self.l_full[w], ph, use)
+                if self.l_slot[w] != use:
                     raise Hazard("epilogue read the 1/l of another item")
-                yield from wait(self.o_full[w][ob], ph, use // 2)
-                if self.o_use[w][ob] != (use, n_kt):
-                    raise Hazard(f"epilogue read O holding {self.o_use[w][ob]}, expected {(use, n_kt)}")
+                yield from wait(self.o_full[w], ph, use)
+                if self.o_use[w] != (use, n_kt):
+                    raise Hazard(f"epilogue read O holding {self.o_use[w]}, expected {(use, n_kt)}")
                 yield
-                if self.o_use[w][ob] != (use, n_kt):
+                if self.o_use[w] != (use, n_kt):
                     raise Hazard("O overwritten while the epilogue was reading it")
                 if warp == 0:
-                    self.o_drained[w][ob] = use
+                    self.o_drained[w] = use
                     self.outputs.append((n, w))
-                self.o_free[w][ob].arrive()
+                self.o_free[w].arrive()
                 yield
 
     # ---------------- scheduler ----------------
@@ -342,22 +335,20 @@ class Sim:
         want = [(n, w) for n, (_, a1) in enumerate(self.items) for w in range(2) if w == 0 or a1]
         if sorted(self.outputs) != want:
             raise Hazard("not every (item, group) tile was written exactly once")
-        if SEQUENCE and self.exp_turns != sorted(self.exp_turns, key=lambda t: (t[1], t[0])):
-            raise Hazard("the exponential phases did not run in turn order")
 
     def snapshot(self):
-        bars = [b for row in (self.q_full + self.q_empty + self.o_full + self.l_full + self.o_free) for b in row]
-        bars += self.kv_full + self.kv_empty + self.s_full + self.p_full + self.seq_done
+        bars = [b for row in (self.q_full + self.q_empty + self.s_full + self.p_full + self.pv_bar) for b in row]
+        bars += self.kv_full + self.kv_empty + self.o_full + self.l_full + self.o_free
         return tuple((b.phase, b.pending) for b in bars) + (len(self.outputs),)
 
 
-def check(runs=200, seed=0, sequence=False):
-    global SEQUENCE
-    SEQUENCE = sequence
+def check(runs=200, seed=0, kv_stages=4):
+    global KV_STAGES
+    KV_STAGES = kv_stages
     rng = random.Random(seed)
     for r in range(runs):
         n_items = rng.randint(1, 7)
-        items = [(rng.randint(1, 5), rng.random() < 0.7) for _ in range(n_items)]
+        items = [(rng.randint(1, 6), rng.random() < 0.7) for _ in range(n_items)]
         Sim(items, rng).run()
     return runs
 
@@ -365,6 +356,6 @@ def check(runs=200, seed=0, sequence=False):
 if __name__ == "__main__":
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-    sequence = "--sequence" in sys.argv
-    print("ok:", check(runs, seed, sequence), "random schedules, no deadlock, no parity aliasing, no data hazard",
-          "(softmax groups take turns: -DMHA2_SEQUENCE)" if sequence else "")
+    stages = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    print("ok:", check(runs, seed, stages), f"random schedules ({stages} K/V stages), no deadlock, no parity aliasing, "
+          "no data hazard")
