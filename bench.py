@@ -37,9 +37,22 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", default="S", choices=["S", "M", "L"])
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--seconds", type=float, default=30.0)
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="index into BASELINE.json configs: 1 = S model, 64 x 30 s (the metric's configuration, default); "
+                         "2 = M model, length-bucketed ragged batches sharded over the ranks; 3 = L model, 16 x 45-60 s "
+                         "per GPU; 4 = front-end only (Fbank + normalise + CNN) sweep over 10 k utterances of 1-30 s")
+    ap.add_argument("--size", default=None, choices=["S", "M", "L"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--seconds", type=float, default=None)
+    ap.add_argument("--min-seconds", type=float, default=None,
+                    help="ragged batch: utterance lengths uniform in [min-seconds, seconds], zero-padded to --seconds")
+    ap.add_argument("--utterances", type=int, default=None, help="configs 2 / 4: utterances in the synthetic corpus")
+    ap.add_argument("--max-batch-len", type=float, default=200.0,
+                    help="configs 2 / 4: seconds of audio per length bucket batch (DynamicBatchSampler's max_batch_len; "
+                         "200 = the reference's M-size evaluation value, ablations/run_m_and_l_size.sh:87-88)")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="configs 2 / 4: CUDA streams the batches of a rank are replayed on (a 200 s batch fills a "
+                         "fraction of the GPU: independent batches run side by side)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gather", default="bf16", choices=["ids", "bf16", "fp32"],
                     help="what travels to rank 0 besides enc_out when N > 1: greedy ids only, bf16 or fp32 posteriors")
@@ -51,7 +64,18 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances in the CPU-baseline sample")
     ap.add_argument("--trace-out", default=None, help="write the per-kernel timing table (json) here")
-    return ap.parse_args()
+    args = ap.parse_args()
+    defaults = {1: ("S", 64, 30.0, None), 2: ("M", None, 30.0, None), 3: ("L", 16, 60.0, 45.0), 4: ("S", None, 30.0, None)}
+    size, batch, seconds, min_s = defaults[args.config]
+    args.size = args.size or size
+    args.batch = args.batch or batch
+    args.seconds = args.seconds or seconds
+    args.min_seconds = args.min_seconds if args.min_seconds is not None else min_s
+    if args.config == 3 and args.cpu_batch == 8:
+        args.cpu_batch = 2                          # L model, 60 s: two utterances are ~20 s of CPU work per pass
+    if args.utterances is None:
+        args.utterances = {2: 4096, 4: 10000}.get(args.config)
+    return args
 
 
 def peaks():
@@ -136,9 +160,11 @@ def work_table(size_cfg, batch, n_samples, kv_len_sum_sq_like):
 
 # --------------------------------------------------------------------------
 def workload_config(args, t2, world):
-    cfg_idx = {("S", 64, 30.0): "configs[1]"}.get((args.size, args.batch, args.seconds), "custom")
+    cfg_idx = {("S", 64, 30.0, None): "configs[1]", ("L", 16, 60.0, 45.0): "configs[3]"}.get(
+        (args.size, args.batch, args.seconds, args.min_seconds), "custom")
+    ragged = "" if args.min_seconds is None else f" (ragged: {args.min_seconds:g}-{args.seconds:g} s, key-padding masks)"
     return {"workload": f"{cfg_idx}: STAC-ST {args.size} encoder + CTC head, batch {args.batch} x "
-                        f"{args.seconds:g} s multi-turn synthetic 16 kHz segments per GPU",
+                        f"{args.seconds:g} s multi-turn synthetic 16 kHz segments per GPU{ragged}",
             "precision": args.precision, "frames_25hz": t2,
             "l2": "per-step working set (~6 GB of activations) >> 126 MB L2, no explicit flush",
             "multi_gpu": ("whole batches per rank; enc_out + greedy ids"
@@ -236,8 +262,9 @@ def cpu_baseline(args, mods=None, wavs=None, wl=None):
 PARITY_TOL = {"bf16": 2e-2, "fp32": 1e-4}      # north_star: relative tolerance on encoder states / posteriors
 
 
-def parity_block(res, ref, n, precision):
-    """The timed batch's outputs (first n utterances) against the oracle's on the same audio and weights."""
+def parity_block(res, ref, n, precision, wl=None):
+    """The timed batch's outputs (first n utterances) against the oracle's on the same audio and weights, over the
+    frames encode() keeps (j <= floor(wav_len * T2), TransformerMultiTask.py:289-294)."""
     from stac_speech_translation_b200.pipeline import ctc_greedy_collapse
 
     def rel(a, b_):
@@ -248,16 +275,20 @@ def parity_block(res, ref, n, precision):
     ids = res["greedy"][:n].cpu().long()
     ref_ids = ref["p_ctc"].argmax(-1)
     t2 = ids.shape[1]
-    seq = ctc_greedy_collapse(ids, [t2] * n)
-    ref_seq = ctc_greedy_collapse(ref_ids, [t2] * n)
+    keep = [t2] * n if wl is None else (torch.floor(wl[:n].float() * t2) + 1).clamp(max=t2).long().tolist()
+    mask = torch.arange(t2)[None, :] < torch.tensor(keep)[:, None]
+    seq = ctc_greedy_collapse(ids, keep)
+    ref_seq = ctc_greedy_collapse(ref_ids, keep)
     top2 = ref["p_ctc"].topk(2, dim=-1).values
     margin = (top2[..., 0] - top2[..., 1])
-    flipped = ids != ref_ids
+    flipped = (ids != ref_ids) & mask
     tol = PARITY_TOL[precision]
+    enc, p = enc * mask[..., None], p * mask[..., None]
+    ref = {"enc_out": ref["enc_out"] * mask[..., None], "p_ctc": ref["p_ctc"] * mask[..., None]}
     out = {"utterances": n, "enc_rel_l2": round(rel(enc, ref["enc_out"]), 6),
            "pctc_rel_l2": round(rel(p, ref["p_ctc"]), 6),
            "pctc_max_abs": round(float((p - ref["p_ctc"]).abs().max()), 5),
-           "greedy_frame": round(float((~flipped).float().mean()), 5),
+           "greedy_frame": round(1.0 - float(flipped.sum()) / float(mask.sum()), 5),
            "greedy_seq": round(sum(a == b_ for a, b_ in zip(seq, ref_seq)) / n, 4),
            "max_margin_of_flipped_frame": round(float(margin[flipped].max()) if flipped.any() else 0.0, 5),
            "tolerance": tol,
@@ -318,6 +349,17 @@ def run_ours(args, rank, world, local_rank):
     hp = sb.HParams.for_size(args.size)
     mods = sb.build_modules(hp, precision=args.precision, device=dev)
     wavs_cpu, wl_cpu = synth.fast_synth_batch(args.batch, args.seconds, seed=1234 + rank)
+    if args.min_seconds is not None:
+        # ragged batch (configs[3]): lengths uniform in [min, seconds]; right zero padding and wav_lens = len / Lmax as
+        # the reference's PaddedBatch builds them.  The longest utterance keeps the full length.
+        g_len = torch.Generator().manual_seed(4321 + rank)
+        frac = args.min_seconds / args.seconds
+        wl_cpu = frac + (1.0 - frac) * torch.rand(args.batch, generator=g_len)
+        wl_cpu[0] = 1.0
+        n_valid = torch.round(wl_cpu * wavs_cpu.shape[1]).long()
+        for i in range(args.batch):
+            wavs_cpu[i, int(n_valid[i]):] = 0.0
+        wl_cpu = (n_valid.double() / wavs_cpu.shape[1]).float()
     # normaliser statistics: one SpeechBrain-style statistics step on a calibration slice
     calib = wavs_cpu[: min(8, args.batch), : 16000 * 4].to(dev)
     mods["normalize"].calibrate(mods["compute_features"](calib), torch.ones(calib.shape[0], device=dev))
@@ -328,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
     wavs = pinned.to(dev, non_blocking=True)
     wl = wl_cpu.to(dev)
     n_samples = wavs.shape[1]
-    audio_s = args.batch * n_samples / 16000.0
+    audio_s = float(wl_cpu.double().sum()) * n_samples / 16000.0        # valid (unpadded) audio of this rank's batch
+    padded_audio_s = args.batch * n_samples / 16000.0
     t2 = ops.frames_of(n_samples)[2]
 
     # ---- multi-GPU: results of every rank to rank 0 ----
@@ -529,6 +572,12 @@ def run_ours(args, rank, world, local_rank):
                         raise RuntimeError(f"peer gather mismatch: rank {r} {k}: {got} != {want}")
             gather_check = "checksums of every rank's last step match what rank 0 pulled"
 
+    if world > 1:                                  # valid audio differs per rank when the batch is ragged
+        t_a = torch.tensor([audio_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_a)
+        total_audio = float(t_a)
+    else:
+        total_audio = audio_s
     if rank != 0:
         return
 
@@ -550,13 +599,14 @@ def run_ours(args, rank, world, local_rank):
         cpu, ref = cpu_baseline(args, mods, wavs_cpu, wl_cpu)
         res = pipe(wavs, wl)                       # the batch every timed step ran on, same kernels
         torch.cuda.synchronize()
-        parity = parity_block(res, ref, ref["enc_out"].shape[0], args.precision)
-    total_audio = audio_s * world
+        parity = parity_block(res, ref, ref["enc_out"].shape[0], args.precision, wl_cpu)
     line = {
         "metric": METRIC, "value": round(total_audio / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": workload_config(args, t2, world),
+        "config": {**workload_config(args, t2, world),
+                   "audio": "value counts valid (unpadded) audio seconds; padded rate "
+                            f"{padded_audio_s * world / (ms * 1e-3):.0f} audio-s/s"},
         "e2e": {"value": round(total_audio / (e2e_ms * 1e-3), 1), "unit": UNIT,
                 "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(args.batch * t2 * 4),
                 "ms_per_step": round(e2e_ms, 3), "pinned_h2d_gbs": round(h2d_gbs, 1),
@@ -571,6 +621,312 @@ def run_ours(args, rank, world, local_rank):
         "parity": parity,
         "kernels": [{k: v for k, v in r.items() if k != "work_per_launch"} for r in table[:8]],
     }
+    emit(line)
+    if parity is not None and not parity["ok"]:
+        print(f"bench: PARITY FAILURE against the oracle: {parity}", file=sys.stderr)
+        sys.exit(3)
+
+
+# --------------------------------------------------------------------------
+# configs[2] / configs[4]: a corpus of length-bucketed ragged batches, whole batches sharded over the ranks
+# --------------------------------------------------------------------------
+def run_bucketed(args, rank, world, local_rank):
+    """configs[2]: M model over `--utterances` utterances with LogNormal(median 8 s, sigma 0.7) durations clipped to
+    [1, 30] s; configs[4]: front-end only (Fbank + normalise + ConvolutionFrontEnd) over 10 k utterances of 1-30 s.
+    Batches are built the way the reference's DynamicBatchSampler set-up builds them (synth.bucket_batches,
+    /root/reference/stac-st/dataio_and_utils.py:203-231) and WHOLE batches go to ranks longest-processing-time-first
+    (distributed.plan): outputs depend on batch membership (wav_lens = len / Lmax, reflect padding at the batch edge), so
+    a batch is never split.  A step = one pass over the corpus: every rank replays one CUDA graph per batch of its share,
+    round-robin over `--streams` streams, then the ranks' results (encoder states fp32, greedy ids, bf16 posteriors) go
+    to rank 0 with one NCCL send per tensor and rank.  value = valid audio seconds of the corpus / max-over-ranks time:
+    strong scaling (the corpus is fixed, N ranks share it)."""
+    import numpy as np
+    import torch.distributed as dist
+    import stac_speech_translation_b200 as sb
+    from stac_speech_translation_b200 import distributed, ops, synth
+
+    frontend_only = args.config == 4
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    hp = sb.HParams.for_size(args.size)
+    mods = sb.build_modules(hp, precision=args.precision, device=dev)
+    dur = (synth.uniform_durations(args.utterances, 1234) if frontend_only
+           else synth.lognormal_durations(args.utterances, 1234))
+    bucketed, per_rank = distributed.plan(dur, world, max_batch_len=args.max_batch_len)
+    tmpl = synth.fast_synth_batch(8, 30.0, seed=1234)[0]
+    calib = tmpl[:, : 16000 * 4].to(dev)
+    mods["normalize"].calibrate(mods["compute_features"](calib), torch.ones(calib.shape[0], device=dev))
+    tmpl_dev = tmpl.to(dev)
+    d = hp.d_model
+    my_ids = list(per_rank[rank])
+
+    # ---- this rank's batches, PCM resident on the device (and a pinned host copy for the end-to-end leg) ----
+    batches, frames_total = [], 0
+    for bid in my_ids:
+        idx = bucketed.batches[bid]
+        n = [max(640, int(round(float(dur[i]) * 16000))) for i in idx]
+        lmax = (max(n) + 3) // 4 * 4
+        wav = torch.zeros(len(idx), lmax, device=dev)
+        for k, (i, ni) in enumerate(zip(idx, n)):
+            off = (i * 7919) % (tmpl_dev.shape[1] - ni + 1)
+            wav[k, :ni] = tmpl_dev[i % 8, off:off + ni] * (0.5 + (i % 10) / 10.0)
+        wl = torch.tensor([ni / lmax for ni in n], dtype=torch.float64).float().to(dev)
+        t2 = ops.frames_of(lmax)[2]
+        batches.append({"id": bid, "wavs": wav, "wl": wl, "n": len(idx), "lmax": lmax, "t2": t2, "row0": frames_total,
+                        "valid_s": sum(n) / 16000.0, "padded_s": len(idx) * lmax / 16000.0})
+        frames_total += len(idx) * t2
+    valid_s = sum(b["valid_s"] for b in batches)
+    padded_s = sum(b["padded_s"] for b in batches)
+
+    # ---- result buffers of the rank: every batch's kernels write their slice; ONE transfer per tensor to rank 0 ----
+    pdt = torch.float32 if world == 1 else torch.bfloat16
+    flat = {}
+    if not frontend_only:
+        flat = {"enc_out": torch.empty(max(frames_total, 1), d, device=dev),
+                "greedy": torch.empty(max(frames_total, 1), device=dev, dtype=torch.int32)}
+        if args.gather != "ids":
+            flat["p_ctc"] = torch.empty(max(frames_total, 1), VOCAB, device=dev, dtype=pdt)
+    rank_frames = [0] * world
+    if world > 1:
+        t_f = torch.zeros(world, device=dev, dtype=torch.int64)
+        t_f[rank] = frames_total
+        dist.all_reduce(t_f)
+        rank_frames = t_f.tolist()
+    gathered = None
+    if world > 1 and rank == 0 and not frontend_only:
+        gathered = {r: {k: torch.empty((max(rank_frames[r], 1),) + tuple(v.shape[1:]), device=dev, dtype=v.dtype)
+                        for k, v in flat.items()} for r in range(1, world)}
+
+    pipe = sb.EncoderPipeline(mods, posterior_dtype=pdt)
+
+    def outputs_of(b):
+        if frontend_only:
+            return {}
+        r0, r1 = b["row0"], b["row0"] + b["n"] * b["t2"]
+        out = {"enc_out": flat["enc_out"][r0:r1].view(b["n"], b["t2"], d),
+               "greedy": flat["greedy"][r0:r1].view(b["n"], b["t2"])}
+        if "p_ctc" in flat:
+            out["p_ctc"] = flat["p_ctc"][r0:r1].view(b["n"], b["t2"], VOCAB)
+        return out
+
+    call_kw = {"stop_after": "cnn"} if frontend_only else {}
+
+    # ---- untimed traced pass (eager): per-kernel table with the work of every batch shape ----
+    pk = peaks()
+    work_sum, launches_sum = {}, {}
+    ops.TRACE = []
+    for b in batches:
+        kv = ops.kv_lengths(b["wl"], b["n"], b["t2"], dev, False).long()
+        wt = work_table(sb.MODEL_SIZES[args.size], b["n"], b["lmax"], int((kv * b["t2"]).sum()))
+        for k, (bound, work, n_l) in wt.items():
+            work_sum[k] = (bound, work_sum.get(k, (bound, 0))[1] + work * n_l)
+        pipe(b["wavs"], b["wl"], outputs=outputs_of(b), **call_kw)
+    torch.cuda.synchronize()
+    trace, ops.TRACE = ops.TRACE, None
+    per = {}
+    for name, label, e0, e1 in trace:
+        k = ops.trace_key(name, label)
+        t_, n_ = per.get(k, (0.0, 0))
+        per[k] = (t_ + e0.elapsed_time(e1), n_ + 1)
+    table = []
+    for k, (t_, n_) in sorted(per.items(), key=lambda kv_: -kv_[1][0]):
+        bound, work = work_sum.get(k, ("hbm", 0))
+        ach = work / (t_ * 1e-3) / (1e12 if bound == "tensor" else 1e9) if t_ > 0 else 0.0
+        peak = pk["tflops_sustained"] if bound == "tensor" else pk["hbm_gbs"]
+        table.append({"kernel": k, "launches_per_step": n_, "ms_per_step": round(t_, 4), "bound": bound,
+                      "achieved": round(ach, 1), "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                      "frac": round(ach / peak, 4), "work_per_step": work})
+
+    # ---- one CUDA graph per batch; graphs replayed on the same stream share that stream's memory pool ----
+    n_streams = max(1, min(args.streams, max(1, len(batches))))
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+    pools = [torch.cuda.graph_pool_handle() for _ in range(n_streams)]
+    graphs = []
+    for i, b in enumerate(batches):
+        graphs.append(sb.GraphedPipeline(pipe, b["wavs"], b["wl"], warmup=1, pool=pools[i % n_streams],
+                                         outputs=outputs_of(b), **call_kw))
+    torch.cuda.synchronize()
+    main = torch.cuda.current_stream()
+    done = [torch.cuda.Event() for _ in range(n_streams)]
+
+    def gather():
+        if world == 1 or frontend_only:
+            return
+        if rank == 0:
+            ops_ = [dist.P2POp(dist.irecv, gathered[r][k], r) for r in range(1, world) for k in flat if rank_frames[r]]
+        else:
+            ops_ = [dist.P2POp(dist.isend, flat[k], 0) for k in flat] if frames_total else []
+        for wk in (dist.batch_isend_irecv(ops_) if ops_ else []):
+            wk.wait()
+
+    def step(h2d=None):
+        start = torch.cuda.Event()
+        start.record(main)
+        for i, g in enumerate(graphs):
+            st = streams[i % n_streams]
+            if i < n_streams:
+                st.wait_event(start)
+            with torch.cuda.stream(st):
+                if h2d is not None:
+                    g.wavs.copy_(h2d[i], non_blocking=True)
+                g.graph.replay()
+        for k, st in enumerate(streams):
+            done[k].record(st)
+            main.wait_event(done[k])
+        gather()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = sum(r["launches_per_step"] for r in table) * args.steps
+
+    # ---- end to end: pinned host PCM of every batch in, greedy ids (front-end sweep: nothing) out, wall clock ----
+    pinned = [b["wavs"].cpu().pin_memory() for b in batches]
+    ids_host = None if frontend_only else torch.empty(max(sum(rank_frames) if world > 1 else frames_total, 1),
+                                                       dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        step(h2d=pinned)
+        if ids_host is not None and rank == 0:
+            ids_host[:frames_total].copy_(flat["greedy"][:frames_total], non_blocking=True)
+            off = frames_total
+            for r in range(1, world):
+                ids_host[off:off + rank_frames[r]].copy_(gathered[r]["greedy"][:rank_frames[r]], non_blocking=True)
+                off += rank_frames[r]
+        torch.cuda.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    tot = torch.tensor([valid_s, padded_s, float(len(batches))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot)
+    # shard/gather check: what rank 0 holds of every other rank equals what that rank produced (checksums)
+    gather_check = None
+    if world > 1 and not frontend_only:
+        mine = {k: float(v[:frames_total].double().sum()) for k, v in flat.items()} if rank else None
+        sums = [None] * world
+        dist.all_gather_object(sums, mine)
+        if rank == 0:
+            for r in range(1, world):
+                for k, want in sums[r].items():
+                    got = float(gathered[r][k][:rank_frames[r]].double().sum())
+                    if abs(got - want) > 1e-6 * max(1.0, abs(want)):
+                        raise RuntimeError(f"gather mismatch: rank {r} {k}: {got} != {want}")
+            gather_check = "checksums of every rank's results match what rank 0 received"
+    if rank != 0:
+        return
+    total_valid, total_padded, n_batches = [float(x) for x in tot]
+
+    # ---- parity on a bounded sample: the oracle (product's weights) on this rank's shortest batch ----
+    cpu, parity = None, None
+    if not args.no_cpu_baseline and batches:
+        b = min(batches, key=lambda x: x["padded_s"])
+        keep = min(b["n"], args.cpu_batch)
+        sub = dict(args=args)
+        import oracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        omods = oracle.build_reference_modules(args.size)
+        for k in ("CNN", "Transformer", "ctc_lin"):
+            omods[k].load_state_dict({k_: v.detach().float().cpu() for k_, v in mods[k].state_dict().items()}, strict=True)
+        omods["normalize"]._load_statistics_dict({k_: (v.detach().float().cpu() if torch.is_tensor(v) else v)
+                                                  for k_, v in mods["normalize"]._statistics_dict().items()})
+        omods["normalize"].eval()
+        w_cpu, wl_c = b["wavs"].cpu(), b["wl"].cpu()
+        t0 = time.perf_counter()
+        ref = oracle.reference_compute_forward(omods, w_cpu, wl_c, stages="frontend" if frontend_only else None)
+        dt = time.perf_counter() - t0
+        cpu = {"value": round(b["valid_s"] / dt, 2), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"one pass over the shortest batch of the corpus ({b['n']} utterances, {b['padded_s']:.0f} s "
+                         f"padded), torch fp32, {cores} threads"}
+        res = pipe(b["wavs"], b["wl"], **call_kw)
+        torch.cuda.synchronize()
+        if frontend_only:
+            a_, r_ = res["cnn"].float().cpu().reshape(ref["cnn"].shape[0], ref["cnn"].shape[1], -1), \
+                ref["cnn"].reshape(ref["cnn"].shape[0], ref["cnn"].shape[1], -1)
+            err = float((a_ - r_).double().norm() / r_.double().norm())
+            parity = {"utterances": b["n"], "cnn_rel_l2": round(err, 6), "tolerance": PARITY_TOL[args.precision],
+                      "ok": bool(err <= PARITY_TOL[args.precision])}
+        else:
+            parity = parity_block(res, ref, b["n"], args.precision, wl_c)
+
+    top = table[0]
+    peak = pk["tflops_sustained"] if top["bound"] == "tensor" else pk["hbm_gbs"]
+    roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": peak,
+                "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                "peak_source": pk["source"] + (" (sustained bf16 GEMM)" if top["bound"] == "tensor" else " (copy)"),
+                "algorithmic_per_step": top["work_per_step"], "ms_per_step": top["ms_per_step"],
+                "how": "CUDA events around every launch of an untimed eager pass over rank 0's batches: sum of the "
+                       "algorithmic work of every batch shape / sum of the launch durations"}
+    cfg = {"workload": (f"configs[{args.config}]: " + (
+               f"front-end only (Fbank + InputNormalization + ConvolutionFrontEnd), {args.utterances} utterances "
+               f"U[1, 30] s" if frontend_only else
+               f"STAC-ST {args.size} encoder + CTC head, {args.utterances} utterances LogNormal(median 8 s, sigma 0.7) "
+               f"clipped to [1, 30] s")
+               + f", length-bucketed batches of <= {args.max_batch_len:g} s (DynamicBatchSampler rule), whole batches "
+                 f"sharded over {world} rank(s) longest-processing-time-first"),
+           "precision": args.precision, "batches": int(n_batches), "streams": n_streams,
+           "valid_audio_s": round(total_valid, 1), "padded_audio_s": round(total_padded, 1),
+           "l2": "every batch has its own buffers (corpus PCM resident: no reuse between steps of the same data in L2 "
+                 "beyond what a real pass over a corpus has)",
+           "multi_gpu": "single GPU" if world == 1 else
+                        ("enc_out fp32 + greedy ids" + ("" if args.gather == "ids" else " + bf16 posteriors")
+                         + " of every rank to rank 0, one NCCL send per tensor and rank, inside the timed region")}
+    line = {
+        "metric": METRIC, "value": round(total_valid / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,
+        "e2e": {"value": round(total_valid / (e2e_ms * 1e-3), 1), "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(p.numel() for p in pinned) * 4),
+                "d2h_bytes_per_step": 0 if ids_host is None else int(ids_host.numel() * 4),
+                "ms_per_step": round(e2e_ms, 3),
+                "note": "pinned fp32 PCM of every batch copied in on the batch's stream before its graph replay; greedy "
+                        "ids of the whole corpus read back by rank 0; wall clock, max over ranks"},
+        "gpu_launches": launches,
+        **({"gather_check": gather_check} if gather_check else {}),
+        "clocks": clocks.summary(), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "kernels": [{k: v for k, v in r.items() if k != "work_per_step"} for r in table[:10]],
+    }
+    if frontend_only:
+        def agg(keys):
+            t_ = sum(per[k][0] for k in keys if k in per)
+            w_ = sum(work_sum[k][1] for k in keys if k in per)
+            return t_, w_
+        t_f, w_f = agg(["stac_fbank_logmel_tc", "stac_fbank_logmel", "stac_fbank_topdb_norm"])
+        t_c, w_c = agg(["stac_conv1_bf16"])
+        line["frontend_fractions"] = {
+            "fbank_norm_hbm_frac": round(w_f / (t_f * 1e-3) / 1e9 / pk["hbm_gbs"], 4) if t_f else None,
+            "conv1_tensor_frac": round(w_c / (t_c * 1e-3) / 1e12 / pk["tflops_sustained"], 4) if t_c else None,
+            "note": "a2-a3 are HBM-bound (algorithmic bytes 4 L + 4*80 T per utterance), a4's conv1 is tensor-bound "
+                    "(SURVEY.md 8d): reported separately"}
     emit(line)
     if parity is not None and not parity["ok"]:
         print(f"bench: PARITY FAILURE against the oracle: {parity}", file=sys.stderr)
@@ -611,7 +967,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.config in (2, 4):
+            run_bucketed(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

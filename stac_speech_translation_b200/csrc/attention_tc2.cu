@@ -53,6 +53,12 @@ constexpr int kRegsSoftmax = 176, kRegsOther = 80;     // 256 * 176 + 256 * 80 =
 #ifndef MHA2_POLY
 #define MHA2_POLY 0
 #endif
+#ifndef MHA2_OFFSET
+#define MHA2_OFFSET 0
+#endif
+#ifndef MHA2_MAXCHAINS
+#define MHA2_MAXCHAINS 2
+#endif
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int kOffQ = 0;                               // [2 bufs][2 groups] x 16 KB
 constexpr int kOffOut = 65536;                         // [2 groups] x 16 KB: normalised bf16 O tile for the TMA store
@@ -448,6 +454,16 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint32_t g = 0;                                // per-group step index
     uint32_t uses = 0;
     int ordinal = 0;
+#if MHA2_OFFSET > 0
+    // Timing experiment: group 1 starts MHA2_OFFSET clocks late, so that the two groups' exponential phases (which
+    // otherwise run in lockstep: same start, same step time) overlap each other's barrier / load / maximum phases.
+    if (w == 1) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < MHA2_OFFSET) {}
+    }
+#endif
+    uint32_t v[kKTile / 32][32];
+    bool have_scores = false;                      // (MHA2_EARLY_LD) this step's score load was issued a step early
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
       const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
       if (w == 1 && !it.active1) continue;
@@ -461,13 +477,15 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int sb = g & 1;
         const uint32_t s_tmem = tmem_base + (w * 2 + sb) * kSCols + lane_off;
         if (tr) TRACE2(2 + w, 0, g);
-        mbar_wait(s_full(w, sb), (g >> 1) & 1);
-        if (tr) TRACE2(2 + w, 1, g);
-        tc_fence_after();
-        uint32_t v[kKTile / 32][32];
+        if (!have_scores) {
+          mbar_wait(s_full(w, sb), (g >> 1) & 1);
+          if (tr) TRACE2(2 + w, 1, g);
+          tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < kKTile / 32; ++c) tmem_ld32(s_tmem + c * 32, v[c]);
+          for (int c = 0; c < kKTile / 32; ++c) tmem_ld32(s_tmem + c * 32, v[c]);
+        }
         tmem_ld_wait();
+        have_scores = false;
         if (tr) TRACE2(2 + w, 2, g);
         const int valid = it.n_keys - j * kKTile;      // my columns < valid are real keys
         if (valid < kKTile) {
@@ -476,6 +494,17 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int c = 0; c < kKTile; ++c)
             if (c >= valid) v[c >> 5][c & 31] = 0xff800000u;        // -inf: exp2 gives exactly 0
         }
+#if MHA2_MAXCHAINS == 4
+        float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kKTile; c += 8) {
+          tm0 = max3(tm0, __uint_as_float(v[c >> 5][c & 31]), __uint_as_float(v[c >> 5][(c & 31) + 1]));
+          tm1 = max3(tm1, __uint_as_float(v[c >> 5][(c & 31) + 2]), __uint_as_float(v[c >> 5][(c & 31) + 3]));
+          tm2 = max3(tm2, __uint_as_float(v[c >> 5][(c & 31) + 4]), __uint_as_float(v[c >> 5][(c & 31) + 5]));
+          tm3 = max3(tm3, __uint_as_float(v[c >> 5][(c & 31) + 6]), __uint_as_float(v[c >> 5][(c & 31) + 7]));
+        }
+        const float tile_max = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3));
+#else
         float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
         for (int c = 0; c < kKTile; c += 4) {
@@ -483,6 +512,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           tm1 = max3(tm1, __uint_as_float(v[c >> 5][(c & 31) + 2]), __uint_as_float(v[c >> 5][(c & 31) + 3]));
         }
         const float tile_max = fmaxf(tm0, tm1);
+#endif
         if (j == 0) {
           m_ref = tile_max;                            // O is overwritten by the first P.V of the item
         } else {
@@ -535,6 +565,19 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         l_run += (l0.x + l0.y) + (l1.x + l1.y);
         if (tr && l_run != 123.f) TRACE2(2 + w, 4, g);
+#ifdef MHA2_EARLY_LD
+        // The next step's scores (same item) are normally complete by now - S runs two tiles ahead: start their load
+        // before waiting for the P stores, so that its latency overlaps the store wait, the fence and the arrive.
+        // Never by blocking: the issuer may need this step's p_full before it can issue S(g + 1).
+        if (j + 1 < it.n_kt &&
+            __all_sync(0xffffffffu, mbar_test_wait(s_full(w, sb ^ 1), ((g + 1) >> 1) & 1))) {
+          tc_fence_after();
+          const uint32_t s_next = tmem_base + (w * 2 + (sb ^ 1)) * kSCols + lane_off;
+#pragma unroll
+          for (int c = 0; c < kKTile / 32; ++c) tmem_ld32(s_next + c * 32, v[c]);
+          have_scores = true;
+        }
+#endif
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

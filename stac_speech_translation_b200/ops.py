@@ -24,8 +24,9 @@ CNN_CH = 256
 F1, F2 = 40, 20
 PRECISIONS = ("fp32", "bf16")
 FUSED_FFN = True       # tests flip this to compare against the two-GEMM path
-# Experimental second attention kernel (csrc/attention_tc2.cu).  Off unless asked for: it has not run on a B200 yet.
-MHA_V2 = os.environ.get("STAC_MHA_V2", "0") == "1"
+# Attention kernel of the bf16 path: csrc/attention_tc2.cu (P in TMEM, double-buffered scores; 69.7 us against 87 us at
+# the benchmark shape).  STAC_MHA_V2=0 selects the first kernel (csrc/attention_tc.cu) for comparisons.
+MHA_V2 = os.environ.get("STAC_MHA_V2", "1") == "1"
 
 # Optional launch tracing: bench.py sets TRACE to a list to get (kernel, label, start_event, end_event)
 # per launch; LAUNCHES counts kernel launches either way.
@@ -250,6 +251,9 @@ def conv_frontend(feats: torch.Tensor, w: FrontendWeights, out_dtype: Optional[t
         _call("stac_group_ln_lrelu", ptr(pre), b * t2, F2 * CNN_CH, ptr(w.g1), ptr(w.be1), 1e-5, 0.01, ptr(out),
               DT_BF16 if out_dtype == torch.bfloat16 else DT_F32, stream())
         return out
+    # (conv0 -> conv1 in rounds of a few utterances through one reused, L2-sized buffer was measured: slower at every
+    # round size - 1.52 ms at 32 utterances per round to 3.9 ms at 1, against 1.56 ms for the whole batch,
+    # profiles/r3/r3c_conv_chunks.log - both kernels lose more to short launches than the L2 hits give back)
     n_pad = lib().stac_conv0_padded_elems(b, t1)
     x0 = torch.empty(n_pad, device=dev, dtype=torch.bfloat16)
     _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),

@@ -168,7 +168,7 @@ class GraphedPipeline:
     static tensors on every replay."""
 
     def __init__(self, pipe: "EncoderPipeline", wavs: torch.Tensor, wav_lens: Optional[torch.Tensor], warmup: int = 2,
-                 **call_kwargs):
+                 pool=None, **call_kwargs):
         self.wavs = wavs
         self.wav_lens = wav_lens
         side = torch.cuda.Stream(device=wavs.device)
@@ -178,7 +178,9 @@ class GraphedPipeline:
                 pipe(self.wavs, self.wav_lens, **call_kwargs)
         torch.cuda.current_stream(wavs.device).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # pool: graphs that are only ever replayed one after the other on one stream may share a memory pool
+        # (torch.cuda.graph_pool_handle()); results that must outlive the next replay go to caller-owned `outputs`
+        with torch.cuda.graph(self.graph, pool=pool):
             self.out = pipe(self.wavs, self.wav_lens, **call_kwargs)
 
     def __call__(self, wavs: Optional[torch.Tensor] = None):

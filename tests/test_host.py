@@ -380,3 +380,34 @@ def test_custom_ops_survive_torch_export():
     targets = [str(n.target) for n in ep.graph.nodes if n.op == "call_function"]
     assert [t for t in targets if t.startswith("stac_b200.")] == [
         "stac_b200.input_norm.default", "stac_b200.linear.default", "stac_b200.log_softmax_greedy.default"]
+
+
+def test_bench_configs_and_parity_block():
+    """bench.py: --config N selects BASELINE.json configs[N] (model size, batch shape, raggedness), and the in-run parity
+    block compares only the frames encode() keeps and fails above the north-star tolerance."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    old = sys.argv
+    try:
+        want = {1: ("S", 64, 30.0, None, None), 2: ("M", None, 30.0, None, 4096), 3: ("L", 16, 60.0, 45.0, None),
+                4: ("S", None, 30.0, None, 10000)}
+        for cfg, (size, batch, secs, min_s, n_utt) in want.items():
+            sys.argv = ["bench.py", "--config", str(cfg)]
+            a = bench.parse_args()
+            assert (a.size, a.batch, a.seconds, a.min_seconds, a.utterances) == (size, batch, secs, min_s, n_utt)
+    finally:
+        sys.argv = old
+    g = torch.Generator().manual_seed(0)
+    p = torch.log_softmax(torch.randn(2, 10, 50, generator=g) * 4, -1)
+    enc = torch.randn(2, 10, 8, generator=g)
+    ref = {"enc_out": enc, "p_ctc": p}
+    wl = torch.tensor([1.0, 0.55])                       # second utterance keeps floor(0.55 * 10) + 1 = 6 frames
+    res = {"enc_out": enc.clone(), "p_ctc": p.clone(), "greedy": p.argmax(-1).int()}
+    res["enc_out"][1, 6:] += 100.0                       # garbage in the padded frames must not count
+    res["greedy"][1, 6:] = 0
+    out = bench.parity_block(res, ref, 2, "bf16", wl)
+    assert out["ok"] and out["enc_rel_l2"] == 0 and out["greedy_frame"] == 1.0 and out["greedy_seq"] == 1.0
+    res["enc_out"][0] *= 1.05
+    assert not bench.parity_block(res, ref, 2, "bf16", wl)["ok"]
