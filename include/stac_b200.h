@@ -106,6 +106,17 @@ int stac_conv0_ln_lrelu(const float* feats /*[B,T,80]*/, const float* w0, const 
                         const float* ln_g, const float* ln_b, int64_t batch, int64_t frames,
                         void* out, int out_mode, void* stream);
 
+/* a2 tail + a3 + a4 block 0 in one kernel (bf16 mode, the fused pipeline): the same block-0 kernel reading the RAW dB
+ *        features of stac_fbank_logmel(_tc) and applying, in its loader, the top-dB clamp against the utterance maximum
+ *        (utt_max_ordered as written by the Fbank kernel; per_utterance = 0: one maximum for the batch) and
+ *        (x - mean) * (1 / std) (mean / std [80], both NULL: clamp only; one fp32 ulp from stac_fbank_topdb_norm's
+ *        quotient), so the normalised [B,T,80] tensor is never written.  Replaces the tail of compute_features (inference.py:95),
+ *        modules.normalize (:96) and block 0 of modules.CNN (:99).  out: the padded bf16 layout above. */
+int stac_conv0_topdb_norm_bf16(const float* logmel_db, const uint32_t* utt_max_ordered, int per_utterance,
+                               float top_db, const float* mean, const float* std, const float* w0,
+                               const float* b0, const float* ln_g, const float* ln_b, int64_t batch,
+                               int64_t frames, uint16_t* out, void* stream);
+
 /* Block 1 convolution only (pre-LayerNorm), fp32 CUDA-core implicit GEMM:
  *   x [B,T1,40,256] fp32, w1 packed [256(out)][9 = kf*3+kt][256(in)], out [B,T2,20,256]. */
 int stac_conv1_f32(const float* x, const float* w1, const float* b1, int64_t batch, int64_t t1,
@@ -179,9 +190,9 @@ int stac_mha_f32(const float* qkv, const int32_t* kv_len, int64_t batch, int64_t
 int stac_mha_bf16(const uint16_t* qkv, const uint16_t* v_t, const int32_t* kv_len, int64_t batch,
                   int64_t seq_len, int64_t t_pad, int64_t d_model, int64_t n_head, uint16_t* ctx,
                   void* stream);
-/* EXPERIMENTAL (csrc/attention_tc2.cu; not on the default path, selected by STAC_MHA_V2=1 in ops.py; not yet run
- * on a B200): same contract as stac_mha_bf16 with v_t = NULL.  128-key tiles, one thread per query row, P kept in
- * TMEM as the A operand of P.V, epilogue warpgroup with O double-buffered in TMEM.                               */
+/* The attention kernel of the bf16 path (csrc/attention_tc2.cu; STAC_MHA_V2=0 in ops.py selects stac_mha_bf16 for
+ * comparisons): same contract as stac_mha_bf16 with v_t = NULL.  96-key tiles, one thread per query row, P kept in TMEM
+ * as the A operand of P.V, scores double-buffered per query group, O / l epilogue in its own warpgroup.            */
 int stac_mha_bf16_v2(const uint16_t* qkv, const int32_t* kv_len, int64_t batch, int64_t seq_len,
                      int64_t d_model, int64_t n_head, uint16_t* ctx, void* stream);
 
@@ -221,7 +232,7 @@ int stac_ctc_spikes(const int32_t* ids, int64_t batch, int64_t t2, int32_t turn_
  * decoder side -- building blocks of TransformerMultiTask.decode()
  *        (/root/reference/stac-st/modules/TransformerMultiTask.py:234-271) and of the decoder half of forward()
  *        (:185-209) that the encoder entry points above do not cover.  First correct path: fp32, CUDA cores, the whole
- *        prefix per call as the reference's forward_step asks (mutitask_decoder.py:119-128).  Not yet run on a B200.
+ *        prefix per call as the reference's forward_step asks (mutitask_decoder.py:119-128).
  * stac_embed_scale_pe: out[row] = emb[tokens[row]] * scale + pe[row % seq_len]   (NormalizedEmbedding + positional
  *        encoding, :248-256); tokens int64 [rows], emb [vocab, d_model], pe [>= seq_len, d_model].
  * stac_attention_f32: softmax(q k^T + masks) v per head (head_dim 64; q is expected pre-scaled by 1/8).
@@ -250,9 +261,16 @@ int stac_pcm_i16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream)
  * training-stage statistics of InputNormalization -- replaces the per-utterance torch.mean / torch.std
  *        loop of normalize(feats, wav_lens, epoch) in train mode (/root/reference/stac-st/train_multitask.py:60-61):
  *        mean / unbiased std (floored at eps) of x[b, :round(wav_len[b] * frames), :] per utterance and bin;
- *        x [batch, frames, dim], wav_len fp32 [batch], mean / std fp32 [batch, dim].  Not yet run on a B200. */
+ *        x [batch, frames, dim], wav_len fp32 [batch], mean / std fp32 [batch, dim]. */
 int stac_utt_mean_std(const float* x, const float* wav_len, int64_t batch, int64_t frames, int64_t dim, float eps,
                       float* mean, float* std, void* stream);
+
+/* a7, bf16 mode, d_model = 256: attention output projection + residual add + the LayerNorm that follows, one kernel
+ *        (north_star's "fused LayerNorm"; replaces `src = src + dropout1(self_att(...))` and `norm2(src)` of SpeechBrain's
+ *        pre-LN TransformerEncoderLayer, reached from /root/reference/stac-st/modules/TransformerMultiTask.py:304-308):
+ *          x[m,256] (fp32, in place) += a[m,256] (bf16) . w[256,256]^T (bf16) + bias;   h[m,256] (bf16) = LayerNorm(x) */
+int stac_outproj_ln_bf16(const uint16_t* a, const uint16_t* w, const float* bias, float* x, const float* ln_g,
+                         const float* ln_b, float eps, uint16_t* h, int64_t m, void* stream);
 
 /* fp32 -> bf16 conversion (weight packing / activation hand-off) */
 int stac_cast_bf16(const float* x, int64_t n, uint16_t* out, void* stream);

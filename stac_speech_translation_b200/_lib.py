@@ -34,6 +34,7 @@ _SIGNATURES = {
     "stac_input_norm": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "stac_conv0_padded_elems": (c_int64, [c_int64, c_int64]),
     "stac_conv0_ln_lrelu": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, c_int, _P]),
+    "stac_conv0_topdb_norm_bf16": (c_int, [_P, _P, c_int, c_float, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P]),
     "stac_conv1_f32": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "stac_conv1_bf16": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P, _P]),
     "stac_group_ln_lrelu": (c_int, [_P, c_int64, c_int64, _P, _P, c_float, c_float, _P, c_int, _P]),
@@ -56,6 +57,7 @@ _SIGNATURES = {
                                    _P, _P, c_int64, _P, c_int64, _P, _P]),
     "stac_pcm_i16_to_f32": (c_int, [_P, c_int64, _P, _P]),
     "stac_utt_mean_std": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
+    "stac_outproj_ln_bf16": (c_int, [_P, _P, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "stac_cast_bf16": (c_int, [_P, c_int64, _P, _P]),
     "stac_cast_f32": (c_int, [_P, c_int64, _P, _P]),
 }

@@ -49,7 +49,8 @@ constexpr int kOffWraw = kOffOut + kOutStages * kOutBytes;       // fp32 w0 [256
 constexpr int kOffFeat = kOffWraw + (kC * 9 + kC) * 4;            // float [5][82]
 constexpr int kOffRowStat = kOffFeat + 5 * kFRow * 4;             // float2 [80]
 constexpr int kOffTab = kOffRowStat + kN * 8;                     // float [128]: wsum[9] G[81] bw[9] bsum bb
-constexpr int kOffBar = kOffTab + 128 * 4;
+constexpr int kOffNorm = kOffTab + 128 * 4;                       // float [80] mean | float [80] 1 / std | float floor_all
+constexpr int kOffBar = kOffNorm + (2 * kMel + 4) * 4;
 constexpr int kNumBars = 4 * kStages + 2 * kOutStages;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 
@@ -88,7 +89,10 @@ __host__ __device__ constexpr int stage_row(int f1) { return (f1 & 1) ? (f1 + 1)
 __global__ void __launch_bounds__(kThreads, 1)
 conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, const float* __restrict__ b0,
                 const float* __restrict__ ln_g, const float* __restrict__ ln_b, int frames, int t1_len,
-                int tiles_per_utt, int n_tiles, __nv_bfloat16* __restrict__ out) {
+                int tiles_per_utt, int n_tiles, __nv_bfloat16* __restrict__ out,
+                // fused a2 tail + a3 (nullptr utt_max: feats are already clamped and normalised)
+                const unsigned int* __restrict__ utt_max, int per_utt, float top_db, const float* __restrict__ nmean,
+                const float* __restrict__ nstd, int batch) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* sptr = smem_raw + (sbase - smem_u32(smem_raw));
@@ -116,6 +120,20 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
   if (warp == 11) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   for (int i = tid; i < kC * 9; i += kThreads) wraw[i] = __ldg(w0 + i);
   for (int i = tid; i < kC; i += kThreads) wraw[kC * 9 + i] = __ldg(b0 + i);
+  float* normtab = reinterpret_cast<float*>(sptr + kOffNorm);
+  const bool fused_norm = utt_max != nullptr;
+  if (fused_norm) {
+    for (int i = tid; i < kMel; i += kThreads) {
+      normtab[i] = nmean != nullptr ? __ldg(nmean + i) : 0.f;
+      normtab[kMel + i] = nstd != nullptr ? 1.0f / __ldg(nstd + i) : 1.f;      // reciprocal: the loader multiplies
+    }
+    if (warp == 12 && !per_utt) {               // batch-global top-dB (older SpeechBrain): one maximum for everybody
+      float mx = -INFINITY;
+      for (int i = lane; i < batch; i += 32) mx = fmaxf(mx, ordered_to_float(__ldg(utt_max + i)));
+      mx = warp_max(mx);
+      if (lane == 0) normtab[2 * kMel] = mx - top_db;
+    }
+  }
   __syncthreads();
   if (tid < kC) {
     // weight row of channel c: [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | b_hi | 1 | 1 | 0 ...] bf16, 128-byte
@@ -236,10 +254,16 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
     // input rows t = 2*t1_0 - 1 .. 2*t1_0 + 3 (reflected at the batch edges), bins -1..79 (bin -1 mirrors bin 1);
     // the loads of tile n+1 are issued while tile n is built
     float ld[5];
+    float ld_floor = 0.f;                            // (fused mode) top-dB floor of the utterance the loads belong to
     auto fetch = [&](int tile) {
       const int b = tile / tiles_per_utt;
       const int t1_0 = (tile - b * tiles_per_utt) * kTs;
       const float* frow = feats + (int64_t)b * frames * kMel;
+      // fused mode: the features are the raw dB values of the Fbank kernel; the top-dB clamp against the utterance
+      // maximum and (x - mean) / std are applied when the values are CONSUMED (one tile later: these loads are the
+      // prefetch of the next tile and must not be waited for here), with the expressions of topdb_norm_kernel
+      // (fbank.cu), so the normalised [B, T, 80] tensor never exists in HBM
+      if (fused_norm) ld_floor = per_utt ? ordered_to_float(__ldg(utt_max + b)) - top_db : normtab[2 * kMel];
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int idx = p + i * kProducerThreads;       // 0 .. 5*81-1
@@ -260,7 +284,17 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int idx = p + i * kProducerThreads;
-        if (idx < 5 * (kMel + 1)) { const int r = idx / (kMel + 1); fbuf[r * kFRow + (idx - r * (kMel + 1))] = ld[i]; }
+        if (idx < 5 * (kMel + 1)) {
+          const int r = idx / (kMel + 1), fi = idx - r * (kMel + 1);
+          float v = ld[i];
+          if (fused_norm) {
+            const int bin = fi == 0 ? 1 : fi - 1;
+            // (a true division here costs the producer warps - the critical path of this kernel - 0.1 ms per batch;
+            // the product with the reciprocal differs from topdb_norm_kernel's quotient by at most one fp32 ulp)
+            v = (fmaxf(v, ld_floor) - normtab[bin]) * normtab[kMel + bin];
+          }
+          fbuf[r * kFRow + fi] = v;
+        }
       }
       named_bar_sync(2, kProducerThreads);
       if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
@@ -387,7 +421,8 @@ int num_sms_conv0() { return stac_grid_limit(); }
 
 // called by stac_conv0_ln_lrelu (conv_frontend.cu) for out_mode == STAC_DT_BF16
 int stac_conv0_tc_launch(const float* feats, const float* w0, const float* b0, const float* ln_g, const float* ln_b,
-                         int64_t batch, int64_t frames, int t1, uint16_t* out, cudaStream_t st) {
+                         int64_t batch, int64_t frames, int t1, uint16_t* out, cudaStream_t st,
+                         const uint32_t* utt_max, int per_utt, float top_db, const float* mean, const float* std) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -399,6 +434,7 @@ int stac_conv0_tc_launch(const float* feats, const float* w0, const float* b0, c
   if (n_tiles >= (1ll << 30)) return STAC_ERR_UNSUPPORTED_SHAPE;
   const int grid = (int)std::min<int64_t>(n_tiles, num_sms_conv0());
   conv0_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(feats, w0, b0, ln_g, ln_b, (int)frames, t1, tiles_per_utt,
-                                                      (int)n_tiles, reinterpret_cast<__nv_bfloat16*>(out));
+                                                      (int)n_tiles, reinterpret_cast<__nv_bfloat16*>(out), utt_max, per_utt,
+                                                      top_db, mean, std, (int)batch);
   STAC_LAUNCH_CHECK();
 }

@@ -7,7 +7,8 @@
 #include "gemm_simt.cuh"
 
 int stac_conv0_tc_launch(const float* feats, const float* w0, const float* b0, const float* ln_g, const float* ln_b,
-                         int64_t batch, int64_t frames, int t1, uint16_t* out, cudaStream_t st);
+                         int64_t batch, int64_t frames, int t1, uint16_t* out, cudaStream_t st,
+                         const uint32_t* utt_max, int per_utt, float top_db, const float* mean, const float* std);
 
 namespace {
 
@@ -146,11 +147,23 @@ extern "C" int stac_conv0_ln_lrelu(const float* feats, const float* w0, const fl
   } else if (out_mode == STAC_DT_BF16) {
     // tensor-core version (conv0_tc.cu)
     return stac_conv0_tc_launch(feats, w0, b0, ln_g, ln_b, batch, frames, t1, reinterpret_cast<uint16_t*>(out),
-                                as_stream(stream));
+                                as_stream(stream), nullptr, 1, 0.f, nullptr, nullptr);
   } else {
     return STAC_ERR_INVALID_ARGUMENT;
   }
   STAC_LAUNCH_CHECK();
+}
+
+extern "C" int stac_conv0_topdb_norm_bf16(const float* logmel_db, const uint32_t* utt_max_ordered, int per_utterance,
+                                          float top_db, const float* mean, const float* std, const float* w0,
+                                          const float* b0, const float* ln_g, const float* ln_b, int64_t batch,
+                                          int64_t frames, uint16_t* out, void* stream) {
+  STAC_REQUIRE(logmel_db && utt_max_ordered && w0 && b0 && ln_g && ln_b && out);
+  STAC_REQUIRE((mean == nullptr) == (std == nullptr));
+  STAC_REQUIRE(batch > 0 && batch < 65536 && frames >= 3 && frames < (1 << 30));
+  const int t1 = (int)((frames - 1) / 2 + 1);
+  return stac_conv0_tc_launch(logmel_db, w0, b0, ln_g, ln_b, batch, frames, t1, out, as_stream(stream),
+                              utt_max_ordered, per_utterance, top_db, mean, std);
 }
 
 extern "C" int stac_group_ln_lrelu(const float* x, int64_t rows, int64_t dim, const float* gamma,

@@ -6,7 +6,7 @@
 // yaml transformer_multitask.yaml:208-210): actual_size = round(lengths[b] * T) in fp32, mean / std over
 // x[b, :actual_size], std floored at eps.  The running-average update of the 80 global values stays on the host.
 // HBM-bound: the features are read twice (two-pass variance, the second pass from L2), 32 B written per utterance and bin.
-// Written after the round-1 GPU budget was spent: not yet run on a B200.
+// Parity on a B200: tests/test_gpu_ytrain_norm.py.
 #include "common.cuh"
 
 namespace {

@@ -63,7 +63,7 @@ class InputNormalization(nn.Module):
     ``normalizer.ckpt`` (dict keys count/glob_mean/glob_std/spk_dict_*).  Updating the statistics
     (train mode, ``train_multitask.py:60-61``): the per-utterance mean / std over the valid frames come from
     ``stac_utt_mean_std`` on the device, the running-average update of the 80 global values is SpeechBrain's code on the
-    host copies (first device version, not yet run on a B200).  ``calibrate`` computes them once from a batch with
+    host copies.  ``calibrate`` computes them once from a batch with
     SpeechBrain's formula.
     """
 

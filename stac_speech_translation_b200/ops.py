@@ -24,6 +24,21 @@ CNN_CH = 256
 F1, F2 = 40, 20
 PRECISIONS = ("fp32", "bf16")
 FUSED_FFN = True       # tests flip this to compare against the two-GEMM path
+# Top-dB clamp + normalisation inside conv block 0's loader (stac_conv0_topdb_norm_bf16) instead of their own pass.
+# Measured on a B200 at the benchmark shape (profiles/r3/): the separate pass costs 0.050 ms, but block 0's producer
+# warps are its critical path and the three extra operations per feature cost it 0.076 ms (0.518 -> 0.594 ms; 0.615 ms
+# with a true division, 1.19 ms when the loader consumed its prefetch early).  Correct (tests/test_gpu_tc_conv.py), not
+# faster: off by default.
+FUSED_CONV0_NORM = os.environ.get("STAC_FUSED_CONV0_NORM", "0") == "1"
+# Attention output projection + residual add + LayerNorm 2 in ONE kernel (stac_outproj_ln_bf16, d_model 256): the
+# LayerNorm folded into the producer of the residual stream (north_star's "fused LayerNorm").  Correct
+# (tests/test_gpu_tc_gemm.py, path tests) and 25 % less HBM traffic than GEMM + LayerNorm, but measured NOT faster on a
+# B200: 43.4 us per layer against 27.5 + 15.1 us (profiles/r3/r3f_call10_ln_fusion_ab.log) - with whole rows per thread
+# the epilogue is one serial chain of TMEM loads, row loads and six staged TMA stores per warp and tile, and the
+# two-kernel form overlaps better.  Folding the following LayerNorm into the fused feed-forward kernel the same way was
+# measured too and cost it 36 us per launch (its epilogue is the tile boundary the tensor pipe already waits for); that
+# variant was removed.  Off by default.
+FUSED_OUTPROJ_LN = os.environ.get("STAC_FUSED_OUTPROJ_LN", "0") == "1"
 # Attention kernel of the bf16 path: csrc/attention_tc2.cu (P in TMEM, double-buffered scores; 69.7 us against 87 us at
 # the benchmark shape).  STAC_MHA_V2=0 selects the first kernel (csrc/attention_tc.cu) for comparisons.
 MHA_V2 = os.environ.get("STAC_MHA_V2", "1") == "1"
@@ -155,9 +170,22 @@ def build_fbank_tc_tables(device):
     return tab.to(device=device, dtype=torch.float32).contiguous(), tw.to(device)
 
 
+@dataclass
+class RawFeatures:
+    """Un-clamped, un-normalised dB features of the Fbank kernel + what the consumer needs to finish a2 / a3 in its own
+    loader (stac_conv0_topdb_norm_bf16): the fused pipeline never writes the normalised [B, T, 80] tensor."""
+    db: torch.Tensor                  # [B, T, 80] fp32: 10 log10(max(mel, 1e-10))
+    utt_max: torch.Tensor             # [B] int32: order-preserving key of the utterance maximum
+    top_db: float
+    per_utterance: bool
+    mean: Optional[torch.Tensor]
+    std: Optional[torch.Tensor]
+
+
 def fbank_tc(wavs: torch.Tensor, tc_tables, top_db: float = 80.0, per_utterance: bool = True,
-             mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """a2 (+a3) with the STFT on tensor cores (bf16 mode): [B, L] fp32 PCM -> [B, T, 80] fp32 features."""
+             mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None, raw: bool = False):
+    """a2 (+a3) with the STFT on tensor cores (bf16 mode): [B, L] fp32 PCM -> [B, T, 80] fp32 features, or (raw=True)
+    the RawFeatures hand-off for conv_frontend."""
     if wavs.dim() != 2:
         raise _lib.StacB200Error("Fbank expects [batch, samples] waveforms")
     wavs = wavs.contiguous()
@@ -168,19 +196,21 @@ def fbank_tc(wavs: torch.Tensor, tc_tables, top_db: float = 80.0, per_utterance:
         key = str(wavs.device)
         if key not in _FFT_TABLES:
             _FFT_TABLES[key] = build_fbank_tables(wavs.device)
-        return fbank(wavs, _FFT_TABLES[key], top_db, per_utterance, mean, std)
+        return fbank(wavs, _FFT_TABLES[key], top_db, per_utterance, mean, std, raw=raw)
     t = 1 + n // HOP
     db = torch.empty(b, t, N_MELS, device=wavs.device, dtype=torch.float32)
     umax = torch.empty(b, device=wavs.device, dtype=torch.int32)      # zeroed by the call (stream-ordered memset)
     _call("stac_fbank_logmel_tc", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tab), ptr(tw, torch.float16),
           ptr(db), ptr(umax), stream())
+    if raw:
+        return RawFeatures(db, umax, float(top_db), bool(per_utterance), mean, std)
     _call("stac_fbank_topdb_norm", ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),
           b, t, N_MELS, ptr(db), stream())
     return db
 
 
 def fbank(wavs: torch.Tensor, tables: torch.Tensor, top_db: float = 80.0, per_utterance: bool = True,
-          mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None) -> torch.Tensor:
+          mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None, raw: bool = False):
     """a2 (+a3 when mean/std are given): [B, L] fp32 PCM -> [B, T, 80] fp32 features."""
     if wavs.dim() != 2:
         raise _lib.StacB200Error("Fbank expects [batch, samples] waveforms")
@@ -191,6 +221,8 @@ def fbank(wavs: torch.Tensor, tables: torch.Tensor, top_db: float = 80.0, per_ut
     umax = torch.empty(b, device=wavs.device, dtype=torch.int32)      # zeroed by the call (stream-ordered memset)
     _call("stac_fbank_logmel", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tables), ptr(db),
                                   ptr(umax), stream())
+    if raw:
+        return RawFeatures(db, umax, float(top_db), bool(per_utterance), mean, std)
     _call("stac_fbank_topdb_norm", ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),
                                       b, t, N_MELS, ptr(db), stream())
     return db
@@ -231,8 +263,14 @@ def pack_frontend(conv0_w, conv0_b, ln0_w, ln0_b, conv1_w, conv1_b, ln1_w, ln1_b
                            f(ln0_b).flatten(), w1p, f(conv1_b), f(ln1_w).flatten(), f(ln1_b).flatten())
 
 
-def conv_frontend(feats: torch.Tensor, w: FrontendWeights, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """a4: [B, T, 80] fp32 -> [B, T2, 5120] (fp32, or bf16 when out_dtype=torch.bfloat16)."""
+def conv_frontend(feats, w: FrontendWeights, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """a4: [B, T, 80] fp32 -> [B, T2, 5120] (fp32, or bf16 when out_dtype=torch.bfloat16).  bf16 mode also takes the
+    RawFeatures of fbank(raw=True): the top-dB clamp and the normalisation then run inside block 0's loader."""
+    raw = feats if isinstance(feats, RawFeatures) else None
+    if raw is not None:
+        if w.precision != "bf16":
+            raise _lib.StacB200Error("raw feature hand-off exists in bf16 mode only")
+        feats = raw.db
     feats = feats.contiguous()
     b, t, nm = feats.shape
     if nm != N_MELS:
@@ -256,8 +294,13 @@ def conv_frontend(feats: torch.Tensor, w: FrontendWeights, out_dtype: Optional[t
     # profiles/r3/r3c_conv_chunks.log - both kernels lose more to short launches than the L2 hits give back)
     n_pad = lib().stac_conv0_padded_elems(b, t1)
     x0 = torch.empty(n_pad, device=dev, dtype=torch.bfloat16)
-    _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
-          b, t, ptr(x0), DT_BF16, stream())
+    if raw is not None:
+        _call("stac_conv0_topdb_norm_bf16", ptr(feats, torch.float32), ptr(raw.utt_max), int(raw.per_utterance),
+              raw.top_db, ptr(raw.mean), ptr(raw.std), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0), b, t, ptr(x0),
+              stream())
+    else:
+        _call("stac_conv0_ln_lrelu", ptr(feats, torch.float32), ptr(w.w0), ptr(w.b0), ptr(w.g0), ptr(w.be0),
+              b, t, ptr(x0), DT_BF16, stream())
     out = torch.empty(b, t2, F2 * CNN_CH, device=dev, dtype=torch.bfloat16)
     _call("stac_conv1_bf16", ptr(x0), ptr(w.w1, torch.bfloat16), ptr(w.b1), ptr(w.g1), ptr(w.be1), b, t1, ptr(out),
           stream())
@@ -401,6 +444,11 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
     fused_ffn = prec == "bf16" and d == 256 and d_ffn % 128 == 0 and 128 <= d_ffn <= 4096 and FUSED_FFN
     ff = None if fused_ffn else torch.empty(m, d_ffn, device=dev, dtype=act_dt)
     t_pad = (t2 + 7) // 8 * 8
+    # (enc_out: caller-provided result buffer, e.g. the slot rank 0 pulls from in the multi-GPU gather)
+    enc = enc_out if enc_out is not None else torch.empty(b, t2, d, device=dev, dtype=torch.float32)
+    if enc.shape != (b, t2, d) or enc.dtype != torch.float32:
+        raise _lib.StacB200Error("enc_out buffer must be fp32 [batch, frames, d_model]")
+    enc_bf16 = torch.empty(b, t2, d, device=dev, dtype=torch.bfloat16) if want_bf16_copy else None
     for L in w.layers:
         if prec == "fp32":
             _layernorm(x, L.ln1_g, L.ln1_b, 1e-6, out_f32=hbuf)
@@ -415,23 +463,24 @@ def encoder_stack(src: torch.Tensor, w: EncoderWeights, kv_len: torch.Tensor, wa
             else:
                 _call("stac_mha_bf16", ptr(qkv), ptr(None), ptr(kv_len, torch.int32), b, t2, t_pad, d, h, ptr(ctx),
                       stream())
-        _gemm(ctx, L.w_o, L.b_o, x, prec, resid=x, tag="out_proj")
-        if prec == "fp32":
-            _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_f32=hbuf)
+        if prec == "bf16" and d == 256 and FUSED_OUTPROJ_LN:
+            # x += ctx W_o^T + b_o and hbuf = LayerNorm2(x) in one launch: the residual stream's producer holds whole rows
+            _call("stac_outproj_ln_bf16", ptr(ctx, torch.bfloat16), ptr(L.w_o, torch.bfloat16), ptr(L.b_o), ptr(x),
+                  ptr(L.ln2_g), ptr(L.ln2_b), 1e-6, ptr(hbuf, torch.bfloat16), m, stream())
         else:
-            _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_bf16=hbuf)
+            _gemm(ctx, L.w_o, L.b_o, x, prec, resid=x, tag="out_proj")
+            if prec == "fp32":
+                _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_f32=hbuf)
+            else:
+                _layernorm(x, L.ln2_g, L.ln2_b, 1e-6, out_bf16=hbuf)
         if fused_ffn:
             _call("stac_ffn_fused_bf16", ptr(hbuf), ptr(L.w_1, torch.bfloat16), ptr(L.b_1), ptr(L.w_2, torch.bfloat16),
                   ptr(L.b_2), ptr(x), m, d, d_ffn, stream())
         else:
             _gemm(hbuf, L.w_1, L.b_1, ff, prec, act=ACT_GELU_ERF, tag="ffn1")
             _gemm(ff, L.w_2, L.b_2, x, prec, resid=x, tag="ffn2")
-    # (enc_out: caller-provided result buffer, e.g. the slot rank 0 pulls from in the multi-GPU gather)
-    enc = enc_out if enc_out is not None else torch.empty(b, t2, d, device=dev, dtype=torch.float32)
-    if enc.shape != (b, t2, d) or enc.dtype != torch.float32:
-        raise _lib.StacB200Error("enc_out buffer must be fp32 [batch, frames, d_model]")
-    enc_bf16 = torch.empty(b, t2, d, device=dev, dtype=torch.bfloat16) if want_bf16_copy else None
-    _layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=enc.view(m, d), out_bf16=None if enc_bf16 is None else enc_bf16.view(m, d))
+    _layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=enc.view(m, d),
+               out_bf16=None if enc_bf16 is None else enc_bf16.view(m, d))
     return (enc, enc_bf16) if want_bf16_copy else enc
 
 

@@ -127,7 +127,9 @@ class EncoderPipeline:
         mean, std = norm.device_stats(dev, ops.N_MELS)
         bf16 = self.precision == "bf16"
         if bf16:      # STFT as a tensor-core GEMM (fp16 operands, fp32 accumulation); fp32 mode keeps the exact FFT kernel
-            feats = ops.fbank_tc(wavs, fb.tc_tables(dev), fb.top_db, fb.top_db_per_utterance, mean, std)
+            # (ops.FUSED_CONV0_NORM: raw hand-off, the top-dB clamp + normalisation then happen in conv block 0's loader)
+            feats = ops.fbank_tc(wavs, fb.tc_tables(dev), fb.top_db, fb.top_db_per_utterance, mean, std,
+                                 raw=ops.FUSED_CONV0_NORM)
         else:
             feats = ops.fbank(wavs, fb.tables(dev), fb.top_db, fb.top_db_per_utterance, mean, std)
         src = ops.conv_frontend(feats, m["CNN"].packed(), torch.bfloat16 if bf16 else torch.float32)

@@ -14,7 +14,7 @@ called: the arithmetic runs in libstac_b200 (ops.encoder_stack).
 
 The decoder side (``decode`` :234-271, decoder half of ``forward`` :185-209) runs on the
 device too when ``num_decoder_layers > 0`` (decoder.py: parameters under ``decoder.*`` / ``custom_tgt_module.*`` with
-SpeechBrain's names, a first fp32 CUDA path that has not run on a B200 yet).  An external decoder can still be attached
+SpeechBrain's names, fp32 CUDA path, parity on a B200 in tests/test_gpu_decoder.py).  An external decoder can still be attached
 with ``attach_decoder``; it then takes precedence.
 """
 from __future__ import annotations

@@ -139,6 +139,19 @@ class Emulator:
     def stac_cast_bf16(self, x, n, out, stream):
         _tarr(out, n, torch.bfloat16)[:] = torch.from_numpy(_arr(x, n).copy()).to(torch.bfloat16)
 
+    def stac_outproj_ln_bf16(self, a, w, bias, x, ln_g, ln_b, eps, h, m, stream):
+        y = _tarr(a, m * 256, torch.bfloat16).double().view(m, 256).numpy() @ \
+            _tarr(w, 256 * 256, torch.bfloat16).double().view(256, 256).numpy().T
+        if bias:
+            y = y + _arr(bias, 256)
+        xs = _arr(x, m * 256).reshape(m, 256)
+        xn = (xs.astype(np.float64) + y).astype(np.float32)
+        xs[:] = xn
+        xd = xn.astype(np.float64)
+        mu, var = xd.mean(-1, keepdims=True), xd.var(-1, keepdims=True)
+        out = (xd - mu) / np.sqrt(var + eps) * _arr(ln_g, 256) + _arr(ln_b, 256)
+        _tarr(h, m * 256, torch.bfloat16).view(m, 256)[:] = torch.from_numpy(out).to(torch.bfloat16)
+
     def stac_cast_f32(self, x, n, out, stream):
         _arr(out, n)[:] = _tarr(x, n, torch.bfloat16).float().numpy()
 
@@ -318,6 +331,13 @@ class Emulator:
         planes = _tarr(out, batch * 4 * tp2 * 21 * 256, torch.bfloat16).view(batch, 4, tp2, 21, 256)
         for par in range(4):
             planes[:, par] = torch.from_numpy(np.ascontiguousarray(pad[:, (par >> 1)::2, (par & 1)::2])).to(torch.bfloat16)
+
+    def stac_conv0_topdb_norm_bf16(self, logmel_db, utt_max_ordered, per_utterance, top_db, mean, std, w0, b0, ln_g, ln_b,
+                                   batch, frames, out, stream):
+        tmp = np.zeros(batch * frames * 80, np.float32)
+        self.stac_fbank_topdb_norm(logmel_db, utt_max_ordered, per_utterance, top_db, mean, std, batch, frames, 80,
+                                   tmp.ctypes.data, stream)
+        self.stac_conv0_ln_lrelu(tmp.ctypes.data, w0, b0, ln_g, ln_b, batch, frames, out, _lib.DT_BF16, stream)
 
     def stac_conv1_f32(self, x, w1, b1, batch, t1, out, stream):
         t2 = (t1 - 1) // 2 + 1

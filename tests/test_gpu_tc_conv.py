@@ -92,3 +92,31 @@ def test_conv0_tc_block_padded_layout(b, t):
     assert exact > 0.97, float(exact)
     assert float(((got - want).abs() <= want.abs() * 2.0 ** -7 + 1e-4).float().mean()) > 0.9999
     assert float((guard.float() - 7.0).abs().max()) == 0.0
+
+
+def test_conv0_with_fused_topdb_norm_equals_the_two_kernel_path():
+    """stac_conv0_topdb_norm_bf16 (clamp + normalisation inside block 0's loader) must give what stac_fbank_topdb_norm
+    followed by stac_conv0_ln_lrelu gives (the loader multiplies by 1 / std where the separate kernel divides: one fp32
+    ulp on the features, far below the bf16 output's resolution) - for the per-utterance and the batch-global top-dB
+    rule, with and without statistics, on a ragged batch."""
+    import stac_speech_translation_b200 as sb
+    from stac_speech_translation_b200 import ops, synth
+    mods = sb.build_modules(sb.HParams.for_size("S", num_encoder_layers=1), precision="bf16", device="cuda")
+    w = mods["CNN"].packed()
+    wavs, _ = synth.synth_batch([2.0, 0.7, 1.31], seed=5)
+    wavs = wavs[:, : wavs.shape[1] // 4 * 4].contiguous().cuda()
+    wavs[1] *= 0.01                                        # a quiet utterance: its own maximum matters
+    g = torch.Generator().manual_seed(3)
+    mean = (torch.randn(80, generator=g) * 5 - 20).cuda()
+    std = (torch.rand(80, generator=g) * 10 + 5).cuda()
+    tabs = ops.build_fbank_tc_tables(wavs.device)
+    for per_utt in (True, False):
+        for stats in ((mean, std), (None, None)):
+            feats = ops.fbank_tc(wavs, tabs, 80.0, per_utt, *stats)
+            raw = ops.fbank_tc(wavs, tabs, 80.0, per_utt, *stats, raw=True)
+            a = ops.conv_frontend(feats, w, torch.bfloat16)
+            b = ops.conv_frontend(raw, w, torch.bfloat16)
+            torch.cuda.synchronize()
+            assert rel_l2(a, b) < 1e-3, (per_utt, stats[0] is not None, rel_l2(a, b))
+            if stats[0] is None:
+                assert torch.equal(a, b)                # clamp only: no arithmetic differs

@@ -147,3 +147,30 @@ def test_fused_ffn_block(m, dffn):
     # unsupported widths are refused, not mis-computed
     assert ops.lib().stac_ffn_fused_bf16(ops.ptr(h_d), ops.ptr(w1_d), ops.ptr(b1_d), ops.ptr(w2_d), ops.ptr(b2_d),
                                          ops.ptr(x), m, 512, dffn, ops.stream()) == -2
+
+
+@pytest.mark.parametrize("m", [1, 127, 128, 129, 4000, 48064])
+def test_outproj_residual_layernorm_fused(m):
+    """stac_outproj_ln_bf16 against fp64 arithmetic on the same bf16 operands: x += ctx W^T + b (fp32 residual stream, in
+    place), h = LayerNorm(x) in bf16; rows past m untouched (guard band), including the ragged last tile."""
+    from stac_speech_translation_b200 import ops
+    g = torch.Generator().manual_seed(m)
+    a = (torch.randn(m, 256, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(256, 256, generator=g) / 16).to(torch.bfloat16)
+    bias = torch.randn(256, generator=g)
+    x0 = torch.randn(m, 256, generator=g) * 3 + 0.5
+    gam, bet = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    xg = torch.full((m + 64, 256), 7.0)
+    xg[:m] = x0
+    xg = xg.cuda()
+    hg = torch.full((m + 64, 256), 3.0, dtype=torch.bfloat16).cuda()
+    a_d, w_d, b_d, g_d, be_d = a.cuda(), w.cuda(), bias.cuda(), gam.cuda(), bet.cuda()     # (kept alive: ptr() of a
+    ops._call("stac_outproj_ln_bf16", ops.ptr(a_d), ops.ptr(w_d), ops.ptr(b_d), ops.ptr(xg),  # temporary dangles)
+              ops.ptr(g_d), ops.ptr(be_d), 1e-6, ops.ptr(hg), m, ops.stream())
+    torch.cuda.synchronize()
+    x_ref = x0.double() + a.double() @ w.double().T + bias.double()
+    mu, var = x_ref.mean(-1, keepdim=True), x_ref.var(-1, unbiased=False, keepdim=True)
+    h_ref = (x_ref - mu) / torch.sqrt(var + 1e-6) * gam.double() + bet.double()
+    assert rel_l2(xg[:m].cpu(), x_ref) < 1e-5
+    assert rel_l2(hg[:m].float().cpu(), h_ref) < 4e-3                 # bf16 rounding of the output
+    assert torch.all(xg[m:] == 7.0) and torch.all(hg[m:].float() == 3.0)

@@ -297,6 +297,16 @@ def test_bf16_path_host_orchestration_against_the_oracle(monkeypatch, mha_v2, ti
     assert ("stac_mha_bf16_v2" if mha_v2 else "stac_mha_bf16") in emu.calls
     assert {"stac_fbank_logmel_tc", "stac_conv1_bf16", "stac_ctc_head_bf16"} <= set(emu.calls)
     assert ("stac_ffn_fused_bf16" in emu.calls) == (not tiny)
+    n_layers = len(mods["Transformer"].packed().layers)
+    assert emu.calls.count("stac_layernorm") == 2 * n_layers + 1
+    if not tiny:
+        # the out-proj + residual + LayerNorm 2 kernel (off by default: measured not faster) gives the same result
+        monkeypatch.setattr(ops, "FUSED_OUTPROJ_LN", True)
+        emu.calls.clear()
+        res2 = sb.EncoderPipeline(mods)(wavs, wl)
+        assert emu.calls.count("stac_outproj_ln_bf16") == n_layers and emu.calls.count("stac_layernorm") == n_layers + 1
+        assert rel_l2(res2["enc_out"], res["enc_out"]) < 5e-3
+        monkeypatch.setattr(ops, "FUSED_OUTPROJ_LN", False)
     # the six-call sequence in bf16 mode (fp32 tensors at every stage boundary, as the reference's callers expect)
     got = sb.compute_forward(mods, wavs, wl)
     assert all(got[k].dtype == torch.float32 for k in ("fbank", "feats", "cnn", "enc_out", "logits", "p_ctc"))

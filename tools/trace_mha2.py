@@ -44,4 +44,4 @@ for role in (2, 3):
     ends = [int(tr[role, s + 1, 1]) for s in range(8, 40) if int(tr[role, s, 1]) and int(tr[role, s + 1, 1])]
     if starts:
         per = sum((e - s) & 0xffffffff for s, e in zip(starts, ends)) / len(starts)
-        print(f"softmax group {role - 2}: mean period of a 128-key step {per:.0f} clk (MUFU floor for both groups: 2048)")
+        print(f"softmax group {role - 2}: mean period of a 96-key step {per:.0f} clk (MUFU floor for both groups: 1536)")
