@@ -56,11 +56,15 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--gather", default="bf16", choices=["ids", "bf16", "fp32"],
                     help="what travels to rank 0 besides enc_out when N > 1: greedy ids only, bf16 or fp32 posteriors")
-    ap.add_argument("--gather-transport", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: rank 0 pulls results over peer memory with the copy engines (default), or NCCL send/recv")
+    ap.add_argument("--gather-transport", default="push", choices=["push", "peer", "nccl"],
+                    help="N > 1: every rank pushes its results into rank 0's peer-mapped buffers with its own copy "
+                         "engines (default), rank 0 pulls them (peer), or NCCL send/recv")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="SMs left free for the NCCL transfer kernels when N > 1 (default 0: measured no gain at N=8, "
                          "the gather is bound by NCCL's per-peer point-to-point bandwidth, not by SM contention)")
+    ap.add_argument("--pcm", default="int16", choices=["int16", "fp32"],
+                    help="what the end-to-end leg ships from the host: 16-bit PCM as a wav file holds it (decoded on the "
+                         "device, sample / 32768, SURVEY.md 8f-2) or the fp32 waveform the reference's DataLoader builds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=8, help="utterances in the CPU-baseline sample")
     ap.add_argument("--trace-out", default=None, help="write the per-kernel timing table (json) here")
@@ -172,9 +176,12 @@ def workload_config(args, t2, world):
             "l2": "per-step working set (~6 GB of activations) >> 126 MB L2, no explicit flush",
             "multi_gpu": ("whole batches per rank; enc_out + greedy ids"
                           + ("" if args.gather == "ids" else f" + {args.gather} posteriors")
-                          + (" pulled by rank 0 over NVLink peer memory (copy engines; torch.distributed gloo control "
-                             "messages, NCCL barrier)" if getattr(args, "gather_transport", "peer") == "peer"
-                             else " sent to rank 0 with NCCL point-to-point")
+                          + ({"peer": " pulled by rank 0 over NVLink peer memory (copy engines; torch.distributed gloo "
+                                      "control messages, NCCL barrier)",
+                              "push": " pushed by every rank's own copy engines into rank 0's peer-mapped buffers over "
+                                      "NVLink (no communication kernel, one working context per GPU; gloo control "
+                                      "messages, NCCL barrier)"}.get(getattr(args, "gather_transport", "push"),
+                                                                     " sent to rank 0 with NCCL point-to-point"))
                           + " inside the timed region") if world > 1 else "single GPU"}
 
 
@@ -352,6 +359,10 @@ def run_ours(args, rank, world, local_rank):
     hp = sb.HParams.for_size(args.size)
     mods = sb.build_modules(hp, precision=args.precision, device=dev)
     wavs_cpu, wl_cpu = synth.fast_synth_batch(args.batch, args.seconds, seed=1234 + rank)
+    # the synthetic audio is what a 16-bit wav file holds (sample / 32768): the device-resident batch, the oracle's input and
+    # the int16 PCM of the end-to-end leg are the same signal
+    pcm16_cpu = (wavs_cpu * 32768.0).round().clamp(-32768, 32767).to(torch.int16)
+    wavs_cpu = pcm16_cpu.float() / 32768.0
     if args.min_seconds is not None:
         # ragged batch (configs[3]): lengths uniform in [min, seconds]; right zero padding and wav_lens = len / Lmax as
         # the reference's PaddedBatch builds them.  The longest utterance keeps the full length.
@@ -362,6 +373,7 @@ def run_ours(args, rank, world, local_rank):
         n_valid = torch.round(wl_cpu * wavs_cpu.shape[1]).long()
         for i in range(args.batch):
             wavs_cpu[i, int(n_valid[i]):] = 0.0
+            pcm16_cpu[i, int(n_valid[i]):] = 0
         wl_cpu = (n_valid.double() / wavs_cpu.shape[1]).float()
     # normaliser statistics: one SpeechBrain-style statistics step on a calibration slice
     calib = wavs_cpu[: min(8, args.batch), : 16000 * 4].to(dev)
@@ -382,13 +394,13 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         d = hp.d_model
         pdt = torch.bfloat16 if (args.gather == "bf16" and args.precision == "bf16") else torch.float32
-        if args.gather_transport == "peer":
-            from stac_speech_translation_b200.distributed import PeerGather, PeerGatherUnavailable
+        if args.gather_transport in ("peer", "push"):
+            from stac_speech_translation_b200.distributed import PeerGather, PeerGatherUnavailable, PushGather
             specs = {"enc_out": ((args.batch, t2, d), torch.float32), "greedy": ((args.batch, t2), torch.int32)}
             if args.gather != "ids":
                 specs["p_ctc"] = ((args.batch, t2, VOCAB), pdt)
             try:
-                peer = PeerGather(specs, dev)
+                peer = (PushGather if args.gather_transport == "push" else PeerGather)(specs, dev)
             except PeerGatherUnavailable as e:     # raised on every rank together: all fall back to NCCL p2p
                 if rank == 0:
                     print(f"bench: peer transport unavailable ({e}); using NCCL point-to-point", file=sys.stderr)
@@ -405,7 +417,7 @@ def run_ours(args, rank, world, local_rank):
     def drain(keep=0):
         if peer is not None:
             if keep == 0:
-                peer.finish()
+                peer.finish(gstep[0] - 1)
             return
         while len(pending) > keep:
             works, _ = pending.pop(0)
@@ -526,6 +538,10 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end: pinned host PCM in (H2D inside the timed region), greedy ids out (D2H) ----
     ids_host = [torch.empty(args.batch, t2, dtype=torch.int32).pin_memory() for _ in range(2)]
+    use_i16 = args.pcm == "int16"
+    if use_i16:
+        pinned_i16 = pcm16_cpu.pin_memory()
+        dev_i16 = [torch.empty_like(pinned_i16, device=dev) for _ in range(2)]
     in_ready = [torch.cuda.Event() for _ in range(2)]
     in_free = [torch.cuda.Event() for _ in range(2)]
     out_done = [torch.cuda.Event() for _ in range(2)]
@@ -538,7 +554,12 @@ def run_ours(args, rank, world, local_rank):
                 s = (k0 + i) % 2
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(in_free[s])
-                    dev_in[s].copy_(pinned, non_blocking=True)
+                    if use_i16:                # 16-bit PCM over the link, decoded on the device (stac_pcm_i16_to_f32)
+                        dev_i16[s].copy_(pinned_i16, non_blocking=True)
+                        ops.check(ops.lib().stac_pcm_i16_to_f32(ops.ptr(dev_i16[s], torch.int16), dev_i16[s].numel(),
+                                                                ops.ptr(dev_in[s]), ops.stream()), "stac_pcm_i16_to_f32")
+                    else:
+                        dev_in[s].copy_(pinned, non_blocking=True)
                     in_ready[s].record(copy_stream)
             if i > 0:                       # compute step i-1, ship its greedy ids to the host
                 s = (k0 + i - 1) % 2
@@ -584,10 +605,10 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             for r in range(1, world):
                 for k, want in sums[r].items():
-                    got = float(peer.gathered[r][k].double().sum())
+                    got = float(peer.gathered_view(r, last)[k].double().sum())
                     if abs(got - want) > 1e-6 * max(1.0, abs(want)):
                         raise RuntimeError(f"peer gather mismatch: rank {r} {k}: {got} != {want}")
-            gather_check = "checksums of every rank's last step match what rank 0 pulled"
+            gather_check = "checksums of every rank's last step match what rank 0 holds"
 
     if world > 1:                                  # valid audio differs per rank when the batch is ragged
         t_a = torch.tensor([audio_s], device=dev, dtype=torch.float64)
@@ -638,9 +659,11 @@ def run_ours(args, rank, world, local_rank):
                    "audio": "value counts valid (unpadded) audio seconds; padded rate "
                             f"{padded_audio_s * world / (ms * 1e-3):.0f} audio-s/s"},
         "e2e": {"value": round(total_audio / (e2e_ms * 1e-3), 1), "unit": UNIT,
-                "h2d_bytes_per_step": int(pinned.numel() * 4), "d2h_bytes_per_step": int(args.batch * t2 * 4),
+                "h2d_bytes_per_step": int(pinned.numel() * (2 if use_i16 else 4)),
+                "d2h_bytes_per_step": int(args.batch * t2 * 4),
                 "ms_per_step": round(e2e_ms, 3), "pinned_h2d_gbs": round(h2d_gbs, 1),
-                "note": "pinned fp32 PCM in (double-buffered on a copy stream), one CUDA-graph replay of the path "
+                "note": ("pinned 16-bit PCM in, decoded to fp32 on the device (sample / 32768)" if use_i16 else
+                         "pinned fp32 PCM in") + " (double-buffered on a copy stream), one CUDA-graph replay of the path "
                         "(GraphedPipeline) per step, greedy CTC ids out; enc_out and p_ctc stay on the device as in "
                         "the reference's compute_forward"},
         "gpu_launches": launches,
@@ -747,7 +770,7 @@ def run_bucketed(args, rank, world, local_rank):
     work_sum, launches_sum = {}, {}
     ops.TRACE = []
     for b in batches:
-        kv = ops.kv_lengths(b["wl"], b["n"], b["t2"], dev, False).long()
+        kv = ops.kv_lengths(b["wl"].cpu(), b["n"], b["t2"], "cpu", False).long()      # (host twin: keeps the trace clean)
         wt = work_table(sb.MODEL_SIZES[args.size], b["n"], b["lmax"], int((kv * b["t2"]).sum()))
         for k, (bound, work, n_l) in wt.items():
             work_sum[k] = (bound, work_sum.get(k, (bound, 0))[1] + work * n_l)

@@ -29,8 +29,10 @@
 //
 // TMEM (512 columns): S/P buffer (group w, buffer sb) at (w * 2 + sb) * 96 (96 fp32 score columns; P = 48 columns of
 // packed bf16 pairs on top of the first 48); O[group] at 384 + group * 64.
-// Threads (512): warps 0-3 softmax group 0, 4-7 softmax group 1 (warp & 3 = TMEM lane quarter), 8-11 epilogue
-// warpgroup, 12/13 MMA issuers of group 0/1, 14 TMA producer, 15 idle.  setmaxnreg: 176 / 80 / 80.
+// Threads (512): warps 0-3 / 4-7 softmax group 0 / 1 (one thread per row), 8-11 epilogue warpgroup, 12/13 MMA issuers of
+// group 0/1, 14 TMA producer, 15 idle; setmaxnreg 176 / 80.  (-DMHA2_SPLIT: 768 threads - warps 0-7 softmax group 0, 0-3
+// keys 0-47 and 4-7 keys 48-95 of every tile, 8-15 group 1, 16-19 epilogue, 20/21 issuers, 22 producer; setmaxnreg 96 /
+// 48.)  warp & 3 = TMEM lane quarter in every role that touches tensor memory.
 #include <algorithm>
 #include <type_traits>
 #include "tc_common.cuh"
@@ -48,8 +50,22 @@ constexpr int kKBytes = kKTile * kHd * 2;             // one K (or V) tile
 constexpr int kStageBytes = 2 * kKBytes;
 constexpr int kSCols = kKTile;                         // fp32 score columns of one S buffer
 constexpr int kOCol = 4 * kSCols;                      // first O column
-constexpr int kThreads = 512;
+// -DMHA2_SPLIT (measured, not adopted): TWO softmax threads per query row, each owning 48 of the tile's 96 keys - 16
+// softmax warps, four per scheduler instead of two, one exchange of the row maximum per step between the two warps of
+// a row (shared memory + a 64-thread named barrier).  Parity green; 73.0 us against 69.5 us at the benchmark shape
+// (profiles/r3/r3i_mha_split.log): the exponential phase becomes MUFU-bound (4 x 48 x 8 = 1536 clk, measured ~1650), but
+// all four warps of a scheduler still move in lockstep (same score barrier, pair barrier), so the ~1800 clk of barrier /
+// TMEM load / maximum / store-wait per step stay un-overlapped and the step is as long as before.
+#ifdef MHA2_SPLIT
+constexpr int kSoftWarps = 16;
+constexpr int kRegsSoftmax = 96, kRegsOther = 48;      // 512 * 96 + 256 * 48 = 61440 <= 65536 (launch: 768 * 80)
+#else
+constexpr int kSoftWarps = 8;
 constexpr int kRegsSoftmax = 176, kRegsOther = 80;     // 256 * 176 + 256 * 80 = 512 * 128
+#endif
+constexpr int kEpiWarp0 = kSoftWarps;                  // 4 epilogue warps, then 2 MMA issuers, the TMA producer, 1 idle
+constexpr int kIssuer0 = kSoftWarps + 4, kProducer = kSoftWarps + 6;
+constexpr int kThreads = (kSoftWarps + 8) * 32;
 #ifndef MHA2_POLY
 #define MHA2_POLY 0
 #endif
@@ -63,8 +79,9 @@ constexpr int kRegsSoftmax = 176, kRegsOther = 80;     // 256 * 176 + 256 * 80 =
 constexpr int kOffQ = 0;                               // [2 bufs][2 groups] x 16 KB
 constexpr int kOffOut = 65536;                         // [2 groups] x 16 KB: normalised bf16 O tile for the TMA store
 constexpr int kOffKV = 98304;                          // [stages] x (K 16 KB + V 16 KB)
-constexpr int kOffX = kOffKV + kKvStages * kStageBytes; // float [2 groups][128 rows]: 1 / row sum
-constexpr int kOffLen = kOffX + 2 * 128 * 4;           // int [kLenCache]
+constexpr int kOffX = kOffKV + kKvStages * kStageBytes; // float [2 groups][2 halves][128 rows]: (partial) row sums
+constexpr int kOffMax = kOffX + 2 * 2 * 128 * 4;       // float [2 step parities][2 groups][2 halves][128 rows]: row maxima (MHA2_SPLIT)
+constexpr int kOffLen = kOffMax + 2 * 2 * 2 * 128 * 4; // int [kLenCache]
 constexpr int kLenCache = 128;
 constexpr int kOffBar = kOffLen + kLenCache * 4;
 constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 9;
@@ -137,6 +154,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] . B[smem]: A = 128 lanes (rows) x 8 columns of packed bf16 pairs per K = 16 step
@@ -222,14 +247,14 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int i = 0; i < 4; ++i) { mbar_init(q_full(i >> 1, i & 1), 1); mbar_init(q_empty(i >> 1, i & 1), 1); }
     for (int s = 0; s < kKvStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }
     for (int w = 0; w < 2; ++w) {
-      for (int sb = 0; sb < 2; ++sb) { mbar_init(s_full(w, sb), 1); mbar_init(p_full(w, sb), 4); mbar_init(pv_done(w, sb), 1); }
+      for (int sb = 0; sb < 2; ++sb) { mbar_init(s_full(w, sb), 1); mbar_init(p_full(w, sb), kSoftWarps / 2); mbar_init(pv_done(w, sb), 1); }
       mbar_init(o_full(w), 1);
-      mbar_init(l_full(w), 4);
+      mbar_init(l_full(w), kSoftWarps / 2);
       mbar_init(o_free(w), 4);
     }
     fence_barrier_init();
   }
-  if (warp == 12) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == kIssuer0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -238,9 +263,9 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   // (setmaxnreg at the top of each role's branch: ptxas derives the register limit of a region from the setmaxnreg that
   // dominates it; the two 80-register warpgroups release before the softmax warpgroups can grow)
-  if (warp >= 12) {
+  if (warp >= kIssuer0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
-    if (warp == 14) {
+    if (warp == kProducer) {
       // ============================ TMA producer ============================
       if (lane == 0) {
         int stage = 0;
@@ -272,7 +297,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
       __syncwarp();
-    } else if (warp < 14) {
+    } else if (warp < kProducer) {
       // ============================ MMA issuers: warp 12 -> group 0, warp 13 -> group 1 ============================
       // Order per group: S(0) S(1) | P.V(0) S(2) | P.V(1) S(3) | ...  S(g + 2) lands in the buffer P(g) lives in, so it
       // is issued behind P.V(g): the tcgen05.mma of one thread execute in issue order, which is what keeps S(g + 2) from
@@ -390,11 +415,11 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
       };
-      if (warp == 12) issuer(std::integral_constant<int, 0>{});
+      if (warp == kIssuer0) issuer(std::integral_constant<int, 0>{});
       else issuer(std::integral_constant<int, 1>{});
       __syncwarp();
     }
-  } else if (warp >= 8) {
+  } else if (warp >= kEpiWarp0) {
     // ============================ epilogue warpgroup ============================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     const int quarter = warp & 3;
@@ -411,16 +436,20 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (w == 1 && !it.active1) continue;
         const uint32_t ph = uses[w] & 1;
         ++uses[w];
-        const bool tr = warp == 8 && lane == 0;
+        const bool tr = warp == kEpiWarp0 && lane == 0;
         if (tr) TRACE2(4, 0, ordinal * 2 + w);
         mbar_wait(l_full(w), ph);
         if (tr) TRACE2(4, 1, ordinal * 2 + w);
+#ifdef MHA2_SPLIT
+        const float inv = 1.0f / (xch[(w * 2) * 128 + r] + xch[(w * 2 + 1) * 128 + r]);     // the two halves' partial sums
+#else
         const float inv = xch[w * 128 + r];
+#endif
         mbar_wait(o_full(w), ph);
         if (tr) TRACE2(4, 2, ordinal * 2 + w);
         tc_fence_after();
         // the previous TMA store out of this group's staging tile must have read it
-        if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         named_bar_sync(1, 128);
         const uint32_t srow = sbase + kOffOut + w * 16384 + r * 128;
 #pragma unroll
@@ -445,7 +474,7 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (tr) TRACE2(4, 4, ordinal * 2 + w);
-        if (warp == 8 && lane == 0) {
+        if (warp == kEpiWarp0 && lane == 0) {
           // rows past the end of the utterance are clipped by the 3-D map
           asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                        ::"l"(reinterpret_cast<uint64_t>(&tmap_ctx)), "r"(sbase + kOffOut + w * 16384),
@@ -455,8 +484,119 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (tr) TRACE2(4, 5, ordinal * 2 + w);
       }
     }
-    if (warp == 8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (warp == kEpiWarp0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
+#ifdef MHA2_SPLIT
+    // ============================ softmax groups, two threads per query row ============================
+    // warps 0-3 / 4-7: group 0, keys 0-47 / 48-95 of every tile; warps 8-11 / 12-15: group 1.  warp & 3 = TMEM lane quarter,
+    // so the two warps of a row sit on the same scheduler.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
+    const int w = warp >> 3;                       // group / query tile
+    const int half = (warp >> 2) & 1;              // which 48 keys of a tile
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;             // row inside the tile = TMEM lane
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t o_tmem = tmem_base + kOCol + w * kHd + half * 32 + lane_off;    // my 32 of the row's 64 O columns
+    float* xch = reinterpret_cast<float*>(sptr + kOffX);
+    float* xmax = reinterpret_cast<float*>(sptr + kOffMax);
+    const int pair_bar = 2 + w * 4 + quarter;      // named barrier of the two warps that share these 32 rows
+    constexpr int kHalf = kKTile / 2;              // 48 keys
+    uint32_t g = 0;                                // per-group step index
+    uint32_t uses = 0;
+    int ordinal = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
+      const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
+      if (w == 1 && !it.active1) continue;
+      constexpr float kRaise = 40.0f;              // see the one-thread-per-row form below
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < it.n_kt; ++j, ++g) {
+        const bool tr = (warp & 7) == 0 && lane == 0;
+        const int sb = g & 1;
+        const uint32_t s_tmem = tmem_base + (w * 2 + sb) * kSCols + lane_off;
+        if (tr) TRACE2(2 + w, 0, g);
+        mbar_wait(s_full(w, sb), (g >> 1) & 1);
+        if (tr) TRACE2(2 + w, 1, g);
+        tc_fence_after();
+        uint32_t v[kHalf / 16][16];
+#pragma unroll
+        for (int c = 0; c < kHalf / 16; ++c) tmem_ld16(s_tmem + half * kHalf + c * 16, v[c]);
+        tmem_ld_wait();
+        if (tr) TRACE2(2 + w, 2, g);
+        const int valid = it.n_keys - j * kKTile - half * kHalf;      // my columns < valid are real keys
+        if (valid < kHalf) {
+#pragma unroll
+          for (int c = 0; c < kHalf; ++c)
+            if (c >= valid) v[c >> 4][c & 15] = 0xff800000u;         // -inf: exp2 gives exactly 0
+        }
+        float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < kHalf; c += 4) {
+          tm0 = max3(tm0, __uint_as_float(v[c >> 4][c & 15]), __uint_as_float(v[c >> 4][(c & 15) + 1]));
+          tm1 = max3(tm1, __uint_as_float(v[c >> 4][(c & 15) + 2]), __uint_as_float(v[c >> 4][(c & 15) + 3]));
+        }
+        // row maximum of the tile = max over the two halves: exchanged through shared memory (slot = step parity: the
+        // partner cannot be two steps ahead, it needs this warp at the barrier of every step)
+        float* slot = xmax + ((sb * 2 + w) * 2) * 128;
+        slot[half * 128 + r] = fmaxf(tm0, tm1);
+        named_bar_sync(pair_bar, 64);
+        const float tile_max = fmaxf(fmaxf(tm0, tm1), slot[(half ^ 1) * 128 + r]);
+        if (j == 0) {
+          m_ref = tile_max;                            // O is overwritten by the first P.V of the item
+        } else {
+          const bool raise = (tile_max - m_ref) * kLog2e > kRaise;     // same value in both threads of the row
+          if (__any_sync(0xffffffffu, raise)) {
+            // (rare; see the one-thread-per-row form for why this occasional wait cannot alias)  Each half rescales
+            // its own 32 O columns; both apply the same factor to their partial row sum.
+            mbar_wait(pv_done(w, sb ^ 1), ((g - 1) >> 1) & 1);
+            tc_fence_after();
+            const float factor = raise ? ex2_mufu((m_ref - tile_max) * kLog2e) : 1.0f;
+            if (raise) m_ref = tile_max;
+            l_run *= factor;
+#pragma unroll 1
+            for (int c = 0; c < kHd / 2; c += 8) {
+              uint32_t o[8];
+              tmem_ld8(o_tmem + c, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * factor);
+              tmem_st8(o_tmem + c, o);
+            }
+          }
+        }
+        if (tr) TRACE2(2 + w, 3, g);
+        const float m_scaled = m_ref * kLog2e;
+        float2 l0 = make_float2(0.f, 0.f), l1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < kHalf / 16; ++c) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[c][2 * e]), __uint_as_float(v[c][2 * e + 1])),
+                                        make_float2(kLog2e, kLog2e), make_float2(-m_scaled, -m_scaled));
+            const float p0 = ex2_mufu(x.x), p1 = ex2_mufu(x.y);
+            if (e & 1) l1 = __fadd2_rn(l1, make_float2(p0, p1));
+            else l0 = __fadd2_rn(l0, make_float2(p0, p1));
+            pk[e] = pack_bf16x2(p0, p1);
+          }
+          // P column k holds keys 2k, 2k + 1: my 48 keys are P columns half * 24 + [0, 24)
+          tmem_st8(s_tmem + half * (kHalf / 2) + c * 8, pk);
+        }
+        l_run += (l0.x + l0.y) + (l1.x + l1.y);
+        if (tr && l_run != 123.f) TRACE2(2 + w, 4, g);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(w, sb));
+        if (tr) TRACE2(2 + w, 5, g);
+      }
+      // end of the item: hand my partial row sum to the epilogue warpgroup (it adds the two halves)
+      mbar_wait(o_free(w), (uses & 1) ^ 1);
+      xch[(w * 2 + half) * 128 + r] = l_run;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(l_full(w));
+      ++uses;
+    }
+#else
     // ============================ softmax groups (thread = query row) ============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     const int w = warp >> 2;                       // group / query tile
@@ -612,11 +752,12 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (lane == 0) mbar_arrive(l_full(w));
       ++uses;
     }
+#endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == kIssuer0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace

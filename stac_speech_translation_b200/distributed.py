@@ -273,8 +273,177 @@ class PeerGather:
                 self._last[r] = ev
             self._post(step, r)                 # acknowledgement: the pull of `step` is enqueued
 
-    def finish(self) -> None:
+    def gathered_view(self, r: int, step: int) -> Dict[str, torch.Tensor]:
+        return self.gathered[r]
+
+    def finish(self, last_step: Optional[int] = None) -> None:
         """Rank 0: the current stream waits for every pull enqueued so far."""
+        del last_step
         if self.rank == 0:
             for ev in self._last.values():
                 torch.cuda.current_stream(self.device).wait_event(ev)
+
+
+class PushGather:
+    """Results of every rank to rank 0, PUSHED: every producing rank copies its finished result slot into buffers that
+    live on rank 0's GPU (peer-mapped through CUDA IPC) with its OWN copy engines on its OWN side stream.
+
+    Same interface as PeerGather (begin_write / slot / end_write on the producers, collect / finish on rank 0) and the
+    same properties - no communication kernel, no SM, the transfer of step i overlaps the compute of step i + 1 - but
+    exactly ONE working CUDA context per GPU.  PeerGather has rank 0 drive the copies from a second context on every
+    peer GPU; that context's copy and event work is time-sliced against the peer's compute context, which is what a
+    2-GPU step lost (4.99 ms against 4.54 ms on one GPU, and no better when only the ids travelled; round 2).  Here the
+    foreign contexts that opening an IPC handle creates (every rank holds one on GPU 0) never submit work.
+
+    Ordering.  Producer r, step i, slot s = i % slots: the compute stream waits for push(i - slots) to have read the
+    local slot (plain event), the kernels write the slot, the push stream waits for them (plain event) and issues one
+    cudaMemcpyPeerAsync per tensor into rank 0's gathered[r][s] followed by an 8-byte "step i + 1 has landed" mark in
+    rank 0's mailbox - stream order puts the mark behind the data.  Rank 0 never waits on another device's event (that
+    segfaults, see _IpcEvent.wait): `arrived(step)` reads the mailbox with a tiny device-to-host copy on a side stream.
+    Flow control against rank 0's consumer is a control message: producer r may overwrite gathered[r][s] again only
+    after rank 0 released it (collect(step) = wait for the arrival of `step` from every rank, hand the buffers to the
+    caller, acknowledge)."""
+
+    def _agree(self, ok: bool, what: str):
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ctl)
+        if int(flag) == 0:
+            raise PeerGatherUnavailable(what)
+
+    def __init__(self, specs: Dict[str, tuple], device: torch.device, slots: int = 2):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device, self.n_slots, self.keys = device, slots, list(specs)
+        self.ctl = dist.new_group(backend="gloo")
+        self._msg = torch.zeros(1, dtype=torch.int64)
+        ok, payload = True, [None] * self.world
+        try:
+            if self.rank == 0:
+                # gathered[r][s][key] and the mailbox live on rank 0's GPU; every producer gets the handles of its share
+                self._bufs = {r: [{k: torch.empty(shape, dtype=dt, device=device) for k, (shape, dt) in specs.items()}
+                                  for _ in range(slots)] for r in range(1, self.world)}
+                self._mailbox = torch.zeros(self.world, slots, dtype=torch.int64, device=device)
+                self._mail_host = torch.zeros(self.world, slots, dtype=torch.int64).pin_memory()
+                self._mail_stream = torch.cuda.Stream(device=device)
+                torch.cuda.synchronize(device)
+                for r in range(1, self.world):
+                    payload[r] = {"device": device.index,
+                                  "tensors": [{k: reduce_tensor(t) for k, t in s.items()} for s in self._bufs[r]],
+                                  "mailbox": reduce_tensor(self._mailbox)}
+        except Exception as e:                  # noqa: BLE001
+            ok, self._why = False, repr(e)
+        self._agree(ok, "CUDA IPC export of rank 0's gather buffers failed")
+        mine = [None]
+        dist.scatter_object_list(mine, payload if self.rank == 0 else None, src=0, group=self.ctl)
+        try:
+            if self.rank != 0:
+                p = mine[0]
+                self._root_dev = p["device"]
+                if not torch.cuda.can_device_access_peer(device.index, self._root_dev):
+                    raise RuntimeError(f"no peer access {device.index} -> {self._root_dev}")
+                self._remote = [{k: fn(*args) for k, (fn, args) in s.items()} for s in p["tensors"]]
+                fn, args = p["mailbox"]
+                self._remote_mail = fn(*args)
+                self._slots = [{k: torch.empty(shape, dtype=dt, device=device) for k, (shape, dt) in specs.items()}
+                               for _ in range(slots)]
+                self._tick = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(slots)]
+                # one torch cross-device copy makes torch enable peer access between the two devices
+                self._tick[0].copy_(self._remote_mail.view(-1)[:1])
+                self._push_stream = torch.cuda.Stream(device=device)
+                self._computed = [torch.cuda.Event() for _ in range(slots)]
+                self._pushed = [torch.cuda.Event() for _ in range(slots)]
+                for ev in self._pushed:
+                    ev.record(self._push_stream)
+                torch.cuda.synchronize(device)
+        except Exception as e:                  # noqa: BLE001
+            ok, self._why = False, repr(e)
+        self._agree(ok, "a rank could not open rank 0's gather buffers (device not visible to it, or no peer access)")
+        dist.barrier(group=self.ctl)
+
+    def _post(self, value: int, dst: int) -> None:
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        t = torch.tensor([value], dtype=torch.int64)
+        self._inflight.append((dist.isend(t, dst=dst, group=self.ctl), t))
+        self._inflight = [(w, x) for w, x in self._inflight if not w.is_completed()]
+
+    # ---- producing ranks ----
+    def slot(self, step: int) -> Dict[str, torch.Tensor]:
+        return self._slots[step % self.n_slots]
+
+    def begin_write(self, step: int) -> None:
+        """Before the kernels of `step` overwrite their slot: its previous push has read it (event), and rank 0 has
+        released the remote buffers that push will overwrite (control message, from step `slots` on)."""
+        if self.rank == 0:
+            return
+        s = step % self.n_slots
+        torch.cuda.current_stream(self.device).wait_event(self._pushed[s])
+        if step >= self.n_slots:
+            dist.recv(self._msg, src=0, group=self.ctl)                # "step - slots has been consumed"
+
+    def end_write(self, step: int) -> None:
+        """Enqueue the push of `step` behind its kernels: tensors first, then the arrival mark."""
+        if self.rank == 0:
+            return
+        import ctypes
+        s = step % self.n_slots
+        cur = torch.cuda.current_stream(self.device)
+        self._computed[s].record(cur)
+        rt = _IpcEvent.rt()
+        with torch.cuda.stream(self._push_stream):
+            self._push_stream.wait_event(self._computed[s])
+            for k in self.keys:
+                dst, src = self._remote[s][k], self._slots[s][k]
+                _IpcEvent._check(rt.cudaMemcpyPeerAsync(ctypes.c_void_p(dst.data_ptr()), self._root_dev,
+                                                        ctypes.c_void_p(src.data_ptr()), self.device.index,
+                                                        src.numel() * src.element_size(),
+                                                        ctypes.c_void_p(self._push_stream.cuda_stream)),
+                                 "cudaMemcpyPeerAsync")
+            self._tick[s].fill_(step + 1)
+            mark = self._remote_mail[self.rank, s:s + 1]
+            _IpcEvent._check(rt.cudaMemcpyPeerAsync(ctypes.c_void_p(mark.data_ptr()), self._root_dev,
+                                                    ctypes.c_void_p(self._tick[s].data_ptr()), self.device.index, 8,
+                                                    ctypes.c_void_p(self._push_stream.cuda_stream)),
+                             "cudaMemcpyPeerAsync")
+            self._pushed[s].record(self._push_stream)
+
+    # ---- rank 0 ----
+    def arrived(self, step: int) -> bool:
+        """Rank 0: have the results of `step` of every producer landed?  (tiny D2H read of the mailbox, side stream)"""
+        with torch.cuda.stream(self._mail_stream):
+            self._mail_host.copy_(self._mailbox, non_blocking=True)
+        self._mail_stream.synchronize()
+        s = step % self.n_slots
+        return all(int(self._mail_host[r, s]) >= step + 1 for r in range(1, self.world))
+
+    def gathered_view(self, r: int, step: int) -> Dict[str, torch.Tensor]:
+        return self._bufs[r][step % self.n_slots]
+
+    def collect(self, step: int) -> None:
+        """Rank 0, called right after its own step `step` has been enqueued: consume the PREVIOUS step of every producer
+        (wait for its arrival marks; the caller may read gathered_view(r, step - 1) until the next collect) and release
+        those buffers.  Lagging one step keeps rank 0's GPU queue non-empty while its host waits for the marks."""
+        if self.rank != 0 or step < 1:
+            return
+        self._consume(step - 1)
+
+    def _consume(self, upto: int) -> None:
+        """Every step up to `upto` exactly once, in order: wait for its arrival marks, release its buffers."""
+        import time
+        done = getattr(self, "_consumed_upto", -1)
+        for step in range(done + 1, upto + 1):
+            t0 = time.perf_counter()
+            while not self.arrived(step):
+                if time.perf_counter() - t0 > 120.0:
+                    raise RuntimeError(f"PushGather: results of step {step} did not arrive within 120 s")
+            for r in range(1, self.world):
+                self._post(step, r)                                      # release: gathered[r][step % slots] is free
+            self._consumed_upto = step
+
+    def finish(self, last_step: Optional[int] = None) -> None:
+        """Producers: every push enqueued so far has completed.  Rank 0: everything up to `last_step` has arrived."""
+        if self.rank != 0:
+            self._push_stream.synchronize()
+            return
+        if last_step is not None and last_step >= 0:
+            self._consume(last_step)

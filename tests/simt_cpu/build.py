@@ -78,7 +78,8 @@ def build(force: bool = False) -> Path:
         '#include "cuda_runtime.h"\nint stac_grid_limit() { return 148; }\n'
         "// the tensor-core entry points the SIMT files hand over to are not part of this build\n"
         "int stac_conv0_tc_launch(const float*, const float*, const float*, const float*, const float*, long, long, int,\n"
-        "                         unsigned short*, void*) { return -2; }\n")
+        "                         unsigned short*, void*, const unsigned int*, int, float, const float*, const float*)\n"
+        "{ return -2; }\n")
     cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-fpermissive", "-w", f"-I{HERE}", f"-I{CSRC}", *units,
            str(gen / "api_stub.cpp"), "-o", str(LIB)]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -15,10 +15,12 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--seconds", type=float, default=30.0)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--stop-after", default=None, choices=[None, "cnn"])
+ap.add_argument("--layers", type=int, default=None, help="encoder layers (default: the size's own; 1 keeps an ncu capture short)")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
-mods = sb.build_modules(sb.HParams.for_size(args.size), precision="bf16", device=dev)
+hp = sb.HParams.for_size(args.size, **({"num_encoder_layers": args.layers} if args.layers else {}))
+mods = sb.build_modules(hp, precision="bf16", device=dev)
 wavs, wl = synth.fast_synth_batch(args.batch, args.seconds, seed=1234)
 wavs, wl = wavs.to(dev), wl.to(dev)
 calib = wavs[: min(8, args.batch), : 16000 * 4].contiguous()
