@@ -81,9 +81,9 @@ constexpr int kOffOut = 65536;                         // [2 groups] x 16 KB: no
 constexpr int kOffKV = 98304;                          // [stages] x (K 16 KB + V 16 KB)
 constexpr int kOffX = kOffKV + kKvStages * kStageBytes; // float [2 groups][2 halves][128 rows]: (partial) row sums
 constexpr int kOffMax = kOffX + 2 * 2 * 128 * 4;       // float [2 step parities][2 groups][2 halves][128 rows]: row maxima (MHA2_SPLIT)
-constexpr int kOffLen = kOffMax + 2 * 2 * 2 * 128 * 4; // int [kLenCache]
+constexpr int kOffLen = kOffMax + 2 * 2 * 2 * 128 * 4; // int4 [kLenCache]: (b, h, q0, n_keys) of this CTA's first work items
 constexpr int kLenCache = 128;
-constexpr int kOffBar = kOffLen + kLenCache * 4;
+constexpr int kOffBar = kOffLen + kLenCache * 16;
 constexpr int kNumBars = 8 + 2 * kKvStages + 2 * 9;
 constexpr int kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;
 static_assert(kKvStages >= 3 && kSmemBytes <= 232448, "K/V ring does not fit in shared memory");
@@ -195,15 +195,23 @@ struct Item {
   bool active1;      // the second query tile of the block exists
 };
 
-__device__ __forceinline__ Item decode_item(int item, int ordinal, const int* len_cache, int n_qblk, int n_head,
+// The work items of a CTA are decoded once, in parallel, at kernel start (item_cache): every role then reads 16 bytes of
+// shared memory per item instead of running four integer divisions on its critical path (the clock trace showed a
+// ~1000 clk bubble in the softmax warps at every item boundary).  CTAs with more than kLenCache items decode the rest here.
+__device__ __forceinline__ Item decode_item(int item, int ordinal, const int4* item_cache, int n_qblk, int n_head,
                                             int seq_len, const int* __restrict__ kv_len) {
   Item it;
-  const int qb = item % n_qblk;
-  const int bh = item / n_qblk;
-  it.h = bh % n_head;
-  it.b = bh / n_head;
-  it.q0 = qb * 2 * kQTile;
-  it.n_keys = min(max(ordinal < kLenCache ? len_cache[ordinal] : __ldg(kv_len + it.b), 1), seq_len);
+  if (ordinal < kLenCache) {
+    const int4 c = item_cache[ordinal];
+    it.b = c.x; it.h = c.y; it.q0 = c.z; it.n_keys = c.w;
+  } else {
+    const int qb = item % n_qblk;
+    const int bh = item / n_qblk;
+    it.h = bh % n_head;
+    it.b = bh / n_head;
+    it.q0 = qb * 2 * kQTile;
+    it.n_keys = min(max(__ldg(kv_len + it.b), 1), seq_len);
+  }
   it.n_kt = (it.n_keys + kKTile - 1) / kKTile;
   it.active1 = it.q0 + kQTile < seq_len;
   return it;
@@ -235,10 +243,14 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_slot = bars + 8u * kNumBars;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int* len_cache = reinterpret_cast<int*>(sptr + kOffLen);
+  int4* len_cache = reinterpret_cast<int4*>(sptr + kOffLen);
   for (int n = tid; n < kLenCache; n += kThreads) {
     const long long item = (long long)blockIdx.x + (long long)n * gridDim.x;
-    if (item < n_items) len_cache[n] = __ldg(kv_len + (int)(item / n_qblk) / n_head);
+    if (item < n_items) {
+      const int qb = (int)(item % n_qblk), bh = (int)(item / n_qblk);
+      const int b = bh / n_head;
+      len_cache[n] = make_int4(b, bh % n_head, qb * 2 * kQTile, min(max(__ldg(kv_len + b), 1), seq_len));
+    }
   }
   if (tid == 0) {
     prefetch_tmap(&tmap_q);
@@ -621,6 +633,13 @@ mha2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ordinal) {
       const Item it = decode_item(item, ordinal, len_cache, n_qblk, n_head, seq_len, kv_len);
       if (w == 1 && !it.active1) continue;
+#ifdef MHA2_OFFSET_ITEM
+      // Timing experiment: group 1 enters EVERY item MHA2_OFFSET_ITEM clocks late (the groups re-align at item boundaries)
+      if (w == 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < MHA2_OFFSET_ITEM) {}
+      }
+#endif
       // m_ref: the maximum the exponents are taken against.  It is only raised (and O / l rescaled) when the running
       // maximum exceeds it by more than 2^kRaise: P <= 2^kRaise stays far inside bf16 / fp32 range, and O in TMEM is
       // touched by the CUDA cores only on those rare steps.
