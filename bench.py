@@ -141,6 +141,7 @@ def work_table(size_cfg, batch, n_samples, kv_len_sum_sq_like):
     w = {
         "stac_fbank_logmel": ("hbm", batch * (4 * n_samples + 4 * 80 * t), 1),
         "stac_fbank_logmel_tc": ("hbm", batch * (4 * n_samples + 4 * 80 * t), 1),
+        "stac_fbank_logmel_tc2": ("hbm", batch * (4 * n_samples + 4 * 80 * t), 1),
         "stac_fbank_topdb_norm": ("hbm", batch * 2 * 4 * 80 * t, 1),
         "stac_conv0_ln_lrelu": ("hbm", batch * (4 * 80 * t + 2 * 40 * 256 * t1), 1),
         "stac_conv0_topdb_norm_bf16": ("hbm", batch * (4 * 80 * t + 2 * 40 * 256 * t1), 1),
@@ -1041,7 +1042,7 @@ def run_bucketed(args, rank, world, local_rank):
             t_ = sum(per[k][0] for k in keys if k in per)
             w_ = sum(work_sum[k][1] for k in keys if k in per)
             return t_, w_
-        t_f, w_f = agg(["stac_fbank_logmel_tc", "stac_fbank_logmel", "stac_fbank_topdb_norm"])
+        t_f, w_f = agg(["stac_fbank_logmel_tc2", "stac_fbank_logmel_tc", "stac_fbank_logmel", "stac_fbank_topdb_norm"])
         t_c, w_c = agg(["stac_conv1_bf16"])
         line["frontend_fractions"] = {
             "fbank_norm_hbm_frac": round(w_f / (t_f * 1e-3) / 1e9 / pk["hbm_gbs"], 4) if t_f else None,

@@ -75,6 +75,22 @@ int stac_fbank_logmel_tc(const float* pcm, int64_t batch, int64_t n_samples, int
                          const float* tables, const uint16_t* twiddles, float* logmel_db /*[B,T,80]*/,
                          uint32_t* utt_max_ordered /*[B]*/, void* stream);
 
+/* a2 on tensor cores, second design (the bf16 path's default): the same folded fp16 DFT GEMM, but the A operand is built
+ * in registers by a thread that owns one frame and written straight into tensor memory (TS-form tcgen05.mma); with
+ * pair != 0 two CTAs of a cluster form one cta_group::2 instance (2 x 128 frames, each CTA holds half of every twiddle
+ * tile), pair == 0 runs the same kernel per single CTA.  Same outputs as stac_fbank_logmel_tc.
+ *   tables:   stac_fbank_tc2_tables_floats() floats: per-bin mel weights [208][2]
+ *   twiddles: stac_fbank_tc2_twiddle_halfs() fp16: [7 stages][208 bins][64 columns]; columns 0-31 of stage i are
+ *             w[n] cos(2 pi k n / 400) and columns 32-63 -w[n] sin(2 pi k n / 400) for n = 32 i .. 32 i + 31 (w = the
+ *             hamming window, zero where n > 200); the kernel feeds them e[n] = x[n] + x[400 - n], o[n] = x[n] - x[400 - n]
+ *   n_samples must be a multiple of 32 (the PCM tile travels as tensor-map boxes of 32-sample rows): other lengths
+ *   return STAC_ERR_UNSUPPORTED_SHAPE and belong to stac_fbank_logmel_tc / stac_fbank_logmel. */
+int stac_fbank_tc2_tables_floats(void);
+int stac_fbank_tc2_twiddle_halfs(void);
+int stac_fbank_logmel_tc2(const float* pcm, int64_t batch, int64_t n_samples, int64_t pcm_row_stride,
+                          const float* tables, const uint16_t* twiddles, float* logmel_db /*[B,T,80]*/,
+                          uint32_t* utt_max_ordered /*[B]*/, int pair, void* stream);
+
 /* top-dB clamp (+ optional global mean/std normalisation, a3) in one elementwise pass:
  *   y = max(x, max_b - top_db);  if (mean) y = (y - mean[m]) / std[m]
  * per_utterance != 0: max_b is utterance b's maximum, else the maximum over the batch.

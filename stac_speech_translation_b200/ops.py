@@ -10,7 +10,7 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass, field
-from typing import List, Optional
+from typing import List, NamedTuple, Optional
 
 import torch
 
@@ -143,11 +143,18 @@ def build_fbank_tables(device) -> torch.Tensor:
 _FFT_TABLES = {}
 
 
-def build_fbank_tc_tables(device):
-    """Constants of the tensor-core Fbank kernel (layouts in include/stac_b200.h): (tables fp32, twiddles fp16).
-    Window and mel weights come from the same fp32 torch expressions SpeechBrain uses; the per-bin mel layout must
-    have the sparsity structure baked into csrc/fbank_mel_structure.h (checked here); twiddles are computed in
-    float64 and rounded to fp16 once."""
+class FbankTcTables(NamedTuple):
+    """Constants of the two tensor-core Fbank kernels (layouts in include/stac_b200.h)."""
+    tab: torch.Tensor      # fp32: window[400] | per-bin mel weights [208][2]                    (stac_fbank_logmel_tc)
+    tw: torch.Tensor       # fp16: [cos | sin][208 bins][256 columns]
+    tab2: torch.Tensor     # fp32: per-bin mel weights [208][2]                                  (stac_fbank_logmel_tc2)
+    tw2: torch.Tensor      # fp16: [7 stages][208 bins][64 columns: w[n] cos, n = 32 i .. + 31 | -w[n] sin, same n]
+
+
+def build_fbank_tc_tables(device) -> FbankTcTables:
+    """Constants of the tensor-core Fbank kernels.  Window and mel weights come from the same fp32 torch expressions
+    SpeechBrain uses; the per-bin mel layout must have the sparsity structure baked into csrc/fbank_mel_structure.h
+    (checked here); twiddles are computed in float64 and rounded to fp16 once."""
     window = torch.hamming_window(N_FFT)
     fb = mel_filter_matrix()                                   # [80, 201]
     wbin = torch.zeros(208, 2)
@@ -167,7 +174,27 @@ def build_fbank_tc_tables(device):
     tw[1, :201, :199] = -torch.sin(2 * math.pi * kk * n_sin / 400)
     tw = tw.to(torch.float16).reshape(2 * 208, 256).contiguous()
     assert tw.numel() == lib().stac_fbank_tc_twiddle_halfs()
-    return tab.to(device=device, dtype=torch.float32).contiguous(), tw.to(device)
+
+    # second kernel: the frame folded on its symmetry, e[n] = x[n] + x[400 - n] (cos side), o[n] = x[n] - x[400 - n] (sin
+    # side), n = 0..223 in 7 stages of 32 (n = 0 and n = 200 have no mirror partner, n > 200 does not exist: zero
+    # twiddle columns); the hamming window (symmetric, w[400 - n] = w[n]) is folded into the twiddles in float64
+    tab2 = wbin.flatten().clone()
+    assert tab2.numel() == lib().stac_fbank_tc2_tables_floats()
+    n_all = torch.arange(224, dtype=torch.float64)[None, :]
+    kk208 = torch.arange(208, dtype=torch.float64)[:, None]
+    w64 = torch.zeros(224, dtype=torch.float64)
+    w64[:201] = window[:201].double()
+    cos_t = torch.cos(2 * math.pi * kk208 * n_all / 400) * w64[None, :]        # [208, 224]
+    sin_t = -torch.sin(2 * math.pi * kk208 * n_all / 400) * w64[None, :]
+    cos_t[201:] = 0
+    sin_t[201:] = 0
+    sin_t[:, 200:] = 0
+    sin_t[:, 0] = 0
+    tw2 = torch.cat([cos_t.view(208, 7, 32), sin_t.view(208, 7, 32)], dim=2).permute(1, 0, 2)   # [7, 208, 64]
+    tw2 = tw2.to(torch.float16).reshape(7 * 208, 64).contiguous()
+    assert tw2.numel() == lib().stac_fbank_tc2_twiddle_halfs()
+    return FbankTcTables(tab.to(device=device, dtype=torch.float32).contiguous(), tw.to(device),
+                         tab2.to(device=device, dtype=torch.float32).contiguous(), tw2.to(device))
 
 
 @dataclass
@@ -189,10 +216,9 @@ def fbank_tc(wavs: torch.Tensor, tc_tables, top_db: float = 80.0, per_utterance:
     if wavs.dim() != 2:
         raise _lib.StacB200Error("Fbank expects [batch, samples] waveforms")
     wavs = wavs.contiguous()
-    tab, tw = tc_tables
     b, n = wavs.shape
     if n % 4 != 0 or wavs.data_ptr() % 16 != 0:
-        # the tensor-core kernel moves PCM tiles with 16-byte bulk copies; odd lengths take the exact FFT kernel
+        # the tensor-core kernels move PCM tiles with 16-byte bulk copies; odd lengths take the exact FFT kernel
         key = str(wavs.device)
         if key not in _FFT_TABLES:
             _FFT_TABLES[key] = build_fbank_tables(wavs.device)
@@ -200,8 +226,15 @@ def fbank_tc(wavs: torch.Tensor, tc_tables, top_db: float = 80.0, per_utterance:
     t = 1 + n // HOP
     db = torch.empty(b, t, N_MELS, device=wavs.device, dtype=torch.float32)
     umax = torch.empty(b, device=wavs.device, dtype=torch.int32)      # zeroed by the call (stream-ordered memset)
-    _call("stac_fbank_logmel_tc", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tab), ptr(tw, torch.float16),
-          ptr(db), ptr(umax), stream())
+    if os.environ.get("STAC_FBANK_V2", "1") != "0" and n % 32 == 0:
+        # second design (A operand in tensor memory, cta_group::2 pairs; PCM tiles as tensor-map boxes of 32-sample rows,
+        # hence the multiple of 32); STAC_FBANK_PAIR=0: the same kernel per single CTA
+        _call("stac_fbank_logmel_tc2", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tc_tables.tab2),
+              ptr(tc_tables.tw2, torch.float16), ptr(db), ptr(umax),
+              int(os.environ.get("STAC_FBANK_PAIR", "1") != "0"), stream())
+    else:
+        _call("stac_fbank_logmel_tc", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tc_tables.tab),
+              ptr(tc_tables.tw, torch.float16), ptr(db), ptr(umax), stream())
     if raw:
         return RawFeatures(db, umax, float(top_db), bool(per_utterance), mean, std)
     _call("stac_fbank_topdb_norm", ptr(db), ptr(umax), int(per_utterance), float(top_db), ptr(mean), ptr(std),

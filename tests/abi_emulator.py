@@ -242,6 +242,44 @@ class Emulator:
             u = np.float32(db[b].max()).view(np.uint32)
             umax[b] = (~u & 0xffffffff) if (u & 0x80000000) else (u | 0x80000000)
 
+    def stac_fbank_logmel_tc2(self, pcm, batch, n_samples, row_stride, tables, twiddles, logmel_db, utt_max_ordered,
+                              pair, stream):
+        """The second tensor-core kernel, arithmetic as the kernel does it: the frame folded on its symmetry, rounded to
+        fp16, multiplied stage by stage with the windowed twiddle tiles the host built (so their layout is what is under
+        test), fp32-like accumulation, power, mel with the per-bin weights."""
+        from stac_speech_translation_b200 import ops
+        assert pair in (0, 1)
+        wbin = _arr(tables, 208 * 2).reshape(208, 2).astype(np.float64)
+        tw = _tarr(twiddles, 7 * 208 * 64, torch.float16).double().view(7, 208, 64).numpy()
+        fb = ops.mel_filter_matrix().numpy()
+        frames = 1 + n_samples // 160
+        x = _arr(pcm, (batch - 1) * row_stride + n_samples)
+        db = _arr(logmel_db, batch * frames * 80).reshape(batch, frames, 80)
+        umax = _arr(utt_max_ordered, batch, np.uint32)
+        n = np.arange(224)
+        for b in range(batch):
+            sig = np.concatenate([np.zeros(200, np.float32), x[b * row_stride: b * row_stride + n_samples],
+                                  np.zeros(1024, np.float32)])
+            start = np.arange(frames)[:, None] * 160
+            a = sig[start + n[None, :]]
+            m = sig[start + (400 - n)[None, :]]
+            lone = (n == 0) | (n == 200)                        # no mirror partner
+            e = np.where(lone[None, :], a, a + m).astype(np.float16).astype(np.float64)
+            o = (a - m).astype(np.float16).astype(np.float64)
+            re = np.zeros((frames, 208))
+            im = np.zeros((frames, 208))
+            for i in range(7):
+                re += e[:, 32 * i: 32 * i + 32] @ tw[i, :, :32].T
+                im += o[:, 32 * i: 32 * i + 32] @ tw[i, :, 32:].T
+            power = re ** 2 + im ** 2
+            mel = np.zeros((frames, 80))
+            for k in range(201):
+                for j, mm in enumerate(np.nonzero(fb[:, k] > 0)[0]):
+                    mel[:, mm] += power[:, k] * wbin[k, j]
+            db[b] = (10.0 * np.log10(np.maximum(mel, 1e-10))).astype(np.float32)
+            u = np.float32(db[b].max()).view(np.uint32)
+            umax[b] = (~u & 0xffffffff) if (u & 0x80000000) else (u | 0x80000000)
+
     def stac_conv1_bf16(self, xpad, w1, b1, ln_g, ln_b, batch, t1, out, stream):
         t2, tp2 = (t1 - 1) // 2 + 1, (t1 + 3) // 2
         planes = _tarr(xpad, batch * 4 * tp2 * 21 * 256, torch.bfloat16).double().view(batch, 4, tp2, 21, 256).numpy()

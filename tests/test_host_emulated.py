@@ -295,7 +295,7 @@ def test_bf16_path_host_orchestration_against_the_oracle(monkeypatch, mha_v2, ti
     assert rel_l2(res["enc_out"], want["enc_out"]) < BF16_TOL and rel_l2(res["p_ctc"], want["p_ctc"]) < BF16_TOL
     assert (res["greedy"].long() == res["p_ctc"].argmax(-1)).all()
     assert ("stac_mha_bf16_v2" if mha_v2 else "stac_mha_bf16") in emu.calls
-    assert {"stac_fbank_logmel_tc", "stac_conv1_bf16", "stac_ctc_head_bf16"} <= set(emu.calls)
+    assert {"stac_fbank_logmel_tc2", "stac_conv1_bf16", "stac_ctc_head_bf16"} <= set(emu.calls)
     assert ("stac_ffn_fused_bf16" in emu.calls) == (not tiny)
     n_layers = len(mods["Transformer"].packed().layers)
     assert emu.calls.count("stac_layernorm") == 2 * n_layers + 1
@@ -337,3 +337,24 @@ def test_structured_custom_ops_equal_the_pipeline(monkeypatch):
     ctc = mods["ctc_lin"]
     p, ids = ns.ctc_head(enc.to(torch.bfloat16), ctc.packed_weight(), ctc.w.bias.detach().float().contiguous())
     assert rel_l2(p, res["p_ctc"]) < 2e-2 and p.shape == res["p_ctc"].shape and ids.shape == res["greedy"].shape
+
+
+@pytest.mark.parametrize("n", [160 * 3, 16000 + 32, 160 * 129 + 96])
+def test_fbank_tc2_tables_against_the_oracle(monkeypatch, n):
+    """Tables of the second tensor-core Fbank kernel (fold factors wa / wb, the 7 twiddle tiles [208 x (cos 32 | sin 32)])
+    through an emulation that does the kernel's arithmetic with exactly those tables: log-mel equal to the oracle's Fbank
+    and to the first kernel's formulation at the fp16-operand tolerance (1e-3, as the GPU test asserts)."""
+    from stac_speech_translation_b200 import ops, synth
+    from util import oracle_modules
+    abi_emulator.install(monkeypatch)
+    omods = oracle_modules("S", num_encoder_layers=1, vocab=64)
+    wavs, _ = synth.synth_batch([n / 16000.0, max(0.03, 0.61 * n / 16000.0)], seed=n)
+    wavs = wavs[:, :n].contiguous()
+    ref = omods["compute_features"](wavs)
+    tabs = ops.build_fbank_tc_tables("cpu")
+    assert tabs.tab2.numel() == 416 and tuple(tabs.tw2.shape) == (7 * 208, 64)
+    got2 = ops.fbank_tc(wavs, tabs)
+    monkeypatch.setenv("STAC_FBANK_V2", "0")
+    got1 = ops.fbank_tc(wavs, tabs)
+    assert got2.shape == ref.shape
+    assert rel_l2(got2, ref) < 1e-3 and rel_l2(got1, ref) < 1e-3 and rel_l2(got2, got1) < 1e-3
