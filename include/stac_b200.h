@@ -281,6 +281,26 @@ int stac_pcm_i16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream)
 int stac_utt_mean_std(const float* x, const float* wav_len, int64_t batch, int64_t frames, int64_t dim, float eps,
                       float* mean, float* std, void* stream);
 
+/* 8f-4, training-stage pieces on the path's tensors.
+ * stac_spec_augment: SpeechBrain's SpecAugment (`feats = self.hparams.augmentation(feats)`,
+ *        /root/reference/stac-st/train_multitask.py:63-66, yaml transformer_multitask.yaml:283-293) in one pass: bicubic
+ *        time warp (rows [0, warp_width) = rows [0, warp_center) resampled, rows [warp_width, frames) = rows
+ *        [warp_center, frames) resampled, align_corners; warp_width < 0: none), then frequency / time masks
+ *        [pos, pos + len) per utterance filled with `fill`.  x, out [batch, frames, dim] fp32 (out != x);
+ *        freq_pos / freq_len int32 [batch, n_freq], time_pos / time_len int32 [batch, n_time].  The random parameters are
+ *        the host's (augment.SpecAugment draws them in SpeechBrain's order).
+ * stac_ctc_loss: speechbrain.nnet.losses.ctc_loss (`self.hparams.ctc_cost(p_ctc, tokens, wav_lens, tokens_lens)`,
+ *        train_multitask.py:164-170, yaml :256-258) = torch.nn.functional.ctc_loss(zero_infinity=True): forward value.
+ *        log_probs [batch, frames, vocab] fp32, targets int32 [batch, max_targets], input_len / target_len int32 [batch]
+ *        (absolute), nll fp32 [batch] (always written), loss: reduction 0 none (untouched), 1 sum, 2 mean (torch:
+ *        per-target-length then batch mean), 3 batchmean (sum / batch), 4 batch (fp32 [batch]: nll / target_len). */
+int stac_spec_augment(const float* x, int64_t batch, int64_t frames, int64_t dim, int warp_center, int warp_width,
+                      const int32_t* freq_pos, const int32_t* freq_len, int n_freq, const int32_t* time_pos,
+                      const int32_t* time_len, int n_time, float fill, float* out, void* stream);
+int stac_ctc_loss(const float* log_probs, const int32_t* targets, const int32_t* input_len, const int32_t* target_len,
+                  int64_t batch, int64_t frames, int64_t vocab, int64_t max_targets, int blank, int reduction,
+                  float* nll, float* loss, void* stream);
+
 /* a7, bf16 mode, d_model = 256: attention output projection + residual add + the LayerNorm that follows, one kernel
  *        (north_star's "fused LayerNorm"; replaces `src = src + dropout1(self_att(...))` and `norm2(src)` of SpeechBrain's
  *        pre-LN TransformerEncoderLayer, reached from /root/reference/stac-st/modules/TransformerMultiTask.py:304-308):

@@ -9,6 +9,8 @@ from .features import Fbank, InputNormalization  # noqa: F401
 from .convolution import ConvolutionFrontEnd  # noqa: F401
 from .transformer import TransformerMultiTask, EncoderWrapper  # noqa: F401
 from .linear import Linear, LogSoftmax  # noqa: F401
+from .augment import SpecAugment  # noqa: F401
+from .losses import ctc_loss  # noqa: F401
 from .pipeline import (  # noqa: F401
     HParams, MODEL_SIZES, build_modules, compute_forward, EncoderPipeline, GraphedPipeline, ctc_greedy_collapse,
 )
@@ -16,5 +18,5 @@ from .pipeline import (  # noqa: F401
 __all__ = [
     "Fbank", "InputNormalization", "ConvolutionFrontEnd", "TransformerMultiTask", "EncoderWrapper",
     "Linear", "LogSoftmax", "HParams", "MODEL_SIZES", "build_modules", "compute_forward",
-    "EncoderPipeline", "GraphedPipeline", "ctc_greedy_collapse", "StacB200Error",
+    "EncoderPipeline", "GraphedPipeline", "ctc_greedy_collapse", "StacB200Error", "SpecAugment", "ctc_loss",
 ]

@@ -33,6 +33,8 @@ _SIGNATURES = {
     "stac_fbank_tc2_tables_floats": (c_int, []),
     "stac_fbank_tc2_twiddle_halfs": (c_int, []),
     "stac_fbank_logmel_tc2": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int, _P]),
+    "stac_spec_augment": (c_int, [_P, c_int64, c_int64, c_int64, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_float, _P, _P]),
+    "stac_ctc_loss": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int, c_int, _P, _P, _P]),
     "stac_fbank_topdb_norm": (c_int, [_P, _P, c_int, c_float, _P, _P, c_int64, c_int64, c_int64, _P, _P]),
     "stac_input_norm": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P]),
     "stac_conv0_padded_elems": (c_int64, [c_int64, c_int64]),

@@ -26,7 +26,7 @@
 // 10 log10 via lg2, row maximum, rows staged and written coalesced; warps 0-3 own mel filters 0-59 = DFT bins 0-99,
 // warps 4-7 filters 60-79 = bins 96-200: no filter straddles the cut, so the two halves never talk and the time the
 // single-buffered accumulators are held halves), 8-15 A producers (TMEM lane quadrant warp % 4; warps 8-11 build
-// columns 0-15 of every stage, 12-15 columns 16-31), 16 twiddle TMA, 17 PCM loader, 18 TMEM allocation + MMA issue,
+// the even stages, 12-15 the odd ones), 16 twiddle TMA, 17 PCM loader, 18 TMEM allocation + MMA issue,
 // 19 idle (register reallocation works on groups of four warps).
 // First version of this file (one bulk copy per 160-sample segment into a padded layout, cluster-scope release on the
 // remote arrives): correct on its first run and exactly as slow as the first kernel - 130 bulk copies took 8-10 k clk per
@@ -65,7 +65,7 @@ constexpr int kMelCut = 60;                                   // epilogue warps 
 constexpr int kCutChunkA = 13, kCutChunkB = 12;               // ... = 8-bin chunks [0, 13) (bins 0-103) and [12, 25) (96-199)
 // launch: 640 threads x 96 registers = 61 440, which is also the pool setmaxnreg redistributes (NOT the SM's 65 536: an
 // increase beyond what the CTA was launched with blocks for ever): 256 x 144 (epilogue) + 256 x 80 (producers) + 128 x 32
-constexpr int kRegsEpi = 144, kRegsProd = 80, kRegsCtl = 32;
+constexpr int kRegsEpi = 136, kRegsProd = 88, kRegsCtl = 32;
 static_assert(256 * kRegsEpi + 256 * kRegsProd + 128 * kRegsCtl <= kThreads * 96, "register pool");
 constexpr int kNumBars = 2 * kASlots + 2 * kBSlots + 2 + 4;
 constexpr int kTabFloats = 2 * kBins;                         // per-bin mel weights [208][2]
@@ -193,33 +193,33 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return y;
 }
 
-// 16 bytes holding frame sample n (n + kLead a multiple of 4; n compile-time) of the frame whose first row is r5 = 5 r:
-// row q of the tile keeps its 16-byte piece p at piece p ^ (q & 7) (TMA SWIZZLE_128B)
-template <int N>
-__device__ __forceinline__ const unsigned char* pcm_piece(const unsigned char* buf, int r5) {
-  constexpr int q = N + kLead, R = q >> 5, P = (q & 31) >> 2;
-  const int row = r5 + R;
+// 16 bytes holding tile sample Q + 32 * (rowb - 5 r) of the frame that starts at row 5 r (Q compile-time, a multiple of
+// 4): row q of the tile keeps its 16-byte piece p at piece p ^ (q & 7) (TMA SWIZZLE_128B).  The stage index only moves
+// whole rows (32 samples per stage), so it travels in rowb and the stage loop needs no unrolling.
+template <int Q>
+__device__ __forceinline__ const unsigned char* pcm_piece(const unsigned char* buf, int rowb) {
+  constexpr int R = Q >> 5, P = (Q & 31) >> 2;
+  const int row = rowb + R;
   return buf + row * 128 + ((P ^ (row & 7)) << 4);
 }
 
-// ---- A producer: one stage half = 16 columns n0 .. n0 + 15 of e and o for this thread's frame ----
+// ---- A producer: one stage half = 16 columns n0 .. n0 + 15 (n0 = 32 i + 16 HH) of e and o for this thread's frame ----
 struct StageRegs {
   float4 a[4], b[4];
   float carry;
 };
-template <int N0, int J = 0>
-__device__ __forceinline__ void stage_load(const unsigned char* buf, int r5, StageRegs& r) {
+template <int HH, int J = 0>
+__device__ __forceinline__ void stage_load(const unsigned char* buf, int r5, int i, StageRegs& r) {
   if constexpr (J < 4) {
-    r.a[J] = *reinterpret_cast<const float4*>(pcm_piece<N0 + 4 * J>(buf, r5));          // x[n0 + 4 j .. + 3]
-    r.b[J] = *reinterpret_cast<const float4*>(pcm_piece<396 - N0 - 4 * J>(buf, r5));    // x[396 - n0 - 4 j .. + 3]
-    stage_load<N0, J + 1>(buf, r5, r);
+    r.a[J] = *reinterpret_cast<const float4*>(pcm_piece<kLead + 16 * HH + 4 * J>(buf, r5 + i));         // x[n0 + 4 j .. + 3]
+    r.b[J] = *reinterpret_cast<const float4*>(pcm_piece<kLead + 396 - 16 * HH - 4 * J>(buf, r5 - i));   // x[396 - n0 - 4 j ..]
+    stage_load<HH, J + 1>(buf, r5, i, r);
   } else {
-    // x[400 - n0]; n = 0 has no mirror
-    if constexpr (N0 > 0) r.carry = *reinterpret_cast<const float*>(pcm_piece<400 - N0>(buf, r5)); else r.carry = 0.f;
+    r.carry = *reinterpret_cast<const float*>(pcm_piece<kLead + 400 - 16 * HH>(buf, r5 - i));           // x[400 - n0]
   }
 }
-template <int N0>
-__device__ __forceinline__ void stage_fold(const StageRegs& r, uint32_t (&ev)[8], uint32_t (&ov)[8]) {
+template <int HH>
+__device__ __forceinline__ void stage_fold(const StageRegs& r, int i, uint32_t (&ev)[8], uint32_t (&ov)[8]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float av[4] = {r.a[j].x, r.a[j].y, r.a[j].z, r.a[j].w};
@@ -228,10 +228,12 @@ __device__ __forceinline__ void stage_fold(const StageRegs& r, uint32_t (&ev)[8]
     float e[4], o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int n = N0 + 4 * j + k;                       // compile-time after unrolling
-      // the window lives in the twiddles (w[n] cos, -w[n] sin); n = 0 and n = 200 have no mirror partner; columns
-      // n > 200 meet zero twiddle rows and only have to be finite
-      e[k] = (n == 0 || n == 200) ? av[k] : av[k] + bv[k];
+      // the window lives in the twiddles (w[n] cos, -w[n] sin); n = 0 and n = 200 have no mirror partner (their sine
+      // twiddles are zero, so o only has to be finite); columns n > 200 meet zero twiddle rows
+      float m = bv[k];
+      if (HH == 0 && j == 0 && k == 0) m = i == 0 ? 0.f : m;                 // n = 0
+      if (HH == 0 && j == 2 && k == 0) m = i == kStages - 1 ? 0.f : m;       // n = 200
+      e[k] = av[k] + m;
       o[k] = av[k] - bv[k];
     }
     ev[2 * j] = pack_f16x2(e[0], e[1]);
@@ -327,7 +329,7 @@ fbank_tc2_kernel(const __grid_constant__ CUtensorMap tmap_tw, const __grid_const
   if (tid == 0) {
     prefetch_tmap(&tmap_tw);
     prefetch_tmap(&tmap_pcm);
-    for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), kProdWarps * C::kCtas); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < kASlots; ++s) { mbar_init(a_full(s), (kProdWarps / 2) * C::kCtas); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < kBSlots; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, kEpiWarps * C::kCtas);
@@ -352,77 +354,59 @@ fbank_tc2_kernel(const __grid_constant__ CUtensorMap tmap_tw, const __grid_const
     const int r = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t a_full_remote0 = leader_bar(a_full(0));
-    auto run = [&](auto H) {
-      constexpr int h = decltype(H)::value;               // 0: columns 0-15 of every stage, 1: columns 16-31
-      int slot = 0;
-      uint32_t phase = 0;
+    // this warp builds the stages i with i % 2 == half, all 32 columns (the stage loop is a real loop: the first version
+    // unrolled all seven stages, and a quarter of the kernel's stall samples were instruction fetch)
+    {
       int tn = 0;
-      int pending = -1;                                    // slot whose tcgen05.st are in flight and not yet announced
-      // A stage's TMEM stores are announced one stage late: the next stage's loads and arithmetic run while they land
-      auto announce = [&]() {
-        if (pending >= 0) {
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (kPair) mbar_arrive_remote(a_full_remote0 + 8u * pending); else mbar_arrive(a_full(pending));
-          }
-        }
-      };
       for (int ut = unit; ut < unit_tiles; ut += n_units, ++tn) {
         const int buf = tn % C::kPcmBufs;
         const unsigned char* pbuf = sptr + C::kOffPcm + buf * kPcmBufBytes;
         mbar_wait(pcm_full(buf), (uint32_t)(tn / C::kPcmBufs) & 1);
         if (tid == kEpiWarps * 32) BTRACE(0, 0, tn);
-        auto stage = [&](auto I) {
-          constexpr int i = decltype(I)::value;
-#ifdef FB2_NO_BUILD       // timing experiment: no loads, no arithmetic, no TMEM stores
-          constexpr bool work = false;
-#else
-          constexpr bool work = (i < kStages - 1) || h == 0;      // the last stage holds 16 real columns
-#endif
-          constexpr int n0 = work ? 32 * i + 16 * h : 0;
-          uint32_t ev[8], ov[8];
-          if constexpr (work) {
+#pragma unroll 1
+        for (int i = half; i < kStages; i += 2) {
+          const int g = kStages * tn + i;                   // running stage count: ring slot and its parity
+          const int slot = g % kASlots;
+          const uint32_t phase = (uint32_t)(g / kASlots) & 1;
+          // fold first (the PCM tile is there), then wait for the slot: the other warp set is doing the same for the
+          // neighbouring stage, so the store / announce latency of one stage hides behind the other's
+          uint32_t ev[2][8], ov[2][8];
+#ifndef FB2_NO_BUILD      // timing experiment: no loads, no arithmetic, no TMEM stores
+          {
             StageRegs regs;
-            stage_load<n0>(pbuf, 5 * r, regs);
-            stage_fold<n0>(regs, ev, ov);
+            stage_load<0>(pbuf, 5 * r, i, regs);
+            stage_fold<0>(regs, i, ev[0], ov[0]);
+            if (i < kStages - 1) {                          // the last stage holds 16 real columns
+              stage_load<1>(pbuf, 5 * r, i, regs);
+              stage_fold<1>(regs, i, ev[1], ov[1]);
+            }
           }
-          if (i == 1 && tid == kEpiWarps * 32) BTRACE(0, 8, tn);
-          announce();
-          if (i == 1 && tid == kEpiWarps * 32) BTRACE(0, 9, tn);
+#endif
+          if (i == 2 && tid == kEpiWarps * 32) BTRACE(0, 8, tn);
           mbar_wait(a_empty(slot), phase ^ 1);
           tc_fence_after();
-          if (i == 1 && tid == kEpiWarps * 32) BTRACE(0, 10, tn);
-          if constexpr (work) {
-#ifndef FB2_NO_STTM       // timing experiment: the A operand is computed but not written
-            tmem_st8(tmem_base + lane_off + a_half_col(2 * slot) + 8u * h, ev);
-            tmem_st8(tmem_base + lane_off + a_half_col(2 * slot + 1) + 8u * h, ov);
-#else
-            uint32_t x = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x ^= ev[j] ^ ov[j];
-            if (x == 0x12345678u) reinterpret_cast<volatile uint32_t*>(sptr + C::kOffOut)[tid] = x;
-#endif
+          if (i == 2 && tid == kEpiWarps * 32) BTRACE(0, 9, tn);
+#ifndef FB2_NO_BUILD
+          const uint32_t e_addr = tmem_base + lane_off + a_half_col(2 * slot), o_addr = tmem_base + lane_off + a_half_col(2 * slot + 1);
+          tmem_st8(e_addr, ev[0]);
+          tmem_st8(o_addr, ov[0]);
+          if (i < kStages - 1) {
+            tmem_st8(e_addr + 8u, ev[1]);
+            tmem_st8(o_addr + 8u, ov[1]);
           }
-          pending = slot;
+          tmem_st_wait();
+#endif
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kPair) mbar_arrive_remote(a_full_remote0 + 8u * slot); else mbar_arrive(a_full(slot));
+          }
           if (tid == kEpiWarps * 32) BTRACE(0, 1 + i, tn);
-          if (++slot == kASlots) { slot = 0; phase ^= 1; }
-        };
-        stage(std::integral_constant<int, 0>{});
-        stage(std::integral_constant<int, 1>{});
-        stage(std::integral_constant<int, 2>{});
-        stage(std::integral_constant<int, 3>{});
-        stage(std::integral_constant<int, 4>{});
-        stage(std::integral_constant<int, 5>{});
-        stage(std::integral_constant<int, 6>{});
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(pcm_free(buf));           // this warp no longer reads the PCM tile
-        announce();                                          // the tile's last stage must not wait for the next tile's PCM
-        pending = -1;
       }
-    };
-    if (half == 0) run(std::integral_constant<int, 0>{}); else run(std::integral_constant<int, 1>{});
+    }
   } else if (warp >= kWarpB) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
     if (warp == kWarpPcm) {

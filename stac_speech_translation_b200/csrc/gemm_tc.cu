@@ -597,28 +597,42 @@ extern "C" int stac_gemm_bf16(const uint16_t* a, const uint16_t* w, const float*
 }
 
 namespace {
-// CTC head, between the two GEMM passes: combine the per-group statistics of every row
+// CTC head, between the two GEMM passes: combine the per-group statistics of every row.  One CTA = 32 rows, the groups
+// dealt over its 8 warps (a thread per row was 188 CTAs of long dependent load chains: 34 us for 45 MB), the 8 partial
+// (max, sum) pairs of a row merged through shared memory.
 __global__ void __launch_bounds__(256)
 ctc_reduce_kernel(const float* __restrict__ stats, int64_t plane, int n_groups, int64_t m, float* __restrict__ lse,
                   float* __restrict__ row_max, int* __restrict__ argmax) {
-  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (row >= m) return;
-  // two passes of independent, coalesced loads (a single online pass is one long dependent chain per row)
-  const float* pm = stats + row;
-  float mx = -INFINITY;
-#pragma unroll 8
-  for (int g = 0; g < n_groups; ++g) mx = fmaxf(mx, __ldg(pm + (int64_t)g * m));
-  float s0 = 0.f, s1 = 0.f;
-  int g = 0;
+  __shared__ float part_m[8][33], part_s[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * 32 + lane;
+  float mx = -INFINITY, s = 0.f;
+  if (row < m) {
+    // two passes of independent, coalesced loads (a single online pass is one long dependent chain per row)
+    const float* pm = stats + row;
 #pragma unroll 4
-  for (; g + 1 < n_groups; g += 2) {
-    s0 = fmaf(__ldg(pm + plane + (int64_t)g * m), __expf(__ldg(pm + (int64_t)g * m) - mx), s0);
-    s1 = fmaf(__ldg(pm + plane + (int64_t)(g + 1) * m), __expf(__ldg(pm + (int64_t)(g + 1) * m) - mx), s1);
+    for (int g = w; g < n_groups; g += 8) mx = fmaxf(mx, __ldg(pm + (int64_t)g * m));
+#pragma unroll 4
+    for (int g = w; g < n_groups; g += 8)
+      s = fmaf(__ldg(pm + plane + (int64_t)g * m), __expf(__ldg(pm + (int64_t)g * m) - mx), s);
   }
-  if (g < n_groups) s0 = fmaf(__ldg(pm + plane + (int64_t)g * m), __expf(__ldg(pm + (int64_t)g * m) - mx), s0);
-  lse[row] = mx + logf(s0 + s1);
-  row_max[row] = mx;
-  if (argmax) argmax[row] = 0x7fffffff;
+  part_m[w][lane] = mx;
+  part_s[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && row < m) {
+    float big = part_m[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) big = fmaxf(big, part_m[k][lane]);
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float pk = part_m[k][lane];
+      if (pk != -INFINITY) tot = fmaf(part_s[k][lane], __expf(pk - big), tot);     // a warp without groups holds -inf
+    }
+    lse[row] = big + logf(tot);
+    row_max[row] = big;
+    if (argmax) argmax[row] = 0x7fffffff;
+  }
 }
 }  // namespace
 
@@ -640,7 +654,7 @@ extern "C" int stac_ctc_head_bf16(const uint16_t* enc, const uint16_t* w, const 
   ep.stats = workspace; ep.stats_plane = plane;
   int r = launch_linear(enc, w, log_probs, out_dtype, m, vocab, d_model, ep, stream);   // pass 1: statistics only
   if (r != STAC_OK) return r;
-  ctc_reduce_kernel<<<(unsigned)ceil_div64(m, 256), 256, 0, as_stream(stream)>>>(workspace, plane, (int)n_groups, m,
+  ctc_reduce_kernel<<<(unsigned)ceil_div64(m, 32), 256, 0, as_stream(stream)>>>(workspace, plane, (int)n_groups, m,
                                                                                 lse, row_max, argmax);
   if (cudaPeekAtLastError() != cudaSuccess) return (int)cudaGetLastError();
   EpiParams ep2{};

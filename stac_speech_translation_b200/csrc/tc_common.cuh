@@ -56,16 +56,20 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (launch failure) after ~2 s instead of a hung GPU.
+// Bounded wait: a protocol bug becomes a trap (launch failure) after ~2 s instead of a hung GPU.  The report lives in
+// its own function: inlined, the printf argument set-up sat in the middle of every kernel's hot loops (tens of
+// instructions per wait), and instruction fetch is a measurable cost of the warp-specialised kernels.
+static __device__ __noinline__ __attribute__((noreturn)) void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("stac_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
+         (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  // 32-bit clock: the difference is exact modulo 2^32 (~2.2 s), "more than half a period" is the time-out
+  const uint32_t t0 = (uint32_t)clock();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 32)) {
-      printf("stac_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n",
-             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
+    if ((uint32_t)clock() - t0 > 0x80000000u) { mbar_timeout(bar, parity); __trap(); }
   }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {

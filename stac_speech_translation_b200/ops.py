@@ -227,8 +227,9 @@ def fbank_tc(wavs: torch.Tensor, tc_tables, top_db: float = 80.0, per_utterance:
     db = torch.empty(b, t, N_MELS, device=wavs.device, dtype=torch.float32)
     umax = torch.empty(b, device=wavs.device, dtype=torch.int32)      # zeroed by the call (stream-ordered memset)
     if os.environ.get("STAC_FBANK_V2", "1") != "0" and n % 32 == 0:
-        # second design (A operand in tensor memory, cta_group::2 pairs; PCM tiles as tensor-map boxes of 32-sample rows,
-        # hence the multiple of 32); STAC_FBANK_PAIR=0: the same kernel per single CTA
+        # second design (A operand in tensor memory; PCM tiles as tensor-map boxes of 32-sample rows, hence the multiple
+        # of 32) as two-CTA cta_group::2 instances (63.5 us at the benchmark shape); STAC_FBANK_PAIR=0: the same kernel
+        # per single CTA (67.6 us)
         _call("stac_fbank_logmel_tc2", ptr(wavs, torch.float32), b, n, wavs.stride(0), ptr(tc_tables.tab2),
               ptr(tc_tables.tw2, torch.float16), ptr(db), ptr(umax),
               int(os.environ.get("STAC_FBANK_PAIR", "1") != "0"), stream())

@@ -406,6 +406,46 @@ class Emulator:
             _arr(mean, batch * dim).reshape(batch, dim)[b] = seg.mean(0)
             _arr(std, batch * dim).reshape(batch, dim)[b] = np.maximum(seg.std(0, ddof=1), eps)
 
+    def stac_spec_augment(self, x, batch, frames, dim, warp_center, warp_width, freq_pos, freq_len, n_freq, time_pos,
+                          time_len, n_time, fill, out, stream):
+        """From the C-ABI documentation: rows [0, w) = rows [0, c) resampled, rows [w, T) = rows [c, T) resampled (bicubic,
+        align_corners), then the [pos, pos + len) masks - with torch's own interpolate as the resampler."""
+        import torch.nn.functional as F
+        xx = _tarr(x, batch * frames * dim, torch.float32).view(batch, 1, frames, dim).clone()
+        if warp_width >= 0:
+            c, w = warp_center, warp_width
+            xx = torch.cat([F.interpolate(xx[:, :, :c], (w, dim), mode="bicubic", align_corners=True),
+                            F.interpolate(xx[:, :, c:], (frames - w, dim), mode="bicubic", align_corners=True)], 2)
+        xx = xx.view(batch, frames, dim)
+        for pos, ln, n, axis in ((freq_pos, freq_len, n_freq, 2), (time_pos, time_len, n_time, 1)):
+            if n == 0:
+                continue
+            pp, ll = _arr(pos, batch * n, np.int32).reshape(batch, n), _arr(ln, batch * n, np.int32).reshape(batch, n)
+            for b in range(batch):
+                for j in range(n):
+                    if axis == 2:
+                        xx[b, :, pp[b, j]: pp[b, j] + ll[b, j]] = fill
+                    else:
+                        xx[b, pp[b, j]: pp[b, j] + ll[b, j], :] = fill
+        _tarr(out, batch * frames * dim, torch.float32)[:] = xx.flatten()
+
+    def stac_ctc_loss(self, log_probs, targets, input_len, target_len, batch, frames, vocab, max_targets, blank,
+                      reduction, nll, loss, stream):
+        import torch.nn.functional as F
+        lp = _tarr(log_probs, batch * frames * vocab, torch.float32).view(batch, frames, vocab)
+        tg = _tarr(targets, batch * max_targets, torch.int32).view(batch, max_targets).long()
+        il, tl = _tarr(input_len, batch, torch.int32).long(), _tarr(target_len, batch, torch.int32).long()
+        per = F.ctc_loss(lp.transpose(0, 1), tg, il, tl, blank, reduction="none", zero_infinity=True)
+        _tarr(nll, batch, torch.float32)[:] = per
+        if reduction == 1:
+            _tarr(loss, 1, torch.float32)[0] = per.sum()
+        elif reduction == 2:
+            _tarr(loss, 1, torch.float32)[0] = (per / tl.clamp(min=1)).mean()
+        elif reduction == 3:
+            _tarr(loss, 1, torch.float32)[0] = per.sum() / batch
+        elif reduction == 4:
+            _tarr(loss, batch, torch.float32)[:] = per / tl
+
     def stac_input_norm(self, x, mean, std, rows, dim, out, stream):
         _arr(out, rows * dim).reshape(rows, dim)[:] = (_arr(x, rows * dim).reshape(rows, dim) - _arr(mean, dim)) / _arr(std, dim)
 
@@ -449,12 +489,12 @@ def cpu_ptr(t, dtype=None):
 
 def install(monkeypatch):
     """Route the host orchestration's kernel calls to the emulator (CPU tensors)."""
-    from stac_speech_translation_b200 import decoder, ingest, ops, turns
+    from stac_speech_translation_b200 import augment, decoder, ingest, losses, ops, turns
     emu = Emulator()
-    for mod in (ops, decoder, turns, ingest):
+    for mod in (ops, decoder, turns, ingest, augment, losses):
         monkeypatch.setattr(mod, "ptr", cpu_ptr)
         monkeypatch.setattr(mod, "stream", lambda: c_void_p(0))
-    for mod in (turns, ingest):
+    for mod in (turns, ingest, augment, losses):
         monkeypatch.setattr(mod, "lib", lambda: EmuLib(emu))
     monkeypatch.setattr(ops, "_call", emu.call)
     return emu
@@ -480,12 +520,12 @@ def install_simt(monkeypatch, simt_lib):
 
     monkeypatch.setattr(ops, "_call", call)
     # turns.py / ingest.py call the handle directly: give them the CPU build with the ctypes signatures applied
-    from stac_speech_translation_b200 import ingest, turns
+    from stac_speech_translation_b200 import augment, ingest, losses, turns
     for name, (res, sig) in _lib._SIGNATURES.items():
         fn = getattr(simt_lib, name, None)
         if fn is not None:
             fn.restype, fn.argtypes = res, sig
-    for mod in (turns, ingest):
+    for mod in (turns, ingest, augment, losses):
         monkeypatch.setattr(mod, "lib", lambda: simt_lib)
     emu.routed = routed
     return emu

@@ -11,7 +11,8 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE.parent.parent / "stac_speech_translation_b200" / "csrc"
-SOURCES = ["turns.cu", "decoder_f32.cu", "ingest.cu", "norm_stats.cu", "encoder_f32.cu", "conv_frontend.cu", "fbank.cu"]
+SOURCES = ["turns.cu", "decoder_f32.cu", "ingest.cu", "norm_stats.cu", "encoder_f32.cu", "conv_frontend.cu", "fbank.cu",
+           "train_pieces.cu"]
 LIB = HERE / "libstac_simt_cpu.so"
 
 

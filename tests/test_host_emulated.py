@@ -358,3 +358,36 @@ def test_fbank_tc2_tables_against_the_oracle(monkeypatch, n):
     got1 = ops.fbank_tc(wavs, tabs)
     assert got2.shape == ref.shape
     assert rel_l2(got2, ref) < 1e-3 and rel_l2(got1, ref) < 1e-3 and rel_l2(got2, got1) < 1e-3
+
+
+def test_training_stage_pieces_host_side(monkeypatch):
+    """SpecAugment and ctc_loss drop-ins on the CPU through the emulated C ABI: the parameter draws follow
+    SpeechBrain's order (same seed -> same augmentation as the oracle), lengths are rounded the way SpeechBrain rounds
+    them, every reduction is passed through, unsupported settings raise."""
+    from oracle.train_pieces import SpecAugment as OracleAug, ctc_loss as oracle_ctc
+    emu = abi_emulator.install(monkeypatch)
+    cfg = dict(time_warp=True, time_warp_window=5, time_warp_mode="bicubic", freq_mask=True, n_freq_mask=2, time_mask=True,
+               n_time_mask=2, freq_mask_width=30, time_mask_width=40)                 # transformer_multitask.yaml:283-293
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 131, 80, generator=g)
+    ours, ref = sb.SpecAugment(**cfg), OracleAug(**cfg)
+    for step in range(3):
+        torch.manual_seed(100 + step)
+        want = ref(x.clone())
+        torch.manual_seed(100 + step)
+        got = ours(x)
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5) and torch.equal(got == 0, want == 0)
+    assert emu.calls.count("stac_spec_augment") == 3
+    with pytest.raises(sb.StacB200Error):
+        sb.SpecAugment(time_warp_mode="nearest")
+    with pytest.raises(sb.StacB200Error):
+        sb.SpecAugment(replace_with_zero=False)
+    lp = torch.randn(5, 60, 30, generator=g).log_softmax(-1)
+    tg = torch.randint(1, 30, (5, 11), generator=g)
+    in_rel, tg_rel = torch.tensor([1.0, 0.83, 0.5, 0.25, 0.61]), torch.tensor([1.0, 0.5, 0.37, 0.1, 0.9])
+    for reduction in ("mean", "sum", "batchmean", "batch", "none"):
+        got = sb.ctc_loss(lp, tg, in_rel, tg_rel, 0, reduction)
+        want = oracle_ctc(lp, tg, in_rel, tg_rel, 0, reduction)
+        assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-5, atol=1e-5), reduction
+    with pytest.raises(sb.StacB200Error):
+        sb.ctc_loss(lp, tg, in_rel, tg_rel, 0, "median")

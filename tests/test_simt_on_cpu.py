@@ -26,7 +26,7 @@ def simt():
     lib = ctypes.CDLL(str(simt_build.build()))
     for name in ("stac_argmax_rows", "stac_ctc_spikes", "stac_embed_scale_pe", "stac_attention_f32",
                  "stac_pcm_i16_to_f32", "stac_utt_mean_std", "stac_layernorm", "stac_mha_f32", "stac_log_softmax",
-                 "stac_kv_lengths", "stac_cast_bf16", "stac_gemm_f32"):
+                 "stac_kv_lengths", "stac_cast_bf16", "stac_gemm_f32", "stac_spec_augment", "stac_ctc_loss"):
         res, args = _lib._SIGNATURES[name]
         getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
     return lib
@@ -276,3 +276,72 @@ def test_turns_ingest_and_train_norm_drop_ins_on_the_emulated_kernels(simt, monk
         wl = torch.tensor([1.0, 0.73, 0.41])
         assert rel_l2(ours(x, wl, epoch=epoch), ref(x, wl, epoch=epoch)) < 1e-5
         assert rel_l2(ours.glob_mean, ref.glob_mean) < 1e-5 and rel_l2(ours.glob_std, ref.glob_std) < 1e-5
+
+
+def _spec_augment_case(simt, seed, b, t, f, **kw):
+    """One SpecAugment call: the oracle (SpeechBrain's control flow over torch's interpolate / masked_fill_) and the
+    kernel fed with the parameters the product class draws from the SAME generator state."""
+    from oracle.train_pieces import SpecAugment as OracleAug
+    from stac_speech_translation_b200.augment import SpecAugment
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, t, f, generator=g) * 3 + 1
+    torch.manual_seed(seed)
+    want = OracleAug(**kw)(x.clone())
+    torch.manual_seed(seed)
+    c, w, (fpos, flen), (tpos, tlen) = SpecAugment(**kw).draw(b, t, f)
+    out = torch.full_like(x, float("nan"))
+    rc = simt.stac_spec_augment(P(x), b, t, f, c, w, P(fpos), P(flen), 0 if fpos is None else fpos.shape[1], P(tpos),
+                                P(tlen), 0 if tpos is None else tpos.shape[1], 0.0, P(out), None)
+    assert rc == 0
+    return out, want, (c, w)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_spec_augment_kernel(simt, seed):
+    """stac_spec_augment from source against the oracle's SpecAugment with the reference's yaml settings
+    (transformer_multitask.yaml:283-293), and with each of its three parts alone."""
+    ref_cfg = dict(time_warp=True, time_warp_window=5, freq_mask=True, n_freq_mask=2, time_mask=True, n_time_mask=2,
+                   freq_mask_width=30, time_mask_width=40)
+    out, want, (c, w) = _spec_augment_case(simt, seed, 3, 97 + 13 * seed, 80, **ref_cfg)
+    assert c > 0 and w > 0
+    assert torch.allclose(out, want, rtol=1e-5, atol=1e-5), (out - want).abs().max()
+    assert torch.equal(out == 0, want == 0)                        # the masks are exact
+    for part in ("time_warp", "freq_mask", "time_mask"):
+        cfg = dict(ref_cfg, time_warp=False, freq_mask=False, time_mask=False)
+        cfg[part] = True
+        out, want, _ = _spec_augment_case(simt, 10 + seed, 2, 64, 40, **cfg)
+        assert torch.allclose(out, want, rtol=1e-5, atol=1e-5), part
+    # a sequence too short to warp (time - window <= window) passes through the warp untouched
+    out, want, (c, w) = _spec_augment_case(simt, seed, 2, 10, 16, **dict(ref_cfg, freq_mask=False, time_mask=False))
+    assert w < 0 and torch.equal(out, want)
+
+
+@pytest.mark.parametrize("reduction", ["none", "sum", "mean", "batchmean", "batch"])
+def test_ctc_loss_kernel(simt, reduction):
+    """stac_ctc_loss from source against torch.nn.functional.ctc_loss through SpeechBrain's wrapper (oracle): ragged
+    input and target lengths, repeated labels (no skip transition), an empty target, an infeasible utterance (more
+    tokens than frames: infinite loss, zeroed), every reduction."""
+    from oracle.train_pieces import ctc_loss as oracle_ctc
+    g = torch.Generator().manual_seed(21)
+    b, t, v, lmax = 6, 40, 12, 9
+    lp = torch.randn(b, t, v, generator=g).log_softmax(-1)
+    tg = torch.randint(1, v, (b, lmax), generator=g)
+    tg[1, :4] = torch.tensor([3, 3, 3, 5])                         # repeats
+    in_rel = torch.tensor([1.0, 0.9, 0.55, 0.31, 0.1, 1.0])
+    tg_rel = torch.tensor([1.0, 0.45, 0.7, 0.2, 1.0, 0.0])         # row 4: 9 tokens in 4 frames; row 5: empty target
+    want = oracle_ctc(lp, tg, in_rel, tg_rel, 0, reduction)
+    il = (in_rel * t).round().int()
+    tl = (tg_rel * lmax).round().int()
+    mode = {"none": 0, "sum": 1, "mean": 2, "batchmean": 3, "batch": 4}[reduction]
+    nll = torch.full((b,), float("nan"))
+    out = torch.full((b if mode == 4 else 1,), float("nan"))
+    tg32 = tg.int().contiguous()
+    assert simt.stac_ctc_loss(P(lp), P(tg32), P(il), P(tl), b, t, v, lmax, 0, mode, P(nll), P(out), None) == 0
+    per_utt = torch.nn.functional.ctc_loss(lp.transpose(0, 1), tg, il, tl, 0, reduction="none", zero_infinity=True)
+    assert torch.allclose(nll, per_utt, rtol=1e-5, atol=1e-5), (nll, per_utt)
+    assert float(nll[4]) == 0.0                                    # infeasible -> inf -> zero_infinity
+    got = nll if mode == 0 else (out if mode == 4 else out[0])
+    if reduction == "batch":                                       # row 5 divides by a zero target length in both
+        assert torch.allclose(got[:5], want[:5], rtol=1e-5, atol=1e-5)
+    else:
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), (got, want)

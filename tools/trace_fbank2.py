@@ -24,7 +24,7 @@ lib.stac_fbank2_trace(buf.data_ptr())
 call(); torch.cuda.synchronize()
 tr = (buf.cpu().long() & 0xffffffff).view(4, 8, 16)
 base = int(tr[3, 0, 0]) or int(tr[0, 0, 0])
-names = ["producer (first producer warp): 0 pcm_full passed, 1..7 stage i stored; stage 1: 8 folded, 9 announced, 10 slot free", "mma: 0 tempty passed, 1..7 stage i inputs ready",
+names = ["producer (first producer warp): 0 pcm_full passed, 1..7 stage i stored; stage 2: 8 folded, 9 slot free", "mma: 0 tempty passed, 1..7 stage i inputs ready",
          "epilogue: 0 loop top, 1 tfull passed, 2 TMEM released, 3 dB + max done, 4 rows stored",
          "pcm loader: 0 loop top, 1 pcm_free passed, 2 zero fill done, 3 copies issued"]
 print(f"pair={pair}")
