@@ -9,42 +9,70 @@
 
 namespace {
 
-// ---- LayerNorm: one warp per row, dim <= 1024, dim % 128 == 0 ---------------------------------
-template <int kVec>  // float4 per lane = dim / 128
+// ---- LayerNorm: one warp per kRows rows, dim <= 1024, dim % 128 == 0 ---------------------------
+// (kRows rows per warp: all their loads are issued before the first reduction, so a warp keeps kRows x dim x 4 bytes in
+//  flight instead of one row's - with one row per warp the d_model = 256 launch ran at 4.9 TB/s, latency-bound)
+template <int kVec, int kRows>  // float4 per lane and row = dim / 128
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int64_t rows, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
                  __nv_bfloat16* __restrict__ out_bf16) {
   constexpr int dim = kVec * 128;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
-  float4 v[kVec];
-  float s = 0.f;
+  const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * kRows;
+  if (row0 >= rows) return;
+  float4 v[kRows][kVec];
+  float s[kRows];
 #pragma unroll
-  for (int i = 0; i < kVec; ++i) {
-    v[i] = __ldg(xr + lane + 32 * i);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(s) * (1.0f / dim);
-  float q = 0.f;
+  for (int r = 0; r < kRows; ++r) {
+    const int64_t row = min(row0 + r, rows - 1);               // rows past the end repeat the last one (not stored)
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
 #pragma unroll
-  for (int i = 0; i < kVec; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
+    for (int i = 0; i < kVec; ++i) v[r][i] = __ldg(xr + lane + 32 * i);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / dim) + eps);
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    s[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  }
+  float mean[kRows], q[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    mean[r] = s[r] * (1.0f / dim);
+    q[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) {
+      const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
+      q[r] += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+  }
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
     const int col = (lane + 32 * i) * 4;
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
     const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + col));
-    const float y0 = (v[i].x - mean) * rstd * g.x + bb.x, y1 = (v[i].y - mean) * rstd * g.y + bb.y;
-    const float y2 = (v[i].z - mean) * rstd * g.z + bb.z, y3 = (v[i].w - mean) * rstd * g.w + bb.w;
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * dim + col) = make_float4(y0, y1, y2, y3);
-    if (out_bf16)
-      *reinterpret_cast<uint2*>(out_bf16 + row * dim + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;
+      const float rstd = rsqrtf(q[r] * (1.0f / dim) + eps);
+      const float y0 = (v[r][i].x - mean[r]) * rstd * g.x + bb.x, y1 = (v[r][i].y - mean[r]) * rstd * g.y + bb.y;
+      const float y2 = (v[r][i].z - mean[r]) * rstd * g.z + bb.z, y3 = (v[r][i].w - mean[r]) * rstd * g.w + bb.w;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * dim + col) = make_float4(y0, y1, y2, y3);
+      if (out_bf16)
+        *reinterpret_cast<uint2*>(out_bf16 + row * dim + col) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    }
   }
 }
 
@@ -201,12 +229,12 @@ extern "C" int stac_layernorm(const float* x, int64_t rows, int64_t dim, const f
                               void* stream) {
   STAC_REQUIRE(x && gamma && beta && rows > 0 && (out_f32 || out_bf16));
   if (dim % 128 != 0 || dim > 1024 || dim <= 0) return STAC_ERR_UNSUPPORTED_SHAPE;
-  const unsigned grid = (unsigned)ceil_div64(rows, 8);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   cudaStream_t st = as_stream(stream);
+  // rows per warp: 32 floats of row data per lane at most
   switch (dim / 128) {
-#define LN_CASE(V) case V: layernorm_kernel<V><<<grid, 256, 0, st>>>(x, rows, gamma, beta, eps, out_f32, ob); break;
-    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+#define LN_CASE(V, R) case V: layernorm_kernel<V,R><<<(unsigned)ceil_div64(rows, 8 * R), 256, 0, st>>>(x, rows, gamma, beta, eps, out_f32, ob); break;
+    LN_CASE(1, 4) LN_CASE(2, 4) LN_CASE(3, 2) LN_CASE(4, 2) LN_CASE(5, 1) LN_CASE(6, 1) LN_CASE(7, 1) LN_CASE(8, 1)
 #undef LN_CASE
     default: return STAC_ERR_UNSUPPORTED_SHAPE;
   }
