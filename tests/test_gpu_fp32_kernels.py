@@ -1,4 +1,6 @@
 """fp32 CUDA-core kernels against the oracle / plain torch fp32, through the C ABI (GPU only)."""
+import ctypes
+
 import pytest
 import torch
 
@@ -88,3 +90,31 @@ def test_fbank_tc2_many_tiles_ragged_batch(pair, monkeypatch):
     assert torch.equal(got.db, again.db) and torch.equal(got.utt_max, again.utt_max)
     # the per-utterance maximum is the maximum of what was written
     assert torch.equal(got.utt_max, _ordered_key(got.db.amax(dim=(1, 2))))
+
+
+@pytest.mark.parametrize("pair", [1, 0])
+def test_fbank_tc2_edge_shapes(pair, monkeypatch):
+    """stac_fbank_logmel_tc2 at the edges of its contract: utterances shorter than one window, one utterance, an odd number
+    of tiles (the follower of the last pair repeats a tile and stores nothing), rows that are views into a wider buffer
+    (row stride > samples: what lies beyond an utterance's end in memory must not be read as audio)."""
+    monkeypatch.setenv("STAC_FBANK_V2", "1")
+    monkeypatch.setenv("STAC_FBANK_PAIR", str(pair))
+    tabs = ops.build_fbank_tc_tables("cuda")
+    fft = ops.build_fbank_tables("cuda")
+    g = torch.Generator().manual_seed(11)
+    for b, n in [(1, 32), (3, 64), (2, 320), (1, 160 * 128), (5, 160 * 130 + 96), (149, 1600)]:
+        wavs = (torch.randn(b, n, generator=g) * 0.2).cuda()
+        got = ops.fbank_tc(wavs, tabs, raw=True)
+        want = ops.fbank(wavs, fft, raw=True)
+        assert got.db.shape == (b, 1 + n // 160, 80)
+        assert rel_l2(got.db, want.db) < 1e-3, (b, n, rel_l2(got.db, want.db))
+        # strided rows: the same audio inside a buffer whose rows continue with large garbage
+        wide = torch.full((b, n + 4096), 1e3, device="cuda")
+        wide[:, :n] = wavs
+        view = wide[:, :n]
+        assert view.stride(0) == n + 4096
+        db = torch.empty(b, 1 + n // 160, 80, device="cuda")
+        umax = torch.empty(b, dtype=torch.int32, device="cuda")
+        ops._call("stac_fbank_logmel_tc2", ctypes.c_void_p(view.data_ptr()), b, n, view.stride(0), ops.ptr(tabs.tab2),
+                  ops.ptr(tabs.tw2, torch.float16), ops.ptr(db), ops.ptr(umax), pair, ops.stream())
+        assert torch.equal(db, got.db), (b, n)
