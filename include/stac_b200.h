@@ -46,6 +46,11 @@ int stac_version(void);
 /* Persistent kernels launch at most (SM count - n) CTAs from now on (default 0).  Use when a communication kernel
  * (NCCL send/recv of the multi-GPU gather) runs beside the path and holds SMs. */
 int stac_set_reserved_sms(int n);
+/* L2 residency hint (cudaStreamAttributeAccessPolicyWindow + the device's persisting-L2 carve-out) for a buffer the
+ * kernels launched - or captured - on `stream` afterwards re-read and update: the encoder's fp32 residual stream.
+ * bytes == 0 clears the stream's window.  STAC_ERR_UNSUPPORTED_SHAPE: the device has no persisting L2. */
+int stac_l2_persist(const void* base, int64_t bytes, float hit_ratio, void* stream);
+int stac_l2_persist_limits(int64_t* max_persist_bytes, int64_t* max_window_bytes);
 const char* stac_error_string(int code);
 
 /* ---------------------------------------------------------------------------

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "stac_version": (c_int, []),
     "stac_error_string": (c_char_p, [c_int]),
     "stac_set_reserved_sms": (c_int, [c_int]),
+    "stac_l2_persist": (c_int, [_P, c_int64, c_float, _P]),
+    "stac_l2_persist_limits": (c_int, [_P, _P]),
     "stac_fbank_tables_floats": (c_int, []),
     "stac_fbank_logmel": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P]),
     "stac_fbank_tc_tables_floats": (c_int, []),
