@@ -63,6 +63,38 @@ def test_mha_bf16_v2(t, lens, d, h):
     assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
 
 
+@pytest.mark.parametrize("jump_at", [40, 70, 100, 130, 170, 300, 500])
+def test_mha_bf16_v2_reference_raise(jump_at):
+    """The lazy-rescaling path of stac_mha_bf16_v2: keys from position `jump_at` on score far above everything before
+    them (more than 2^40 above the running reference), so the reference maximum must be raised in the middle of an item -
+    in the second / third 32-key chunk of the first tile (only this tile's partial sums and P chunks are rescaled), and in
+    later tiles (O in tensor memory is rescaled too) - and again a second time further on."""
+    g = torch.Generator().manual_seed(jump_at)
+    b, t, d, h = 2, 600, 128, 2
+    qkv = torch.randn(b * t, 3 * d, generator=g) * 0.5
+    q = qkv[:, :d].view(b, t, h, 64)
+    k = qkv[:, d:2 * d].view(b, t, h, 64)
+    # the keys from jump_at on are aligned with the mean query direction and large; a second, larger step later
+    direction = q.mean(1, keepdim=True) / q.mean(1, keepdim=True).norm(dim=-1, keepdim=True)
+    k[:, jump_at:] += 30.0 * direction
+    k[:, min(t - 1, jump_at + 150):] += 30.0 * direction
+    q += 4.0 * direction                                   # every query has a positive component along it
+    qkv = qkv.to(torch.bfloat16)
+    kv = torch.tensor([t, t - 37], dtype=torch.int32)
+    ctx = torch.full((b * t, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    qkv_d, kv_d = qkv.cuda(), kv.cuda()
+    ops.check(ops.lib().stac_mha_bf16_v2(ops.ptr(qkv_d), ops.ptr(kv_d), b, t, d, h, ops.ptr(ctx), ops.stream()))
+    torch.cuda.synchronize()
+    qf, kf, vf = (x.float().view(b, t, h, 64).transpose(1, 2) for x in qkv.split(d, dim=-1))
+    mask = torch.arange(t)[None, :] >= kv[:, None]
+    s = (qf @ kf.transpose(-1, -2)).masked_fill(mask[:, None, None, :], float("-inf"))
+    assert float((s[..., jump_at:].amax(-1) - s[..., :jump_at].amax(-1)).min()) > 40.0      # the jump is there, in nats
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(b * t, d)
+    got = ctx.float().cpu()
+    assert not torch.isnan(got).any() and bool(torch.isfinite(got).all())
+    assert rel_l2(got, ref) < 1e-2, rel_l2(got, ref)
+
+
 # Stress shape for the finding in DESIGN.md section 9: many consecutive one-tile work items per CTA in which both query
 # groups are active (short utterances in a batch padded beyond 128 frames), which is what lets one softmax group run
 # two items ahead of the store warp.  The kernel now has one o_staged barrier per (Q buffer, group), which cannot run
