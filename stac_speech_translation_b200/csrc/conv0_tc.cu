@@ -18,8 +18,12 @@
 //   * a time step's two output planes leave the SM as bulk async copies (full 512-byte rows) issued by a
 //     dedicated warp; staging buffers, B tiles and accumulators are all multi-buffered and every hand-off is an
 //     mbarrier, so no role ever waits at a CTA-wide barrier in the steady state.
-// Roles (13 warps): 0-7 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = channel half), 8-10 producers
-// (patch rows + statistics), 11 MMA issuer + TMEM owner, 12 output bulk-copy issuer.
+// Roles (16 warps): 0-7 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = channel half), 8-10 and 11-13 two producer
+// groups (patch rows + statistics) that take alternate tiles, 14 MMA issuer + TMEM owner, 15 output bulk-copy issuer.
+// (Two producer groups since round 2: the stage was believed to sit on a 3.9 TB/s write ceiling; tools/ubench_write.cu
+// measures 6.3 TB/s for bulk shared -> global copies and 6.9 TB/s for plain stores on this pool, i.e. the kernel was
+// at 55 % of what the memory takes and its ONE producer group - a chain of three barriers, 110 FMAs and a 40-term sum
+// per tile - was the critical path.)
 #include <algorithm>
 #include "tc_common.cuh"
 
@@ -33,8 +37,10 @@ constexpr int kTs = 2;                       // time steps per tile
 constexpr int kN = kTs * kF1;                // 80 positions = UMMA N
 constexpr int kStages = 3;                   // B tiles / accumulators in flight
 constexpr int kOutStages = 4;                // staged time steps in flight
-constexpr int kThreads = 13 * 32;
+constexpr int kThreads = 16 * 32;
 constexpr int kProducerThreads = 96;
+constexpr int kProducerGroups = 2;
+constexpr int kWarpMma = 8 + 3 * kProducerGroups, kWarpOut = kWarpMma + 1;
 
 constexpr int kWBytes = 2 * 128 * 128;                 // two 128-channel halves, 128-byte (64 x bf16) rows
 constexpr int kBBytes = kN * 128;                      // 10240
@@ -46,9 +52,9 @@ constexpr int kOffW = 0;
 constexpr int kOffB = kOffW + kWBytes;
 constexpr int kOffOut = kOffB + kStages * kBBytes;
 constexpr int kOffWraw = kOffOut + kOutStages * kOutBytes;       // fp32 w0 [256][9] + b0 [256] (setup only)
-constexpr int kOffFeat = kOffWraw + (kC * 9 + kC) * 4;            // float [5][82]
-constexpr int kOffRowStat = kOffFeat + 5 * kFRow * 4;             // float2 [80]
-constexpr int kOffTab = kOffRowStat + kN * 8;                     // float [128]: wsum[9] G[81] bw[9] bsum bb
+constexpr int kOffFeat = kOffWraw + (kC * 9 + kC) * 4;            // float [groups][5][82]
+constexpr int kOffRowStat = kOffFeat + kProducerGroups * 5 * kFRow * 4;   // float2 [groups][80]
+constexpr int kOffTab = kOffRowStat + kProducerGroups * kN * 8;                     // float [128]: wsum[9] G[81] bw[9] bsum bb
 constexpr int kOffNorm = kOffTab + 128 * 4;                       // float [80] mean | float [80] 1 / std | float floor_all
 constexpr int kOffBar = kOffNorm + (2 * kMel + 4) * 4;
 constexpr int kNumBars = 4 * kStages + 2 * kOutStages;
@@ -117,7 +123,7 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
     for (int s = 0; s < kOutStages; ++s) { mbar_init(out_full(s), 8); mbar_init(out_empty(s), 1); }
     fence_barrier_init();
   }
-  if (warp == 11) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == kWarpMma) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   for (int i = tid; i < kC * 9; i += kThreads) wraw[i] = __ldg(w0 + i);
   for (int i = tid; i < kC; i += kThreads) wraw[kC * 9 + i] = __ldg(b0 + i);
   float* normtab = reinterpret_cast<float*>(sptr + kOffNorm);
@@ -127,7 +133,7 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
       normtab[i] = nmean != nullptr ? __ldg(nmean + i) : 0.f;
       normtab[kMel + i] = nstd != nullptr ? 1.0f / __ldg(nstd + i) : 1.f;      // reciprocal: the loader multiplies
     }
-    if (warp == 12 && !per_utt) {               // batch-global top-dB (older SpeechBrain): one maximum for everybody
+    if (warp == kWarpOut && !per_utt) {         // batch-global top-dB (older SpeechBrain): one maximum for everybody
       float mx = -INFINITY;
       for (int i = lane; i < batch; i += 32) mx = fmaxf(mx, ordered_to_float(__ldg(utt_max + i)));
       mx = warp_max(mx);
@@ -245,11 +251,14 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
       t1_0 += t1_step;
       if (t1_0 >= t1_wrap) t1_0 -= t1_wrap;
     }
-  } else if (warp < 11) {
+  } else if (warp < kWarpMma) {
     // ============================ producers: LayerNorm statistics + scaled patch rows ============================
-    const int p = tid - 8 * 32;                      // 0..95; rows 0..79 are real positions
-    float* fbuf = reinterpret_cast<float*>(sptr + kOffFeat);
-    float2* rowstat = reinterpret_cast<float2*>(sptr + kOffRowStat);
+    // group grp builds the tiles with local ordinal n = grp, grp + 2, ... (B stage n % kStages)
+    const int grp = (warp - 8) / 3;
+    const int p = tid - (8 + 3 * grp) * 32;          // 0..95; rows 0..79 are real positions
+    float* fbuf = reinterpret_cast<float*>(sptr + kOffFeat) + grp * 5 * kFRow;
+    float2* rowstat = reinterpret_cast<float2*>(sptr + kOffRowStat) + grp * kN;
+    const int bar_id = 2 + grp;
     const int tl = p / kF1, f1 = p - tl * kF1;
     // input rows t = 2*t1_0 - 1 .. 2*t1_0 + 3 (reflected at the batch edges), bins -1..79 (bin -1 mirrors bin 1);
     // the loads of tile n+1 are issued while tile n is built
@@ -276,11 +285,13 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
         }
       }
     };
-    if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
-    int s = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      named_bar_sync(2, kProducerThreads);              // previous tile's patches have been read from fbuf
+    const int tile0 = (int)blockIdx.x + grp * (int)gridDim.x, tile_step = kProducerGroups * (int)gridDim.x;
+    if (tile0 < n_tiles) fetch(tile0);
+    int n = grp;
+    for (int tile = tile0; tile < n_tiles; tile += tile_step, n += kProducerGroups) {
+      const int s = n % kStages;
+      const uint32_t phase = (uint32_t)(n / kStages) & 1;
+      named_bar_sync(bar_id, kProducerThreads);         // previous tile's patches have been read from fbuf
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         const int idx = p + i * kProducerThreads;
@@ -296,8 +307,8 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
           fbuf[r * kFRow + fi] = v;
         }
       }
-      named_bar_sync(2, kProducerThreads);
-      if (tile + (int)gridDim.x < n_tiles) fetch(tile + gridDim.x);
+      named_bar_sync(bar_id, kProducerThreads);
+      if (tile + tile_step < n_tiles) fetch(tile + tile_step);
       float x[9];
       if (p < kN) {
 #pragma unroll
@@ -316,7 +327,7 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
         }
         rowstat[p] = make_float2(s1, s2);
       }
-      named_bar_sync(2, kProducerThreads);
+      named_bar_sync(bar_id, kProducerThreads);
       mbar_wait(b_empty(s), phase ^ 1);
       if (p < kN) {
         // every thread of a time step adds the same 40 row statistics in the same order
@@ -347,9 +358,8 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_full(s));
-      if (++s == kStages) { s = 0; phase ^= 1; }
     }
-  } else if (warp == 11) {
+  } else if (warp == kWarpMma) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, kN);
@@ -412,7 +422,7 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 11) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == kWarpMma) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 int num_sms_conv0() { return stac_grid_limit(); }
