@@ -74,6 +74,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
@@ -145,7 +157,9 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
     // weight row of channel c: [w_hi(9) | w_hi(9) | w_lo(9) | b_hi | b_lo | b_hi | 1 | 1 | 0 ...] bf16, 128-byte
     // swizzled row; the patch rows carry [xs_hi | xs_lo | xs_hi | r_hi | r_hi | r_lo | s_hi | s_lo] with
     // xs = rstd * x, r = rstd, s = -mean * rstd, so the accumulator is (conv + bias - mean) * rstd
-    const int c = tid, r = c & 127;
+    // row r of half h holds channel 2 r + h: an epilogue thread (= TMEM lane r) then owns the ADJACENT channels 2 r, 2 r + 1
+    // (one in each half's accumulator) and stores them as one 32-bit word
+    const int c = tid, r = c >> 1;
     unsigned short kv[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) kv[i] = 0;
@@ -161,7 +175,7 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
     kv[29] = kv[27];
     kv[30] = 0x3f80;
     kv[31] = 0x3f80;
-    const uint32_t row = sbase + kOffW + (c >> 7) * 16384 + r * 128;
+    const uint32_t row = sbase + kOffW + (c & 1) * 16384 + r * 128;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       sts_v4(row + ((j ^ (r & 7)) << 4), kv[8 * j] | ((uint32_t)kv[8 * j + 1] << 16),
@@ -194,13 +208,22 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
   const int tp2 = (t1_len + 3) >> 1;
 
   if (warp < 8) {
-    // ============================ epilogue: thread = one output channel ============================
-    const int half = warp >> 2, quarter = warp & 3;
-    const int c = half * 128 + quarter * 32 + lane;
-    float g[kF1], be[kF1];
+    // ============================ epilogue: thread = two adjacent output channels, half of the frequency bins ============
+    // (round 2: with one channel per thread the stage was bound by its own issue slots and the shared-memory pipe - 41
+    //  two-byte stores and their byte extractions per time step and thread; a thread now takes channels 2 l and 2 l + 1
+    //  from the two halves' accumulators on ITS TMEM lane, packs them into one word and stores 128 contiguous bytes per
+    //  warp; the 2 x 2 x 20 LayerNorm gammas / betas of its bins still live in registers)
+    const int fh = warp >> 2, quarter = warp & 3;          // fh: frequency bins [20 fh, 20 fh + 20)
+    const int l = quarter * 32 + lane;                     // TMEM lane = channel pair
+    constexpr int kFh = kF1 / 2;
+    float g0[kFh], g1[kFh], be0[kFh], be1[kFh];
 #pragma unroll
-    for (int f = 0; f < kF1; ++f) { g[f] = __ldg(ln_g + f * kC + c); be[f] = __ldg(ln_b + f * kC + c); }
-    const uint32_t my_col = sbase + kOffOut + c * 2;
+    for (int f = 0; f < kFh; ++f) {
+      const float2 gg = __ldg(reinterpret_cast<const float2*>(ln_g + (fh * kFh + f) * kC + 2 * l));
+      const float2 bb = __ldg(reinterpret_cast<const float2*>(ln_b + (fh * kFh + f) * kC + 2 * l));
+      g0[f] = gg.x; g1[f] = gg.y; be0[f] = bb.x; be1[f] = bb.y;
+    }
+    const uint32_t my_col = sbase + kOffOut + l * 4;
     const __nv_bfloat162 slope2 = __floats2bfloat162_rn(kSlope, kSlope);
     int n = 0, as = 0;
     uint32_t acc_phase = 0;
@@ -209,16 +232,18 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
       mbar_wait(acc_full(as), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (2 * kN) + half * kN;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * (2 * kN) + fh * kFh;
 #pragma unroll
       for (int tl = 0; tl < kTs; ++tl) {
         const int m = n * kTs + tl, os = m & (kOutStages - 1);
         const bool valid = t1_0 + tl < t1_len;
         mbar_wait(out_empty(os), ((m >> 2) & 1) ^ 1);
         if (valid) {
-          uint32_t va[32], vb[8];
-          tmem_ld32(t_addr + tl * kF1, va);
-          tmem_ld8(t_addr + tl * kF1 + 32, vb);
+          uint32_t ua[16], ub[4], va[16], vb[4];             // channel 2 l (half 0) | channel 2 l + 1 (half 1), 20 bins each
+          tmem_ld16(t_addr + tl * kF1, ua);
+          tmem_ld4(t_addr + tl * kF1 + 16, ub);
+          tmem_ld16(t_addr + kN + tl * kF1, va);
+          tmem_ld4(t_addr + kN + tl * kF1 + 16, vb);
           tmem_ld_wait();
           if (tl == kTs - 1) {
             // last read of this accumulator stage: hand it back to the MMA warp
@@ -226,18 +251,22 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty(as));
           }
+#ifndef C0_NO_EPI          // timing experiment: accumulators read, nothing computed or staged
           const uint32_t col = my_col + os * kOutBytes;
 #pragma unroll
-          for (int f = 0; f < kF1; f += 2) {
-            const float u0 = __uint_as_float(f < 32 ? va[f] : vb[f - 32]);
-            const float u1 = __uint_as_float(f + 1 < 32 ? va[f + 1] : vb[f + 1 - 32]);
-            __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(g[f], u0, be[f]), fmaf(g[f + 1], u1, be[f + 1]));
+          for (int f = 0; f < kFh; ++f) {
+            const float u0 = __uint_as_float(f < 16 ? ua[f] : ub[f - 16]);
+            const float u1 = __uint_as_float(f < 16 ? va[f] : vb[f - 16]);
+            __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(g0[f], u0, be0[f]), fmaf(g1[f], u1, be1[f]));
             y = __hmax2(y, __hmul2(y, slope2));            // LeakyReLU on the packed pair
             const uint32_t bits = *reinterpret_cast<uint32_t*>(&y);
-            sts_u16(col + stage_row(f) * (kC * 2), (unsigned short)(bits & 0xffffu));
-            sts_u16(col + stage_row(f + 1) * (kC * 2), (unsigned short)(bits >> 16));
-            if (f == 0) sts_u16(col, (unsigned short)(bits >> 16));   // padded bin 0 mirrors f1 = 1
+            const int f1 = fh * kFh + f;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(col + stage_row(f1) * (kC * 2)), "r"(bits) : "memory");
+            if (f1 == 1) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col), "r"(bits) : "memory");   // padded bin 0 mirrors f1 = 1
           }
+#else
+          if (ua[0] == 0x12345678u && vb[0] == 1u && ub[0] == 2u && va[0] == 3u) sts_u16(my_col, 1);
+#endif
         } else if (tl == kTs - 1) {
           tc_fence_before();
           __syncwarp();
@@ -403,9 +432,11 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
             for (int i = 0; i < n_tp; ++i) {
               const int tp = tps[i];
               const int64_t plane_t = (int64_t)b * 4 + (tp & 1) * 2;
+#ifndef C0_NO_STORE        // timing experiment: the staged planes are not written
               bulk_store(out + ((plane_t + 0) * tp2 + (tp >> 1)) * (21 * kC), s0, kPlane0Rows * kC * 2);
               bulk_store(out + ((plane_t + 1) * tp2 + (tp >> 1)) * (21 * kC), s0 + kPlane0Rows * kC * 2,
                          kPlane1Rows * kC * 2);
+#endif
             }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
