@@ -190,13 +190,14 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
       const float bc = wraw[kC * 9 + c];
       float v;
       if (i < 9) v = wraw[c * 9 + i];
-      else if (i < 90) v = wraw[c * 9 + (i - 9) / 9] * wraw[c * 9 + (i - 9) % 9];
+      else if (i < 90) v = wraw[c * 9 + (i - 9) / 9] * wraw[c * 9 + (i - 9) % 9];     // (k, k2 > k: stored doubled below)
       else if (i < 99) v = bc * wraw[c * 9 + (i - 90)];
       else if (i == 99) v = bc;
       else v = bc * bc;
       acc += v;
     }
-    tab[i] = acc;
+    // G is symmetric: the producers evaluate x^T G x over the upper triangle only, with the off-diagonal terms doubled
+    tab[i] = (i >= 9 && i < 90 && (i - 9) % 9 > (i - 9) / 9) ? 2.0f * acc : acc;
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -288,10 +289,24 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
     float* fbuf = reinterpret_cast<float*>(sptr + kOffFeat) + grp * 5 * kFRow;
     float2* rowstat = reinterpret_cast<float2*>(sptr + kOffRowStat) + grp * kN;
     const int bar_id = 2 + grp;
-    const int tl = p / kF1, f1 = p - tl * kF1;
+    // position of this thread: warp 0 of the group = time step 0, bins 0-31; warp 1 = time step 1, bins 0-31; warp 2 =
+    // bins 32-39 of both steps (lanes 0-7 / 8-15): a time step's 40 row statistics are reduced with shuffles inside
+    // a warp plus one exchange through shared memory (every thread used to add all 40 in a serial chain)
+    const int pw = p >> 5;
+    const int tl = pw < 2 ? pw : (lane >> 3) & 1, f1 = pw < 2 ? lane : 32 + (lane & 7);
+    const bool has_pos = pw < 2 || lane < 16;
+    const int prow = tl * kF1 + f1;                  // row of the B tile
     // input rows t = 2*t1_0 - 1 .. 2*t1_0 + 3 (reflected at the batch edges), bins -1..79 (bin -1 mirrors bin 1);
-    // the loads of tile n+1 are issued while tile n is built
+    // the loads of tile n+1 are issued while tile n is built.  Staging slot i of this thread: row ld_r[i], bin ld_c[i]
     float ld[5];
+    int ld_r[5], ld_c[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int idx = p + i * kProducerThreads;         // 0 .. 5*81-1
+      ld_r[i] = idx < 5 * (kMel + 1) ? idx / (kMel + 1) : -1;
+      const int fi = idx - max(ld_r[i], 0) * (kMel + 1);
+      ld_c[i] = fi == 0 ? 1 : fi - 1;
+    }
     float ld_floor = 0.f;                            // (fused mode) top-dB floor of the utterance the loads belong to
     auto fetch = [&](int tile) {
       const int b = tile / tiles_per_utt;
@@ -304,13 +319,11 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
       if (fused_norm) ld_floor = per_utt ? ordered_to_float(__ldg(utt_max + b)) - top_db : normtab[2 * kMel];
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        const int idx = p + i * kProducerThreads;       // 0 .. 5*81-1
         ld[i] = 0.f;
-        if (idx < 5 * (kMel + 1)) {
-          const int r = idx / (kMel + 1), fi = idx - r * (kMel + 1);
-          int t = reflect_idx(2 * t1_0 - 1 + r, frames);
+        if (ld_r[i] >= 0) {
+          int t = reflect_idx(2 * t1_0 - 1 + ld_r[i], frames);
           t = min(max(t, 0), frames - 1);               // rows of an invalid second time step are never used
-          ld[i] = __ldg(frow + (int64_t)t * kMel + (fi == 0 ? 1 : fi - 1));
+          ld[i] = __ldg(frow + (int64_t)t * kMel + ld_c[i]);
         }
       }
     };
@@ -323,46 +336,52 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
       named_bar_sync(bar_id, kProducerThreads);         // previous tile's patches have been read from fbuf
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        const int idx = p + i * kProducerThreads;
-        if (idx < 5 * (kMel + 1)) {
-          const int r = idx / (kMel + 1), fi = idx - r * (kMel + 1);
+        if (ld_r[i] >= 0) {
           float v = ld[i];
           if (fused_norm) {
-            const int bin = fi == 0 ? 1 : fi - 1;
-            // (a true division here costs the producer warps - the critical path of this kernel - 0.1 ms per batch;
-            // the product with the reciprocal differs from topdb_norm_kernel's quotient by at most one fp32 ulp)
-            v = (fmaxf(v, ld_floor) - normtab[bin]) * normtab[kMel + bin];
+            // (a true division here costs the producer warps 0.1 ms per batch; the product with the reciprocal differs
+            // from topdb_norm_kernel's quotient by at most one fp32 ulp)
+            v = (fmaxf(v, ld_floor) - normtab[ld_c[i]]) * normtab[kMel + ld_c[i]];
           }
-          fbuf[r * kFRow + fi] = v;
+          const int idx = p + i * kProducerThreads;
+          fbuf[idx + ld_r[i]] = v;                      // = fbuf[r * kFRow + fi]: kFRow = 81 + 1
         }
       }
       named_bar_sync(bar_id, kProducerThreads);
       if (tile + tile_step < n_tiles) fetch(tile + tile_step);
       float x[9];
-      if (p < kN) {
+      float s1 = 0.f, s2 = 0.f;
+      if (has_pos) {
 #pragma unroll
         for (int kf = 0; kf < 3; ++kf)
 #pragma unroll
           for (int kt = 0; kt < 3; ++kt) x[kf * 3 + kt] = fbuf[(2 * tl + kt) * kFRow + 2 * f1 + kf];
-        // row sum and sum of squares over the 256 channels as forms of the 9-tap patch
-        float s1 = tab[99], s2 = tab[100];
+        // row sum and sum of squares over the 256 channels as forms of the 9-tap patch (G: upper triangle, doubled)
+        s1 = tab[99];
+        s2 = tab[100];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
           float q = 2.0f * tab[90 + k];
 #pragma unroll
-          for (int k2 = 0; k2 < 9; ++k2) q = fmaf(tab[9 + k * 9 + k2], x[k2], q);
+          for (int k2 = k; k2 < 9; ++k2) q = fmaf(tab[9 + k * 9 + k2], x[k2], q);
           s1 = fmaf(tab[k], x[k], s1);
           s2 = fmaf(q, x[k], s2);
         }
-        rowstat[p] = make_float2(s1, s2);
       }
+      // sums over the 40 bins of a time step: inside the warp (warps 0 / 1: 32 bins; warp 2: two segments of 8 lanes) ...
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t1 = __shfl_xor_sync(0xffffffffu, s1, o), t2 = __shfl_xor_sync(0xffffffffu, s2, o);
+        if (pw < 2 || o < 8) { s1 += t1; s2 += t2; }
+      }
+      // ... and the two partial sums of a step through shared memory: slots [tl][0] (warp tl) and [tl][1] (warp 2)
+      if (pw < 2) { if (lane == 0) rowstat[2 * pw] = make_float2(s1, s2); }
+      else if (lane == 0 || lane == 8) rowstat[2 * tl + 1] = make_float2(s1, s2);
       named_bar_sync(bar_id, kProducerThreads);
       mbar_wait(b_empty(s), phase ^ 1);
-      if (p < kN) {
-        // every thread of a time step adds the same 40 row statistics in the same order
-        float a1 = 0.f, a2 = 0.f;
-#pragma unroll 8
-        for (int f = 0; f < kF1; ++f) { const float2 r = rowstat[tl * kF1 + f]; a1 += r.x; a2 += r.y; }
+      if (has_pos) {
+        const float2 pa = rowstat[2 * tl], pb = rowstat[2 * tl + 1];
+        const float a1 = pa.x + pb.x, a2 = pa.y + pb.y;
         const float mean = a1 * (1.0f / (kF1 * kC));
         const float var = fmaxf(a2 * (1.0f / (kF1 * kC)) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + kLnEps);
@@ -377,8 +396,8 @@ conv0_tc_kernel(const float* __restrict__ feats, const float* __restrict__ w0, c
         const unsigned short r_hi = bf16_bits(rstd), r_lo = bf16_bits(rstd - bf16_val(r_hi));
         const unsigned short s_hi = bf16_bits(shift), s_lo = bf16_bits(shift - bf16_val(s_hi));
         auto pk = [](unsigned short a, unsigned short bb) { return (uint32_t)a | ((uint32_t)bb << 16); };
-        const uint32_t row = sbase + kOffB + s * kBBytes + p * 128;
-        const int sw = p & 7;
+        const uint32_t row = sbase + kOffB + s * kBBytes + prow * 128;
+        const int sw = prow & 7;
         sts_v4(row + ((0 ^ sw) << 4), pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]), pk(hi[6], hi[7]));
         sts_v4(row + ((1 ^ sw) << 4), pk(hi[8], lo[0]), pk(lo[1], lo[2]), pk(lo[3], lo[4]), pk(lo[5], lo[6]));
         sts_v4(row + ((2 ^ sw) << 4), pk(lo[7], lo[8]), pk(hi[0], hi[1]), pk(hi[2], hi[3]), pk(hi[4], hi[5]));
