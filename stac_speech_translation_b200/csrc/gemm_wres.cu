@@ -28,8 +28,8 @@ constexpr int kSmemLimit = 232448;                // 227 KB per CTA
 
 // BN = columns of W resident per CTA.  256 (default): each row tile of the activations is read N/256 times from L2 and
 // four ring stages fit beside the 128 KB block; 128: 64 KB block, eight ring stages.  Measured on the QKV projection
-// (48064 x 768): ring of 2 / 3 / 4 stages at BN = 256 -> 37 / 28 / 25 us; BN = 128 with 8 stages -> 25 us as well.  At
-// 25 us the launch moves its 74 MB of output at the 3.9 TB/s this pool sustains for write-dominated traffic.
+// (48064 x 768): ring of 2 / 3 / 4 stages at BN = 256 -> 37 / 28 / 25 us; BN = 128 with 8 stages -> 25 us as well.
+// (25 us is neither the tensor floor, 13.6 us, nor the HBM floor, 15 us: this pool writes 6.3 TB/s, tools/ubench_write.cu.)
 template <int BN>
 struct Cfg {
   static constexpr int kBBlock = BN * BK * 2;               // one k-block of the resident weight tile
