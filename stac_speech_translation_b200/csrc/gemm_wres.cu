@@ -178,6 +178,9 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(t_empty(acc));
         }
+#ifdef WRES_NO_EPI        // timing experiment: accumulators read, nothing staged or written
+        if (v[0] != 0x7fc12345u) continue;
+#endif
         const int lcol = cgrp * kColsPerWarp + chunk * 32;                 // column inside the 256-wide block
         const float* bc = bias_s + lcol;
         if (c_bf16) {
@@ -197,10 +200,12 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (half == 1) {
             fence_proxy_async_smem();
             __syncwarp();
+#ifndef WRES_NO_STORE     // timing experiment: tiles staged but not written
             if (row0 < m_rows && elect_one()) {
               tma_store_2d(&tmap_c, stage_buf, n_blk * BN + lcol - 32, row0);
               bulk_commit();
             }
+#endif
             __syncwarp();
           }
         } else {
@@ -217,11 +222,13 @@ gemm_wres_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           fence_proxy_async_smem();
           __syncwarp();
+#ifndef WRES_NO_STORE
           if (row0 < m_rows && elect_one()) {
             if (reduce_add) tma_reduce_add_2d(&tmap_c, stage_buf, n_blk * BN + lcol, row0);
             else tma_store_2d(&tmap_c, stage_buf, n_blk * BN + lcol, row0);
             bulk_commit();
           }
+#endif
           __syncwarp();
         }
       }
