@@ -263,7 +263,12 @@ int stac_ctc_spikes(const int32_t* ids, int64_t batch, int64_t t2, int32_t turn_
  *        head h uses columns h*64 .. h*64+63 of each.
  *        Masks: causal != 0 hides keys j > i; kv_len int32 [rows] (or NULL) hides j >= kv_len[r]; key_tokens int64
  *        [rows, lk] (or NULL) hides keys whose token equals pad_idx.  weights (or NULL): fp32 [rows, lq, lk], the
- *        probabilities averaged over heads (what nn.MultiheadAttention returns with need_weights=True). */
+ *        probabilities averaged over heads (what nn.MultiheadAttention returns with need_weights=True).
+ * stac_attention_beam_f32: the cross-attention of ONE decoding step for all hypothesis rows of an utterance at once
+ *        (lq = 1, no causal / token masks; row r reads memory block r / group, group <= 16): a key / value row is loaded
+ *        once per utterance instead of once per hypothesis.  Same arguments and arithmetic as stac_attention_f32;
+ *        weights (or NULL): fp32 [rows, lk].  STAC_ERR_UNSUPPORTED_SHAPE: group > 16 or lk too long for shared memory
+ *        (use stac_attention_f32). */
 int stac_embed_scale_pe(const int64_t* tokens, const float* emb, const float* pe, int64_t rows, int64_t seq_len,
                         int64_t d_model, int64_t vocab, float scale, float* out, void* stream);
 int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
@@ -271,6 +276,9 @@ int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float*
                        int64_t mem_rows_div, int causal,
                        const int32_t* kv_len, const int64_t* key_tokens, int64_t pad_idx, float* ctx, int64_t ldctx,
                        float* weights, void* stream);
+int stac_attention_beam_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
+                            int64_t kv_row_stride, int64_t rows, int64_t group, int64_t lk, int64_t n_head,
+                            const int32_t* kv_len, float* ctx, int64_t ldctx, float* weights, void* stream);
 
 /* ---------------------------------------------------------------------------
  * host ingest -- in front of a2: replaces shipping the fp32 waveform that librosa.load produced

@@ -35,6 +35,11 @@ from . import ops
 from ._lib import ACT_GELU_ERF, StacB200Error, ptr, stream
 from .convolution import _Holder, _params_version
 
+import os
+
+# STAC_BEAM_ATTENTION=0: the cached step's cross-attention on the general kernel (one CTA per hypothesis row)
+BEAM_ATTENTION = os.environ.get("STAC_BEAM_ATTENTION", "1") == "1"
+
 
 class _DecoderLayerParams(nn.Module):
     def __init__(self, d_model, nhead, d_ffn, dropout, activation):
@@ -104,6 +109,16 @@ class DecoderWeights:
     layers: List[DecoderLayerWeights] = field(default_factory=list)
     lnf_g: torch.Tensor = None
     lnf_b: torch.Tensor = None
+    _bf16: Optional[list] = None         # per layer: the GEMM weights as bf16 (tensor-core mode of DecoderCache)
+
+    def bf16_layers(self):
+        """bf16 copies of every layer's GEMM weights (stac_cast_bf16), built on first use."""
+        if self._bf16 is None:
+            out = []
+            for lw in self.layers:
+                out.append({k: _cast_bf16(getattr(lw, k)) for k in ("w_qkv", "w_o", "w_q2", "w_kv2", "w_o2", "w_1", "w_2")})
+            self._bf16 = out
+        return self._bf16
 
 
 def pack_decoder(decoder: DecoderParams, tgt_module: TgtModule, pe: torch.Tensor, nhead: int) -> DecoderWeights:
@@ -132,6 +147,13 @@ def pack_decoder(decoder: DecoderParams, tgt_module: TgtModule, pe: torch.Tensor
             f(ffn[0].weight), f(ffn[0].bias), f(ffn[3].weight), f(ffn[3].bias)))
     dw.lnf_g, dw.lnf_b = f(decoder.norm.norm.weight), f(decoder.norm.norm.bias)
     return dw
+
+
+def _cast_bf16(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    out = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    ops._call("stac_cast_bf16", ptr(t, torch.float32), t.numel(), ptr(out), stream())
+    return out
 
 
 def _off(t: torch.Tensor, elems: int) -> c_void_p:
@@ -203,6 +225,20 @@ def decoder_stack(tgt: torch.Tensor, memory: torch.Tensor, w: DecoderWeights, me
     return out, weights
 
 
+def _cross_attention_step(q, kv, d, t2, rows, group, heads, mem_len, ctx, weights):
+    """Cross-attention of one decoding step: all rows of an utterance in one CTA when the beam fits (a key / value row is
+    then read once per utterance, not once per hypothesis), else the general kernel."""
+    gp = (group + 3) // 4 * 4
+    smem = (16 * 64 + t2 * gp * (2 if weights is not None else 1) + 8 * 16 * 64) * 4
+    ml = ptr(mem_len, torch.int32) if mem_len is not None else ptr(None)
+    if BEAM_ATTENTION and group <= 16 and smem <= 220 * 1024:
+        ops._call("stac_attention_beam_f32", ptr(q), d, ptr(kv), _off(kv, d), t2 * 2 * d, 2 * d, rows, group, t2, heads, ml,
+                  ptr(ctx), d, ptr(weights), stream())
+    else:
+        ops._call("stac_attention_f32", ptr(q), d, ptr(kv), _off(kv, d), t2 * 2 * d, 2 * d, rows, 1, t2, heads, group, 0,
+                  ml, ptr(None), 0, ptr(ctx), d, ptr(weights), stream())
+
+
 class DecoderCache:
     """KV-cached incremental decoding: the same arithmetic as ``decoder_stack`` on the growing prefix, one token per
     call (what a beam searcher's ``forward_step`` needs, mutitask_decoder.py:119-128, without re-running the whole
@@ -213,25 +249,33 @@ class DecoderCache:
     * the self-attention keys / values of the prefix live in a time-major cache [layer][max_len][rows][2 d], so the
       projection of step t is written by the GEMM straight into slab t and a beam re-ordering is a row gather;
     * ``step(tokens)`` returns what ``decode(prefix)[0][:, -1]`` and ``decode(prefix)[1][:, -1]`` return.
-    Same entry points as ``decoder_stack`` (fp32, CUDA cores); no CPU fallback."""
+    precision "fp32": the entry points of ``decoder_stack`` (CUDA cores).  precision "bf16": every projection and the
+    feed-forward block run on the tensor cores (``stac_gemm_bf16``: bf16 operands, fp32 accumulation; the residual
+    stream, the caches, LayerNorm and both attentions stay fp32), which is what a step is made of at beam-search
+    sizes: 640 rows x seven small GEMMs per layer.  No CPU fallback."""
 
     def __init__(self, w: DecoderWeights, memory: torch.Tensor, rows: int, max_len: int,
-                 mem_len: Optional[torch.Tensor] = None):
+                 mem_len: Optional[torch.Tensor] = None, precision: str = "fp32"):
         bm, t2, d = memory.shape
         if d != w.d_model or rows % bm != 0:
             raise StacB200Error("encoder_out does not match the decoder (d_model / rows not a multiple of its batch)")
         if max_len > w.pe.shape[0]:
             raise StacB200Error(f"{max_len} steps exceed the positional-encoding table ({w.pe.shape[0]})")
+        if precision not in ("fp32", "bf16"):
+            raise StacB200Error("precision must be 'fp32' or 'bf16'")
         self.w, self.rows, self.max_len, self.t = w, rows, max_len, 0
         self.bm, self.t2, self.d = bm, t2, d
         self.mem_len = mem_len
+        self.precision = precision
         dev = memory.device
         f32 = dict(device=dev, dtype=torch.float32)
         mem = memory.float().contiguous().view(bm * t2, d)
+        self.wb = w.bf16_layers() if precision == "bf16" else None
+        mem_a = _cast_bf16(mem) if precision == "bf16" else mem
         self.cross_kv = []
-        for lw in w.layers:
+        for n, lw in enumerate(w.layers):
             kv = torch.empty(bm * t2, 2 * d, **f32)
-            ops._gemm(mem, lw.w_kv2, lw.b_kv2, kv, "fp32", tag="dec_mem_kv")
+            ops._gemm(mem_a, self.wb[n]["w_kv2"] if self.wb else lw.w_kv2, lw.b_kv2, kv, precision, tag="dec_mem_kv")
             self.cross_kv.append(kv)
         self.self_kv = torch.empty(len(w.layers), max_len, rows, 2 * d, **f32)
         self.x = torch.empty(rows, d, **f32)
@@ -239,6 +283,37 @@ class DecoderCache:
         self.q = torch.empty(rows, d, **f32)
         self.ctx = torch.empty(rows, d, **f32)
         self.ff = torch.empty(rows, w.layers[0].w_1.shape[0], **f32)
+        if precision == "bf16":
+            b16 = dict(device=dev, dtype=torch.bfloat16)
+            self.h16 = torch.empty(rows, d, **b16)
+            self.ctx16 = torch.empty(rows, d, **b16)
+            self.ff16 = torch.empty(rows, w.layers[0].w_1.shape[0], **b16)
+
+    def _step_bf16(self, tok, weights):
+        """One position on the tensor-core GEMMs (same sequence as the fp32 step)."""
+        w, r, d, t, t2 = self.w, self.rows, self.d, self.t, self.t2
+        h, x = w.nhead, self.x
+        for n, lw in enumerate(w.layers):
+            wb = self.wb[n]
+            last = n == len(w.layers) - 1
+            ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_bf16=self.h16)
+            ops._gemm(self.h16, wb["w_qkv"][:d], lw.b_qkv[:d], self.q, "bf16", tag="dec_q_self")
+            slab = self.self_kv[n, t]                              # [rows, 2 d]: keys | values of position t
+            ops._gemm(self.h16, wb["w_qkv"][d:], lw.b_qkv[d:], slab, "bf16", tag="dec_kv_self")
+            cache = self.self_kv[n]
+            ops._call("stac_attention_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, 1, t + 1, h,
+                      1, 0, ptr(None), ptr(None), 0, ptr(self.ctx), d, ptr(None), stream())
+            ops._call("stac_cast_bf16", ptr(self.ctx), self.ctx.numel(), ptr(self.ctx16), stream())
+            ops._gemm(self.ctx16, wb["w_o"], lw.b_o, x, "bf16", resid=x, tag="dec_out_proj")
+            ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_bf16=self.h16)
+            ops._gemm(self.h16, wb["w_q2"], lw.b_q2, self.q, "bf16", tag="dec_q")
+            _cross_attention_step(self.q, self.cross_kv[n], d, t2, r, r // self.bm, h, self.mem_len, self.ctx,
+                                  weights if last else None)
+            ops._call("stac_cast_bf16", ptr(self.ctx), self.ctx.numel(), ptr(self.ctx16), stream())
+            ops._gemm(self.ctx16, wb["w_o2"], lw.b_o2, x, "bf16", resid=x, tag="dec_out_proj2")
+            ops._layernorm(x, lw.ln3_g, lw.ln3_b, 1e-6, out_bf16=self.h16)
+            ops._gemm(self.h16, wb["w_1"], lw.b_1, self.ff16, "bf16", act=ACT_GELU_ERF, tag="dec_ffn1")
+            ops._gemm(self.ff16, wb["w_2"], lw.b_2, x, "bf16", resid=x, tag="dec_ffn2")
 
     def step(self, tokens: torch.Tensor):
         """tokens int64 [rows]: the token at position t of every hypothesis.  Returns (prediction [rows, d],
@@ -255,7 +330,9 @@ class DecoderCache:
         ops._call("stac_embed_scale_pe", ptr(tok, torch.int64), ptr(w.emb), _off(w.pe, t * d), r, 1, d, w.vocab,
                   math.sqrt(d), ptr(x), stream())
         weights = torch.empty(r, t2, device=x.device, dtype=torch.float32)
-        for n, lw in enumerate(w.layers):
+        if self.precision == "bf16":
+            self._step_bf16(tok, weights)
+        for n, lw in enumerate(w.layers if self.precision == "fp32" else []):
             last = n == len(w.layers) - 1
             ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_qkv[:d], lw.b_qkv[:d], self.q, "fp32", tag="dec_q_self")
@@ -267,10 +344,8 @@ class DecoderCache:
             ops._gemm(self.ctx, lw.w_o, lw.b_o, x, "fp32", resid=x, tag="dec_out_proj")
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_q2, lw.b_q2, self.q, "fp32", tag="dec_q")
-            kv = self.cross_kv[n]
-            ops._call("stac_attention_f32", ptr(self.q), d, ptr(kv), _off(kv, d), t2 * 2 * d, 2 * d, r, 1, t2, h,
-                      r // self.bm, 0, ptr(self.mem_len, torch.int32) if self.mem_len is not None else ptr(None),
-                      ptr(None), 0, ptr(self.ctx), d, ptr(weights) if last else ptr(None), stream())
+            _cross_attention_step(self.q, self.cross_kv[n], d, t2, r, r // self.bm, h, self.mem_len, self.ctx,
+                                  weights if last else None)
             ops._gemm(self.ctx, lw.w_o2, lw.b_o2, x, "fp32", resid=x, tag="dec_out_proj2")
             ops._layernorm(x, lw.ln3_g, lw.ln3_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_1, lw.b_1, self.ff, "fp32", act=ACT_GELU_ERF, tag="dec_ffn1")

@@ -96,6 +96,13 @@ class Emulator:
                 p = np.exp(s - s.max(1, keepdims=True))
                 out[b, :, h] = (p / p.sum(1, keepdims=True)) @ x[b, :nk, 2, h]
 
+    def stac_attention_beam_f32(self, q, ldq, k, v, kv_bs, kv_rs, rows, group, lk, n_head, kv_len, ctx, ldctx, weights,
+                                stream):
+        """One query per row, `group` rows per memory block: by its documentation the general attention with lq = 1."""
+        assert 0 < group <= 16 and rows % group == 0
+        self.stac_attention_f32(q, ldq, k, v, kv_bs, kv_rs, rows, 1, lk, n_head, group, 0, kv_len, 0, 0, ctx, ldctx,
+                                weights, stream)
+
     def stac_attention_f32(self, q, ldq, k, v, kv_bs, kv_rs, rows, lq, lk, n_head, mem_rows_div, causal, kv_len,
                            key_tokens, pad_idx, ctx, ldctx, weights, stream):
         n_mem = (rows + mem_rows_div - 1) // mem_rows_div

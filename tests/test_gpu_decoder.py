@@ -124,3 +124,30 @@ def test_kv_cached_steps_equal_full_prefix_decode_on_device():
     assert rel_l2(w[::beam], torch.from_numpy(d["attn"])[:, -1]) < FP32_TOL
     full, full_w = tr.decode(rows, enc_out.repeat_interleave(beam, 0))
     assert rel_l2(out, full[:, -1]) < 1e-5 and rel_l2(w, full_w[:, -1]) < 1e-5
+
+
+def test_kv_cached_steps_bf16_gemms_on_device():
+    """DecoderCache(precision="bf16") on the device: tensor-core GEMMs for every projection of the step, against the
+    fp32 cache step by step (bf16 tolerance) and against the reference-generated vectors; with beam rows over the
+    un-inflated memory and a re-ordering."""
+    from util import BF16_TOL
+    d, state = fixture()
+    tr = build(sb.TransformerMultiTask, state, precision="bf16").cuda()
+    prefix, enc_out = torch.from_numpy(d["prefix"]).cuda(), torch.from_numpy(d["enc_out"]).cuda()
+    beam = 3
+    rows = prefix.repeat_interleave(beam, 0)
+    c32 = tr.decoder_cache(enc_out, rows=rows.shape[0], max_len=rows.shape[1])
+    c16 = tr.decoder_cache(enc_out, rows=rows.shape[0], max_len=rows.shape[1], precision="bf16")
+    index = torch.arange(rows.shape[0], device="cuda").flip(0)
+    for t in range(rows.shape[1]):
+        if t == 2:
+            c32.reorder(index)
+            c16.reorder(index)
+        o32, w32 = c32.step(rows[:, t].contiguous())
+        o16, w16 = c16.step(rows[:, t].contiguous())
+        assert rel_l2(o16, o32) < BF16_TOL and rel_l2(w16, w32) < BF16_TOL, t
+    c16b = tr.decoder_cache(enc_out, rows=rows.shape[0], max_len=rows.shape[1], precision="bf16")
+    for t in range(rows.shape[1]):
+        out, w = c16b.step(rows[:, t].contiguous())
+    assert rel_l2(out[::beam], torch.from_numpy(d["pred"])[:, -1]) < BF16_TOL
+    assert rel_l2(w[::beam], torch.from_numpy(d["attn"])[:, -1]) < BF16_TOL

@@ -138,6 +138,32 @@ def test_kv_cached_steps_equal_the_full_prefix_decode(monkeypatch):
         cache.step(cur[:, 0].contiguous())
 
 
+def test_kv_cached_steps_in_bf16_mode(monkeypatch):
+    """DecoderCache(precision="bf16"): the step's projections and feed-forward block through stac_gemm_bf16 (bf16 operand
+    copies of the weights, bf16 LayerNorm outputs, fp32 caches and residual stream): every step within the bf16
+    tolerance of the fp32 cache and of the reference-generated vectors, same call structure (7 GEMMs per layer and step)."""
+    from util import BF16_TOL
+    d, state = fixture()
+    emu = abi_emulator.install(monkeypatch)
+    tr = build(sb.TransformerMultiTask, state, precision="fp32")
+    prefix, enc_out = torch.from_numpy(d["prefix"]), torch.from_numpy(d["enc_out"])
+    b, L = prefix.shape
+    c32 = tr.decoder_cache(enc_out, rows=b, max_len=L)
+    emu.calls.clear()
+    c16 = tr.decoder_cache(enc_out, rows=b, max_len=L, precision="bf16")
+    n_layers = len(tr.packed_decoder().layers)
+    assert emu.calls.count("stac_gemm_bf16") == n_layers                       # cross keys / values, once per layer
+    for t in range(L):
+        o32, w32 = c32.step(prefix[:, t])
+        emu.calls.clear()
+        o16, w16 = c16.step(prefix[:, t])
+        assert emu.calls.count("stac_gemm_bf16") == 7 * n_layers and "stac_gemm_f32" not in emu.calls
+        assert rel_l2(o16, o32) < BF16_TOL and rel_l2(w16, w32) < BF16_TOL, t
+    assert rel_l2(o16, torch.from_numpy(d["pred"])[:, -1]) < BF16_TOL
+    with pytest.raises(sb.StacB200Error):
+        tr.decoder_cache(enc_out, rows=b, max_len=L, precision="fp16")
+
+
 def test_turns_and_ingest_host_code_through_the_emulated_abi(monkeypatch):
     """The Python side of turns.py / ingest.py (argument order, slicing of the compacted spikes, shapes) with the
     emulator behind the C ABI: same golden lines as the reference function, same decode rule."""

@@ -26,7 +26,8 @@ def simt():
     lib = ctypes.CDLL(str(simt_build.build()))
     for name in ("stac_argmax_rows", "stac_ctc_spikes", "stac_embed_scale_pe", "stac_attention_f32",
                  "stac_pcm_i16_to_f32", "stac_utt_mean_std", "stac_layernorm", "stac_mha_f32", "stac_log_softmax",
-                 "stac_kv_lengths", "stac_cast_bf16", "stac_gemm_f32", "stac_spec_augment", "stac_ctc_loss"):
+                 "stac_kv_lengths", "stac_cast_bf16", "stac_gemm_f32", "stac_spec_augment", "stac_ctc_loss",
+                 "stac_attention_beam_f32"):
         res, args = _lib._SIGNATURES[name]
         getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
     return lib
@@ -345,3 +346,40 @@ def test_ctc_loss_kernel(simt, reduction):
         assert torch.allclose(got[:5], want[:5], rtol=1e-5, atol=1e-5)
     else:
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), (got, want)
+
+
+@pytest.mark.parametrize("group,lk,h,with_len,with_w", [(1, 37, 2, False, True), (3, 70, 4, True, True), (10, 129, 4, True, False),
+                                                         (16, 50, 1, False, True)])
+def test_attention_beam_kernel(simt, group, lk, h, with_len, with_w):
+    """stac_attention_beam_f32 from source (all hypothesis rows of an utterance in one CTA) against stac_attention_f32 from
+    source with lq = 1 - the kernel it replaces in the cached decoding step - and against fp64 softmax attention."""
+    g = torch.Generator().manual_seed(group * 100 + lk)
+    bm, d = 3, h * 64
+    rows = bm * group
+    q = torch.randn(rows, d, generator=g) * 0.3
+    kv = torch.randn(bm * lk, 2 * d, generator=g)
+    kl = torch.randint(1, lk + 1, (rows,), generator=g).int() if with_len else None
+    ctx_a, ctx_b = torch.full((rows, d), float("nan")), torch.full((rows, d), float("nan"))
+    w_a = torch.full((rows, lk), float("nan")) if with_w else None
+    w_b = torch.full((rows, lk), float("nan")) if with_w else None
+    k_ptr, v_ptr = c_void_p(kv.data_ptr()), c_void_p(kv.data_ptr() + d * 4)
+    assert simt.stac_attention_beam_f32(P(q), d, k_ptr, v_ptr, lk * 2 * d, 2 * d, rows, group, lk, h, P(kl), P(ctx_a), d,
+                                        P(w_a), None) == 0
+    assert simt.stac_attention_f32(P(q), d, k_ptr, v_ptr, lk * 2 * d, 2 * d, rows, 1, lk, h, group, 0, P(kl), None, 0,
+                                   P(ctx_b), d, P(w_b), None) == 0
+    assert torch.allclose(ctx_a, ctx_b, rtol=1e-5, atol=1e-6)
+    if with_w:
+        assert torch.allclose(w_a, w_b, rtol=1e-5, atol=1e-7)
+    # fp64 reference
+    qq = q.double().view(bm, group, h, 64)
+    kk = kv[:, :d].double().view(bm, lk, h, 64)
+    vv = kv[:, d:].double().view(bm, lk, h, 64)
+    sc = torch.einsum("bghd,bkhd->bghk", qq, kk)
+    if kl is not None:
+        mask = torch.arange(lk)[None, None, :] >= kl.view(bm, group, 1)
+        sc = sc.masked_fill(mask[:, :, None, :], float("-inf"))
+    pr = sc.softmax(-1)
+    want = torch.einsum("bghk,bkhd->bghd", pr, vv).reshape(rows, d)
+    assert torch.allclose(ctx_a.double(), want, rtol=1e-4, atol=1e-5)
+    if with_w:
+        assert torch.allclose(w_a.double(), pr.mean(2).reshape(rows, lk), rtol=1e-4, atol=1e-6)

@@ -52,4 +52,27 @@ def one_step():
 
 
 ms_step = timed(one_step)
-print(f"rows {rows}  prefix {a.prefix}  frames {a.frames}:  full-prefix decode {ms_full:.3f} ms   cached step {ms_step:.3f} ms")
+cache16 = tr.decoder_cache(enc, rows=rows, max_len=a.prefix + 8, precision="bf16")
+for t in range(a.prefix - 1):
+    cache16.step(tok[:, t].contiguous())
+
+
+def one_step16():
+    cache16.t = t0
+    cache16.step(tok[:, t0].contiguous())
+
+
+ms_step16 = timed(one_step16)
+# the same bf16 step replayed as a CUDA graph (what is left is the kernels, not the ~100 Python launches)
+g = torch.cuda.CUDAGraph()
+s = torch.cuda.Stream()
+s.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(s):
+    one_step16()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=s):
+        one_step16()
+torch.cuda.current_stream().wait_stream(s)
+ms_graph16 = timed(g.replay)
+print(f"rows {rows}  prefix {a.prefix}  frames {a.frames}:  full-prefix decode {ms_full:.3f} ms   cached step {ms_step:.3f} ms"
+      f"   cached step, bf16 GEMMs {ms_step16:.3f} ms   the same as a CUDA graph {ms_graph16:.3f} ms")
