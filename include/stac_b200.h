@@ -267,7 +267,10 @@ int stac_ctc_spikes(const int32_t* ids, int64_t batch, int64_t t2, int32_t turn_
  * stac_attention_beam_f32: the cross-attention of ONE decoding step for all hypothesis rows of an utterance at once
  *        (lq = 1, no causal / token masks; row r reads memory block r / group, group <= 16): a key / value row is loaded
  *        once per utterance instead of once per hypothesis.  Same arguments and arithmetic as stac_attention_f32;
- *        weights (or NULL): fp32 [rows, lk].  STAC_ERR_UNSUPPORTED_SHAPE: group > 16 or lk too long for shared memory
+ *        weights (or NULL): fp32 [rows, lk].  head_scratch (or NULL; only read when weights is given): fp32
+ *        [n_head, rows, lk] of work space - with it the heads run on separate CTAs (grid utterances x heads) and a second
+ *        kernel adds their probabilities up in head order; without it one CTA per utterance walks the heads (the same
+ *        sums, four times fewer CTAs).  STAC_ERR_UNSUPPORTED_SHAPE: group > 16 or lk too long for shared memory
  *        (use stac_attention_f32). */
 int stac_embed_scale_pe(const int64_t* tokens, const float* emb, const float* pe, int64_t rows, int64_t seq_len,
                         int64_t d_model, int64_t vocab, float scale, float* out, void* stream);
@@ -278,7 +281,8 @@ int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float*
                        float* weights, void* stream);
 int stac_attention_beam_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
                             int64_t kv_row_stride, int64_t rows, int64_t group, int64_t lk, int64_t n_head,
-                            const int32_t* kv_len, float* ctx, int64_t ldctx, float* weights, void* stream);
+                            const int32_t* kv_len, float* ctx, int64_t ldctx, float* weights, float* head_scratch,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------
  * host ingest -- in front of a2: replaces shipping the fp32 waveform that librosa.load produced

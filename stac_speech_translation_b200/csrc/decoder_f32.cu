@@ -111,6 +111,82 @@ attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __
     for (int j = tid; j < lk; j += kThreads) weights[qrow * lk + j] = wacc[j];
 }
 
+// One decoding step over a short cache (lq = 1, no weights, no token mask, lk <= 256): one WARP per (row, head) - lane =
+// key for the scores (probabilities stay in eight registers per lane), lane = two value columns for P . V, shuffles
+// instead of barriers.  (The CTA-per-row kernel above spends a step's 640 x 4 tiny problems on block reductions and on
+// 16 dependent loads per thread: 37 us per launch at 32 keys.)
+constexpr int kStepWarps = 8, kStepMaxKeys = 256;
+
+__global__ void __launch_bounds__(kStepWarps * 32)
+attention_step_warp_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
+                           const float* __restrict__ v, long long kv_bs, long long kv_rs, int lk, int n_head,
+                           int mem_rows_div, const int* __restrict__ kv_len, float* __restrict__ ctx, long long ldctx,
+                           long long rows) {
+  __shared__ __align__(16) float qs[kStepWarps][kHd];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * kStepWarps + warp;
+  if (item >= rows * n_head) return;                 // (whole warps leave: no CTA barrier below)
+  const long long row = item / n_head;
+  const int h = (int)(item % n_head);
+  const long long rb = row / mem_rows_div;
+  int n_keys = lk;
+  if (kv_len != nullptr) n_keys = min(max(kv_len[row], 0), lk);
+  reinterpret_cast<float2*>(qs[warp])[lane] = *reinterpret_cast<const float2*>(q + row * ldq + h * kHd + 2 * lane);
+  __syncwarp();
+  const float* kb = k + rb * kv_bs + h * kHd;
+  const float* vb = v + rb * kv_bs + h * kHd;
+  float p[kStepMaxKeys / 32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kStepMaxKeys / 32; ++i) {
+    const int j = 32 * i + lane;
+    float a = -INFINITY;
+    if (j < n_keys) {
+      const float4* kp = reinterpret_cast<const float4*>(kb + (long long)j * kv_rs);
+      a = 0.f;
+#pragma unroll
+      for (int c = 0; c < kHd / 4; ++c) {
+        const float4 kk = __ldg(kp + c);
+        const float4 qq = reinterpret_cast<const float4*>(qs[warp])[c];
+        a = fmaf(qq.x, kk.x, a);
+        a = fmaf(qq.y, kk.y, a);
+        a = fmaf(qq.z, kk.z, a);
+        a = fmaf(qq.w, kk.w, a);
+      }
+    }
+    p[i] = a;
+    mx = fmaxf(mx, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kStepMaxKeys / 32; ++i) {
+    p[i] = p[i] == -INFINITY ? 0.f : expf(p[i] - mx);
+    sum += p[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;                      // every key masked: 0 * inf = NaN, as the kernel above
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < kStepMaxKeys / 32; ++i) {
+    if (32 * i < n_keys) {                           // (warp-uniform)
+#pragma unroll 16
+      for (int jj = 0; jj < 32; ++jj) {
+        const float pj = __shfl_sync(0xffffffffu, p[i], jj);
+        const int j = 32 * i + jj;
+        if (j < n_keys) {
+          const float2 vv = __ldg(reinterpret_cast<const float2*>(vb + (long long)j * kv_rs) + lane);
+          acc.x = fmaf(pj, vv.x, acc.x);
+          acc.y = fmaf(pj, vv.y, acc.y);
+        }
+      }
+    }
+  }
+  *reinterpret_cast<float2*>(ctx + row * ldctx + h * kHd + 2 * lane) = make_float2(acc.x * inv, acc.y * inv);
+}
+
 // Cross-attention of one decoding step, all hypothesis rows of an utterance in ONE CTA (round 2): in a KV-cached beam
 // search every row asks one query and the `group` rows of an utterance attend the SAME encoder keys / values; with a CTA
 // per row (attention_f32_kernel) a step of 640 rows read 640 x 1.5 MB of keys and values per layer through L2.  Here a
@@ -118,18 +194,20 @@ attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __
 // no causal / token masks.  Dynamic shared memory: qs[16][64] | p[lk][gp] | wacc[lk][gp] (if weights) | red[8][16][64].
 constexpr int kBeamThreads = 256, kMaxGroup = 16;
 
+template <int kG4>                                  // rows of the group, rounded up to a multiple of four, / 4
 __global__ void __launch_bounds__(kBeamThreads)
 attention_beam_f32_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
-                          const float* __restrict__ v, long long kv_bs, long long kv_rs, int group, int gp, int lk,
+                          const float* __restrict__ v, long long kv_bs, long long kv_rs, int group, int lk,
                           int n_head, const int* __restrict__ kv_len, float* __restrict__ ctx, long long ldctx,
-                          float* __restrict__ weights) {
+                          float* __restrict__ weights, float* __restrict__ head_p, long long rows) {
+  constexpr int gp = 4 * kG4;
   extern __shared__ float sm[];
   float* qs = sm;                                   // [kMaxGroup][64]
   float* pr = qs + kMaxGroup * kHd;                 // [lk][gp]: scores, then probabilities
   float* wacc = pr + (size_t)lk * gp;               // [lk][gp] (only if weights)
-  float* red = wacc + (weights != nullptr ? (size_t)lk * gp : 0);      // [8][kMaxGroup][64]
+  float* red = wacc + (weights != nullptr ? (size_t)lk * gp : 0);      // [8][kMaxGroup][64]; its head: [8][16] exchange
   __shared__ int nk[kMaxGroup];
-  __shared__ float inv_s[kMaxGroup];
+  __shared__ float mx_s[kMaxGroup], inv_s[kMaxGroup];
   const int u = blockIdx.x;                         // memory block (utterance)
   const long long row0 = (long long)u * group;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,85 +217,136 @@ attention_beam_f32_kernel(const float* __restrict__ q, long long ldq, const floa
   if (weights != nullptr)
     for (int i = tid; i < lk * gp; i += kBeamThreads) wacc[i] = 0.f;
   const float inv_heads = 1.0f / (float)n_head;
-  // without the averaged weights the heads are independent: one CTA per (utterance, head) (gridDim.y = heads)
+  // without the in-CTA head average the heads are independent: one CTA per (utterance, head) (gridDim.y = heads)
   const int h_begin = gridDim.y > 1 ? (int)blockIdx.y : 0, h_end = gridDim.y > 1 ? (int)blockIdx.y + 1 : n_head;
   for (int h = h_begin; h < h_end; ++h) {
     __syncthreads();                                // qs / pr / red of the previous head are no longer read
-    for (int i = tid; i < group * kHd; i += kBeamThreads)
-      qs[i] = q[(row0 + i / kHd) * ldq + h * kHd + (i & (kHd - 1))];
+    for (int i = tid; i < gp * kHd; i += kBeamThreads) {
+      const int g = i / kHd;
+      qs[i] = g < group ? q[(row0 + g) * ldq + h * kHd + (i & (kHd - 1))] : 0.f;
+    }
     __syncthreads();
-    // scores: one key per thread, its 64 values in registers, every row of the group against it
+    // scores: one key per thread, its 64 values in registers, four rows of the group at a time against it (four
+    // independent FMA chains; one chain per row ran at the FMA latency: 43 % of the kernel's stall samples)
+    float mxl[gp];
+#pragma unroll
+    for (int g = 0; g < gp; ++g) mxl[g] = -INFINITY;
     for (int j = tid; j < lk; j += kBeamThreads) {
       float4 kk[kHd / 4];
       const float4* kp = reinterpret_cast<const float4*>(kb + (long long)j * kv_rs + h * kHd);
 #pragma unroll
       for (int c = 0; c < kHd / 4; ++c) kk[c] = __ldg(kp + c);
-      for (int g = 0; g < group; ++g) {
-        const float4* q4 = reinterpret_cast<const float4*>(qs + g * kHd);
-        float a = 0.f;
+#pragma unroll
+      for (int g4 = 0; g4 < kG4; ++g4) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < kHd / 4; ++c) {
-          const float4 qq = q4[c];
-          a = fmaf(qq.x, kk[c].x, a);
-          a = fmaf(qq.y, kk[c].y, a);
-          a = fmaf(qq.z, kk[c].z, a);
-          a = fmaf(qq.w, kk[c].w, a);
-        }
-        pr[(size_t)j * gp + g] = j < nk[g] ? a : -INFINITY;
-      }
-    }
-    __syncthreads();
-    // softmax of every row: warp w takes rows w, w + 8
-    for (int g = warp; g < group; g += kBeamThreads / 32) {
-      float mx = -INFINITY;
-      for (int j = lane; j < lk; j += 32) mx = fmaxf(mx, pr[(size_t)j * gp + g]);
-      mx = warp_max(mx);
-      float sum = 0.f;
-      for (int j = lane; j < lk; j += 32) {
-        const float sc = pr[(size_t)j * gp + g];
-        const float p = sc == -INFINITY ? 0.f : expf(sc - mx);
-        pr[(size_t)j * gp + g] = p;
-        sum += p;
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) inv_s[g] = 1.0f / sum;         // every key masked: 0 * inf = NaN, as torch's softmax of -inf
-    }
-    __syncthreads();
-    // P . V: thread = (four value columns, one of sixteen key subsets), four accumulators per row of the group; the two
-    // subsets of a warp meet by shuffle, the eight warps through shared memory.  (The first version gave a thread one
-    // column and a quarter of the keys: 188 dependent global loads per head and thread - 300 us per launch.)
-    const int dq = tid & 15, ks = tid >> 4;
-    float4 acc[kMaxGroup];
-#pragma unroll
-    for (int g = 0; g < kMaxGroup; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int j = ks; j < lk; j += kBeamThreads / 16) {
-      const float4 vj = __ldg(reinterpret_cast<const float4*>(vb + (long long)j * kv_rs + h * kHd) + dq);
-      const float4* p4 = reinterpret_cast<const float4*>(pr + (size_t)j * gp);
-#pragma unroll
-      for (int g4 = 0; g4 < kMaxGroup / 4; ++g4) {
-        if (4 * g4 < gp) {
-          const float4 pp = p4[g4];
-          const float pv[4] = {pp.x, pp.y, pp.z, pp.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            acc[4 * g4 + e].x = fmaf(pv[e], vj.x, acc[4 * g4 + e].x);
-            acc[4 * g4 + e].y = fmaf(pv[e], vj.y, acc[4 * g4 + e].y);
-            acc[4 * g4 + e].z = fmaf(pv[e], vj.z, acc[4 * g4 + e].z);
-            acc[4 * g4 + e].w = fmaf(pv[e], vj.w, acc[4 * g4 + e].w);
+            const float4 qq = reinterpret_cast<const float4*>(qs + (4 * g4 + e) * kHd)[c];
+            a[e] = fmaf(qq.x, kk[c].x, a[e]);
+            a[e] = fmaf(qq.y, kk[c].y, a[e]);
+            a[e] = fmaf(qq.z, kk[c].z, a[e]);
+            a[e] = fmaf(qq.w, kk[c].w, a[e]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          a[e] = j < nk[4 * g4 + e] ? a[e] : -INFINITY;
+          mxl[4 * g4 + e] = fmaxf(mxl[4 * g4 + e], a[e]);
+        }
+        reinterpret_cast<float4*>(pr + (size_t)j * gp)[g4] = make_float4(a[0], a[1], a[2], a[3]);
+      }
+    }
+    // softmax, every thread on its own keys: row maxima and row sums meet through shuffles and red[8][16]
+#pragma unroll
+    for (int g = 0; g < gp; ++g) {
+      const float m = warp_max(mxl[g]);
+      if (lane == 0) red[warp * kMaxGroup + g] = m;
+    }
+    __syncthreads();
+    if (tid < gp) {
+      float m = red[tid];
+      for (int w2 = 1; w2 < kBeamThreads / 32; ++w2) m = fmaxf(m, red[w2 * kMaxGroup + tid]);
+      mx_s[tid] = m;
+    }
+    __syncthreads();
+    float sl[gp];
+#pragma unroll
+    for (int g = 0; g < gp; ++g) {
+      mxl[g] = mx_s[g];
+      sl[g] = 0.f;
+    }
+    for (int j = tid; j < lk; j += kBeamThreads) {
+#pragma unroll
+      for (int g4 = 0; g4 < kG4; ++g4) {
+        float4 sc = reinterpret_cast<const float4*>(pr + (size_t)j * gp)[g4];
+        sc.x = sc.x == -INFINITY ? 0.f : expf(sc.x - mxl[4 * g4]);
+        sc.y = sc.y == -INFINITY ? 0.f : expf(sc.y - mxl[4 * g4 + 1]);
+        sc.z = sc.z == -INFINITY ? 0.f : expf(sc.z - mxl[4 * g4 + 2]);
+        sc.w = sc.w == -INFINITY ? 0.f : expf(sc.w - mxl[4 * g4 + 3]);
+        sl[4 * g4] += sc.x;
+        sl[4 * g4 + 1] += sc.y;
+        sl[4 * g4 + 2] += sc.z;
+        sl[4 * g4 + 3] += sc.w;
+        reinterpret_cast<float4*>(pr + (size_t)j * gp)[g4] = sc;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < gp; ++g) {
+      const float t = warp_sum(sl[g]);
+      if (lane == 0) red[warp * kMaxGroup + g] = t;
+    }
+    __syncthreads();
+    if (tid < gp) {
+      float t = red[tid];
+      for (int w2 = 1; w2 < kBeamThreads / 32; ++w2) t += red[w2 * kMaxGroup + tid];
+      inv_s[tid] = 1.0f / t;                        // every key masked: 0 * inf = NaN, as torch's softmax of -inf
+    }
+    __syncthreads();
+    // P . V: thread = (four value columns, one of sixteen key subsets), four accumulators per row of the group, eight
+    // value loads in flight; the two subsets of a warp meet by shuffle, the eight warps through shared memory.  (The
+    // first version gave a thread one column and a quarter of the keys: 188 dependent global loads per head and thread -
+    // 300 us per launch.)
+    const int dq = tid & 15, ks = tid >> 4;
+    constexpr int kFly = 8, kSub = kBeamThreads / 16;
+    float4 acc[gp];
+#pragma unroll
+    for (int g = 0; g < gp; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = ks; j0 < lk; j0 += kSub * kFly) {
+      float4 vj[kFly];
+#pragma unroll
+      for (int f = 0; f < kFly; ++f) {
+        const int j = j0 + kSub * f;
+        vj[f] = j < lk ? __ldg(reinterpret_cast<const float4*>(vb + (long long)j * kv_rs + h * kHd) + dq)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int f = 0; f < kFly; ++f) {
+        const int j = j0 + kSub * f;
+        if (j < lk) {
+#pragma unroll
+          for (int g4 = 0; g4 < kG4; ++g4) {
+            const float4 pp = reinterpret_cast<const float4*>(pr + (size_t)j * gp)[g4];
+            const float pv[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[4 * g4 + e].x = fmaf(pv[e], vj[f].x, acc[4 * g4 + e].x);
+              acc[4 * g4 + e].y = fmaf(pv[e], vj[f].y, acc[4 * g4 + e].y);
+              acc[4 * g4 + e].z = fmaf(pv[e], vj[f].z, acc[4 * g4 + e].z);
+              acc[4 * g4 + e].w = fmaf(pv[e], vj[f].w, acc[4 * g4 + e].w);
+            }
           }
         }
       }
     }
 #pragma unroll
-    for (int g = 0; g < kMaxGroup; ++g) {
-      if (g < gp) {
-        acc[g].x += __shfl_xor_sync(0xffffffffu, acc[g].x, 16);
-        acc[g].y += __shfl_xor_sync(0xffffffffu, acc[g].y, 16);
-        acc[g].z += __shfl_xor_sync(0xffffffffu, acc[g].z, 16);
-        acc[g].w += __shfl_xor_sync(0xffffffffu, acc[g].w, 16);
-        if (lane < 16) reinterpret_cast<float4*>(red + (warp * kMaxGroup + g) * kHd)[dq] = acc[g];
-      }
+    for (int g = 0; g < gp; ++g) {
+      acc[g].x += __shfl_xor_sync(0xffffffffu, acc[g].x, 16);
+      acc[g].y += __shfl_xor_sync(0xffffffffu, acc[g].y, 16);
+      acc[g].z += __shfl_xor_sync(0xffffffffu, acc[g].z, 16);
+      acc[g].w += __shfl_xor_sync(0xffffffffu, acc[g].w, 16);
+      if (lane < 16) reinterpret_cast<float4*>(red + (warp * kMaxGroup + g) * kHd)[dq] = acc[g];
     }
     __syncthreads();
     for (int i = tid; i < group * kHd; i += kBeamThreads) {
@@ -232,11 +361,27 @@ attention_beam_f32_kernel(const float* __restrict__ q, long long ldq, const floa
         const int g = i % gp;
         if (g < group) wacc[i] += pr[i] * inv_s[g] * inv_heads;
       }
+    if (head_p != nullptr)                           // heads on separate CTAs: head_average_kernel adds them up
+      for (int g = 0; g < group; ++g)
+        for (int j = tid; j < lk; j += kBeamThreads)
+          head_p[((long long)h * rows + row0 + g) * lk + j] = pr[(size_t)j * gp + g] * inv_s[g];
   }
   if (weights != nullptr) {
     __syncthreads();
     for (int g = 0; g < group; ++g)
       for (int j = tid; j < lk; j += kBeamThreads) weights[(row0 + g) * lk + j] = wacc[(size_t)j * gp + g];
+  }
+}
+
+// weights[i] = sum over the heads, in head order, of head_p[h][i] / heads (the order and the rounding of the
+// one-CTA-for-all-heads path above)
+__global__ void __launch_bounds__(256)
+head_average_kernel(const float* __restrict__ head_p, long long n, int n_head, float* __restrict__ weights) {
+  const float inv_heads = 1.0f / (float)n_head;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int h = 0; h < n_head; ++h) a += head_p[(long long)h * n + i] * inv_heads;
+    weights[i] = a;
   }
 }
 
@@ -265,6 +410,17 @@ extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, c
   if (kv_row_stride % 4 != 0 || kv_batch_stride % 4 != 0 || (reinterpret_cast<uintptr_t>(k) & 15) != 0)
     return STAC_ERR_UNSUPPORTED_SHAPE;
   if (rows * lq >= (1ll << 31) || lk >= (1 << 24) || n_head > 65535) return STAC_ERR_UNSUPPORTED_SHAPE;
+  if (lq == 1 && weights == nullptr && key_tokens == nullptr && lk <= kStepMaxKeys && kv_row_stride % 2 == 0 &&
+      ldq % 2 == 0 && ldctx % 2 == 0 && (reinterpret_cast<uintptr_t>(q) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(v) & 7) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 7) == 0) {
+    // (lq = 1: "causal" only caps the keys at 1, which a one-token prefix already is)
+    const long long items = (long long)rows * n_head;
+    const int lk_eff = causal ? 1 : (int)lk;
+    attention_step_warp_kernel<<<(unsigned)((items + kStepWarps - 1) / kStepWarps), kStepWarps * 32, 0, as_stream(stream)>>>(
+        q, (long long)ldq, k, v, (long long)kv_batch_stride, (long long)kv_row_stride, lk_eff, (int)n_head,
+        (int)mem_rows_div, kv_len, ctx, (long long)ldctx, (long long)rows);
+    STAC_LAUNCH_CHECK();
+  }
   const size_t smem = (size_t)(2 * lk + kHd + kThreads + 40) * sizeof(float);
   if (smem > 200 * 1024) return STAC_ERR_UNSUPPORTED_SHAPE;
   if (smem > 48 * 1024) {
@@ -280,7 +436,7 @@ extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, c
 extern "C" int stac_attention_beam_f32(const float* q, int64_t ldq, const float* k, const float* v,
                                        int64_t kv_batch_stride, int64_t kv_row_stride, int64_t rows, int64_t group,
                                        int64_t lk, int64_t n_head, const int32_t* kv_len, float* ctx, int64_t ldctx,
-                                       float* weights, void* stream) {
+                                       float* weights, float* head_scratch, void* stream) {
   STAC_REQUIRE(q && k && v && ctx && rows > 0 && group > 0 && lk > 0 && n_head > 0 && rows % group == 0);
   STAC_REQUIRE(ldq >= n_head * kHd && kv_row_stride >= n_head * kHd && kv_batch_stride > 0 && ldctx >= n_head * kHd);
   if (group > kMaxGroup) return STAC_ERR_UNSUPPORTED_SHAPE;          // wider beams: stac_attention_f32
@@ -289,15 +445,37 @@ extern "C" int stac_attention_beam_f32(const float* q, int64_t ldq, const float*
     return STAC_ERR_UNSUPPORTED_SHAPE;
   if (rows / group >= (1ll << 31) || lk >= (1 << 24) || n_head > 65535) return STAC_ERR_UNSUPPORTED_SHAPE;
   const int gp = (int)((group + 3) / 4 * 4);
-  const size_t smem = ((size_t)kMaxGroup * kHd + (size_t)lk * gp * (weights ? 2 : 1) + (size_t)8 * kMaxGroup * kHd) * sizeof(float);
+  // the averaged weights: with a scratch of heads x rows x lk floats the heads still run on separate CTAs and a second
+  // kernel adds them up; without one, one CTA per utterance walks the heads and sums in shared memory
+  const bool serial_heads = weights != nullptr && head_scratch == nullptr;
+  const size_t smem =
+      ((size_t)kMaxGroup * kHd + (size_t)lk * gp * (serial_heads ? 2 : 1) + (size_t)8 * kMaxGroup * kHd) * sizeof(float);
   if (smem > 220 * 1024) return STAC_ERR_UNSUPPORTED_SHAPE;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(attention_beam_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+  const dim3 grid((unsigned)(rows / group), serial_heads ? 1u : (unsigned)n_head);
+  float* w_serial = serial_heads ? weights : nullptr;
+  float* w_heads = weights != nullptr && !serial_heads ? head_scratch : nullptr;
+#define STAC_BEAM_LAUNCH(G4)                                                                                          \
+  do {                                                                                                                \
+    if (smem > 48 * 1024) {                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(attention_beam_f32_kernel<G4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem);                                                                \
+      if (e != cudaSuccess) return (int)e;                                                                            \
+    }                                                                                                                 \
+    attention_beam_f32_kernel<G4><<<grid, kBeamThreads, smem, as_stream(stream)>>>(                                   \
+        q, (long long)ldq, k, v, (long long)kv_batch_stride, (long long)kv_row_stride, (int)group, (int)lk,           \
+        (int)n_head, kv_len, ctx, (long long)ldctx, w_serial, w_heads, (long long)rows);                              \
+  } while (0)
+  switch (gp / 4) {
+    case 1: STAC_BEAM_LAUNCH(1); break;
+    case 2: STAC_BEAM_LAUNCH(2); break;
+    case 3: STAC_BEAM_LAUNCH(3); break;
+    default: STAC_BEAM_LAUNCH(4); break;
   }
-  attention_beam_f32_kernel<<<dim3((unsigned)(rows / group), weights ? 1u : (unsigned)n_head), kBeamThreads, smem,
-                              as_stream(stream)>>>(
-      q, (long long)ldq, k, v, (long long)kv_batch_stride, (long long)kv_row_stride, (int)group, gp, (int)lk, (int)n_head,
-      kv_len, ctx, (long long)ldctx, weights);
+#undef STAC_BEAM_LAUNCH
+  if (weights != nullptr && !serial_heads) {
+    const long long n = (long long)rows * lk;
+    head_average_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, as_stream(stream)>>>(
+        head_scratch, n, (int)n_head, weights);
+  }
   STAC_LAUNCH_CHECK();
 }

@@ -225,15 +225,15 @@ def decoder_stack(tgt: torch.Tensor, memory: torch.Tensor, w: DecoderWeights, me
     return out, weights
 
 
-def _cross_attention_step(q, kv, d, t2, rows, group, heads, mem_len, ctx, weights):
+def _cross_attention_step(q, kv, d, t2, rows, group, heads, mem_len, ctx, weights, head_scratch=None):
     """Cross-attention of one decoding step: all rows of an utterance in one CTA when the beam fits (a key / value row is
     then read once per utterance, not once per hypothesis), else the general kernel."""
     gp = (group + 3) // 4 * 4
-    smem = (16 * 64 + t2 * gp * (2 if weights is not None else 1) + 8 * 16 * 64) * 4
+    smem = (16 * 64 + t2 * gp * (2 if weights is not None and head_scratch is None else 1) + 8 * 16 * 64) * 4
     ml = ptr(mem_len, torch.int32) if mem_len is not None else ptr(None)
     if BEAM_ATTENTION and group <= 16 and smem <= 220 * 1024:
         ops._call("stac_attention_beam_f32", ptr(q), d, ptr(kv), _off(kv, d), t2 * 2 * d, 2 * d, rows, group, t2, heads, ml,
-                  ptr(ctx), d, ptr(weights), stream())
+                  ptr(ctx), d, ptr(weights), ptr(head_scratch), stream())
     else:
         ops._call("stac_attention_f32", ptr(q), d, ptr(kv), _off(kv, d), t2 * 2 * d, 2 * d, rows, 1, t2, heads, group, 0,
                   ml, ptr(None), 0, ptr(ctx), d, ptr(weights), stream())
@@ -282,6 +282,8 @@ class DecoderCache:
         self.h = torch.empty(rows, d, **f32)
         self.q = torch.empty(rows, d, **f32)
         self.ctx = torch.empty(rows, d, **f32)
+        # per-head probabilities of the last layer's cross-attention (its head average is what step() returns)
+        self.head_scratch = torch.empty(w.nhead, rows, t2, **f32)
         self.ff = torch.empty(rows, w.layers[0].w_1.shape[0], **f32)
         if precision == "bf16":
             b16 = dict(device=dev, dtype=torch.bfloat16)
@@ -308,7 +310,7 @@ class DecoderCache:
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_bf16=self.h16)
             ops._gemm(self.h16, wb["w_q2"], lw.b_q2, self.q, "bf16", tag="dec_q")
             _cross_attention_step(self.q, self.cross_kv[n], d, t2, r, r // self.bm, h, self.mem_len, self.ctx,
-                                  weights if last else None)
+                                  weights if last else None, self.head_scratch)
             ops._call("stac_cast_bf16", ptr(self.ctx), self.ctx.numel(), ptr(self.ctx16), stream())
             ops._gemm(self.ctx16, wb["w_o2"], lw.b_o2, x, "bf16", resid=x, tag="dec_out_proj2")
             ops._layernorm(x, lw.ln3_g, lw.ln3_b, 1e-6, out_bf16=self.h16)
@@ -345,7 +347,7 @@ class DecoderCache:
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_q2, lw.b_q2, self.q, "fp32", tag="dec_q")
             _cross_attention_step(self.q, self.cross_kv[n], d, t2, r, r // self.bm, h, self.mem_len, self.ctx,
-                                  weights if last else None)
+                                  weights if last else None, self.head_scratch)
             ops._gemm(self.ctx, lw.w_o2, lw.b_o2, x, "fp32", resid=x, tag="dec_out_proj2")
             ops._layernorm(x, lw.ln3_g, lw.ln3_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_1, lw.b_1, self.ff, "fp32", act=ACT_GELU_ERF, tag="dec_ffn1")

@@ -97,7 +97,7 @@ class Emulator:
                 out[b, :, h] = (p / p.sum(1, keepdims=True)) @ x[b, :nk, 2, h]
 
     def stac_attention_beam_f32(self, q, ldq, k, v, kv_bs, kv_rs, rows, group, lk, n_head, kv_len, ctx, ldctx, weights,
-                                stream):
+                                head_scratch, stream):
         """One query per row, `group` rows per memory block: by its documentation the general attention with lq = 1."""
         assert 0 < group <= 16 and rows % group == 0
         self.stac_attention_f32(q, ldq, k, v, kv_bs, kv_rs, rows, 1, lk, n_head, group, 0, kv_len, 0, 0, ctx, ldctx,

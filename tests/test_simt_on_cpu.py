@@ -108,6 +108,31 @@ def test_attention_f32_kernel(simt, rows, lq, lk, h, div, causal):
     assert (w.double() - p.mean(1)).norm() / p.mean(1).norm() < 1e-5
 
 
+@pytest.mark.parametrize("rows,lk,h,div,with_len", [(5, 1, 1, 1, False), (6, 33, 2, 2, True), (3, 256, 4, 1, True),
+                                                    (9, 70, 4, 3, False)])
+def test_attention_step_warp_kernel(simt, rows, lk, h, div, with_len):
+    """lq = 1 without weights / token mask and at most 256 keys: stac_attention_f32 runs the warp-per-(row, head) kernel
+    (rows * h not a multiple of the eight warps of a CTA: idle warps leave)."""
+    g = torch.Generator().manual_seed(rows * 1000 + lk)
+    d = 64 * h
+    n_mem = rows // div
+    q = torch.randn(rows, d, generator=g)
+    kv = torch.randn(n_mem * lk, 2 * d, generator=g)
+    kv_len = torch.randint(1, lk + 1, (rows,), generator=g, dtype=torch.int32)
+    ctx = torch.full((rows, d), float("nan"))
+    rc = simt.stac_attention_f32(P(q), d, P(kv), c_void_p(kv.data_ptr() + 4 * d), lk * 2 * d, 2 * d, rows, 1, lk, h, div,
+                                 0, P(kv_len) if with_len else None, None, 0, P(ctx), d, None, None)
+    assert rc == 0
+    qq = q.view(rows, 1, h, 64).permute(0, 2, 1, 3).double()
+    k = kv[:, :d].reshape(n_mem, lk, h, 64).permute(0, 2, 1, 3).double().repeat_interleave(div, 0)
+    v = kv[:, d:].reshape(n_mem, lk, h, 64).permute(0, 2, 1, 3).double().repeat_interleave(div, 0)
+    sc = qq @ k.transpose(-1, -2)
+    if with_len:
+        sc = sc.masked_fill((torch.arange(lk)[None, :] >= kv_len[:, None])[:, None, None, :], float("-inf"))
+    want = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(rows, d)
+    assert (ctx.double() - want).norm() / want.norm() < 1e-5
+
+
 def test_attention_time_major_cache_and_embedding(simt):
     """The addressing DecoderCache uses: keys / values in a time-major cache [lk][rows][2 d]; and the embedding kernel
     with a position offset into the table."""
@@ -364,7 +389,13 @@ def test_attention_beam_kernel(simt, group, lk, h, with_len, with_w):
     w_b = torch.full((rows, lk), float("nan")) if with_w else None
     k_ptr, v_ptr = c_void_p(kv.data_ptr()), c_void_p(kv.data_ptr() + d * 4)
     assert simt.stac_attention_beam_f32(P(q), d, k_ptr, v_ptr, lk * 2 * d, 2 * d, rows, group, lk, h, P(kl), P(ctx_a), d,
-                                        P(w_a), None) == 0
+                                        P(w_a), None, None) == 0
+    if with_w:                  # the same with the heads on separate CTAs (scratch given): bit-identical weights
+        ctx_c, w_c = torch.full((rows, d), float("nan")), torch.full((rows, lk), float("nan"))
+        scratch = torch.full((h, rows, lk), float("nan"))
+        assert simt.stac_attention_beam_f32(P(q), d, k_ptr, v_ptr, lk * 2 * d, 2 * d, rows, group, lk, h, P(kl), P(ctx_c),
+                                            d, P(w_c), P(scratch), None) == 0
+        assert torch.equal(ctx_c, ctx_a) and torch.equal(w_c, w_a)
     assert simt.stac_attention_f32(P(q), d, k_ptr, v_ptr, lk * 2 * d, 2 * d, rows, 1, lk, h, group, 0, P(kl), None, 0,
                                    P(ctx_b), d, P(w_b), None) == 0
     assert torch.allclose(ctx_a, ctx_b, rtol=1e-5, atol=1e-6)

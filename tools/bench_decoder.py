@@ -76,3 +76,19 @@ torch.cuda.current_stream().wait_stream(s)
 ms_graph16 = timed(g.replay)
 print(f"rows {rows}  prefix {a.prefix}  frames {a.frames}:  full-prefix decode {ms_full:.3f} ms   cached step {ms_step:.3f} ms"
       f"   cached step, bf16 GEMMs {ms_step16:.3f} ms   the same as a CUDA graph {ms_graph16:.3f} ms")
+if os.environ.get("STAC_DECODER_PROFILE", "1") != "0":
+    # warm per-kernel device times of the graph-less bf16 step (CUPTI through torch.profiler; a breakdown, not a bench value)
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        n_prof = 5
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(n_prof):
+                one_step16()
+            torch.cuda.synchronize()
+        rows_ = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        print("kernel, launches per step, us per launch, us per step")
+        for e in rows_[:12]:
+            print(f"  {e.key[:70]:70s} {e.count / n_prof:6.1f} {e.device_time_total / max(e.count, 1):9.2f} "
+                  f"{e.device_time_total / n_prof:9.1f}")
+    except Exception as exc:  # noqa: BLE001 - the breakdown is optional
+        print("profiler breakdown unavailable:", exc)
