@@ -271,7 +271,13 @@ int stac_ctc_spikes(const int32_t* ids, int64_t batch, int64_t t2, int32_t turn_
  *        [n_head, rows, lk] of work space - with it the heads run on separate CTAs (grid utterances x heads) and a second
  *        kernel adds their probabilities up in head order; without it one CTA per utterance walks the heads (the same
  *        sums, four times fewer CTAs).  STAC_ERR_UNSUPPORTED_SHAPE: group > 16 or lk too long for shared memory
- *        (use stac_attention_f32). */
+ *        (use stac_attention_f32).
+ * stac_attention_step_f32: the self-attention of ONE decoding step over a time-major cache (lq = 1, every row attends
+ *        keys 0 .. lk-1; one warp per (row, head), any lk).  Key / value j of hypothesis row r at
+ *        k|v + src * kv_row_stride + j * kv_time_stride with src = row_map[j * rows + r] (int32 [lk, rows]) or src = r
+ *        when row_map is NULL: a beam search re-orders its hypotheses by permuting the small map (DecoderCache.reorder)
+ *        instead of gathering the cached prefix (reference: permute_mem / the index_select of
+ *        /root/reference/stac-st/modules/mutitask_decoder.py:109-112 on the token memory; the reference has no cache). */
 int stac_embed_scale_pe(const int64_t* tokens, const float* emb, const float* pe, int64_t rows, int64_t seq_len,
                         int64_t d_model, int64_t vocab, float scale, float* out, void* stream);
 int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
@@ -279,6 +285,9 @@ int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float*
                        int64_t mem_rows_div, int causal,
                        const int32_t* kv_len, const int64_t* key_tokens, int64_t pad_idx, float* ctx, int64_t ldctx,
                        float* weights, void* stream);
+int stac_attention_step_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_row_stride,
+                            int64_t kv_time_stride, int64_t rows, int64_t lk, int64_t n_head, const int32_t* row_map,
+                            float* ctx, int64_t ldctx, void* stream);
 int stac_attention_beam_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
                             int64_t kv_row_stride, int64_t rows, int64_t group, int64_t lk, int64_t n_head,
                             const int32_t* kv_len, float* ctx, int64_t ldctx, float* weights, float* head_scratch,

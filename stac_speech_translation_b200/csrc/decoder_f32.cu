@@ -111,79 +111,95 @@ attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __
     for (int j = tid; j < lk; j += kThreads) weights[qrow * lk + j] = wacc[j];
 }
 
-// One decoding step over a short cache (lq = 1, no weights, no token mask, lk <= 256): one WARP per (row, head) - lane =
-// key for the scores (probabilities stay in eight registers per lane), lane = two value columns for P . V, shuffles
-// instead of barriers.  (The CTA-per-row kernel above spends a step's 640 x 4 tiny problems on block reductions and on
-// 16 dependent loads per thread: 37 us per launch at 32 keys.)
+// One decoding step over the cache (lq = 1, no weights, no token mask): one WARP per (row, head) - lane = key for the
+// scores (the probabilities of a 256-key chunk stay in eight registers per lane), lane = two value columns for P . V,
+// shuffles instead of barriers; caches longer than 256 keys go chunk by chunk with a running maximum / sum (one chunk:
+// the plain two-pass softmax).  (The CTA-per-row kernel above spends a step's 640 x 4 tiny problems on block reductions
+// and on 16 dependent loads per thread: 37 us per launch at 32 keys.)
+// row_map (or NULL): int32 [lk][rows]; key / value j of hypothesis row r lives in cache row row_map[j * rows + r] - the
+// lazy form of a beam re-ordering (DecoderCache.reorder permutes this small table instead of moving the cache).
 constexpr int kStepWarps = 8, kStepMaxKeys = 256;
 
 __global__ void __launch_bounds__(kStepWarps * 32)
 attention_step_warp_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
                            const float* __restrict__ v, long long kv_bs, long long kv_rs, int lk, int n_head,
-                           int mem_rows_div, const int* __restrict__ kv_len, float* __restrict__ ctx, long long ldctx,
-                           long long rows) {
+                           int mem_rows_div, const int* __restrict__ kv_len, const int* __restrict__ row_map,
+                           float* __restrict__ ctx, long long ldctx, long long rows) {
   __shared__ __align__(16) float qs[kStepWarps][kHd];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * kStepWarps + warp;
   if (item >= rows * n_head) return;                 // (whole warps leave: no CTA barrier below)
   const long long row = item / n_head;
   const int h = (int)(item % n_head);
-  const long long rb = row / mem_rows_div;
+  const int rb = (int)(row / mem_rows_div);
   int n_keys = lk;
   if (kv_len != nullptr) n_keys = min(max(kv_len[row], 0), lk);
   reinterpret_cast<float2*>(qs[warp])[lane] = *reinterpret_cast<const float2*>(q + row * ldq + h * kHd + 2 * lane);
   __syncwarp();
-  const float* kb = k + rb * kv_bs + h * kHd;
-  const float* vb = v + rb * kv_bs + h * kHd;
-  float p[kStepMaxKeys / 32];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < kStepMaxKeys / 32; ++i) {
-    const int j = 32 * i + lane;
-    float a = -INFINITY;
-    if (j < n_keys) {
-      const float4* kp = reinterpret_cast<const float4*>(kb + (long long)j * kv_rs);
-      a = 0.f;
-#pragma unroll
-      for (int c = 0; c < kHd / 4; ++c) {
-        const float4 kk = __ldg(kp + c);
-        const float4 qq = reinterpret_cast<const float4*>(qs[warp])[c];
-        a = fmaf(qq.x, kk.x, a);
-        a = fmaf(qq.y, kk.y, a);
-        a = fmaf(qq.z, kk.z, a);
-        a = fmaf(qq.w, kk.w, a);
-      }
-    }
-    p[i] = a;
-    mx = fmaxf(mx, a);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < kStepMaxKeys / 32; ++i) {
-    p[i] = p[i] == -INFINITY ? 0.f : expf(p[i] - mx);
-    sum += p[i];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float inv = 1.0f / sum;                      // every key masked: 0 * inf = NaN, as the kernel above
+  const float* kb = k + h * kHd;
+  const float* vb = v + h * kHd + 2 * lane;
+  float m_run = -INFINITY, l_run = 0.f;
   float2 acc = make_float2(0.f, 0.f);
+  for (int base = 0; base < n_keys; base += kStepMaxKeys) {
+    float p[kStepMaxKeys / 32];
+    int src[kStepMaxKeys / 32];                      // cache row of my key in each 32-key group
+    float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < kStepMaxKeys / 32; ++i) {
-    if (32 * i < n_keys) {                           // (warp-uniform)
+    for (int i = 0; i < kStepMaxKeys / 32; ++i) {
+      const int j = base + 32 * i + lane;
+      float a = -INFINITY;
+      src[i] = rb;
+      if (j < n_keys) {
+        if (row_map != nullptr) src[i] = __ldg(row_map + (long long)j * rows + row);
+        const float4* kp = reinterpret_cast<const float4*>(kb + (long long)src[i] * kv_bs + (long long)j * kv_rs);
+        a = 0.f;
+#pragma unroll
+        for (int c = 0; c < kHd / 4; ++c) {
+          const float4 kk = __ldg(kp + c);
+          const float4 qq = reinterpret_cast<const float4*>(qs[warp])[c];
+          a = fmaf(qq.x, kk.x, a);
+          a = fmaf(qq.y, kk.y, a);
+          a = fmaf(qq.z, kk.z, a);
+          a = fmaf(qq.w, kk.w, a);
+        }
+      }
+      p[i] = a;
+      mx = fmaxf(mx, a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float m_new = fmaxf(m_run, mx);
+    const float scale = m_run == -INFINITY ? 0.f : expf(m_run - m_new);      // (first chunk: nothing to rescale)
+    acc.x *= scale;
+    acc.y *= scale;
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kStepMaxKeys / 32; ++i) {
+      p[i] = p[i] == -INFINITY ? 0.f : expf(p[i] - m_new);
+      sum += p[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    l_run = l_run * scale + sum;
+    m_run = m_new;
+#pragma unroll
+    for (int i = 0; i < kStepMaxKeys / 32; ++i) {
+      if (base + 32 * i < n_keys) {                  // (warp-uniform)
 #pragma unroll 16
-      for (int jj = 0; jj < 32; ++jj) {
-        const float pj = __shfl_sync(0xffffffffu, p[i], jj);
-        const int j = 32 * i + jj;
-        if (j < n_keys) {
-          const float2 vv = __ldg(reinterpret_cast<const float2*>(vb + (long long)j * kv_rs) + lane);
-          acc.x = fmaf(pj, vv.x, acc.x);
-          acc.y = fmaf(pj, vv.y, acc.y);
+        for (int jj = 0; jj < 32; ++jj) {
+          const float pj = __shfl_sync(0xffffffffu, p[i], jj);
+          const int rj = __shfl_sync(0xffffffffu, src[i], jj);
+          const int j = base + 32 * i + jj;
+          if (j < n_keys) {
+            const float2 vv = __ldg(reinterpret_cast<const float2*>(vb + (long long)rj * kv_bs + (long long)j * kv_rs));
+            acc.x = fmaf(pj, vv.x, acc.x);
+            acc.y = fmaf(pj, vv.y, acc.y);
+          }
         }
       }
     }
   }
+  const float inv = 1.0f / l_run;                    // every key masked: 0 * inf = NaN, as the kernel above
   *reinterpret_cast<float2*>(ctx + row * ldctx + h * kHd + 2 * lane) = make_float2(acc.x * inv, acc.y * inv);
 }
 
@@ -418,7 +434,7 @@ extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, c
     const int lk_eff = causal ? 1 : (int)lk;
     attention_step_warp_kernel<<<(unsigned)((items + kStepWarps - 1) / kStepWarps), kStepWarps * 32, 0, as_stream(stream)>>>(
         q, (long long)ldq, k, v, (long long)kv_batch_stride, (long long)kv_row_stride, lk_eff, (int)n_head,
-        (int)mem_rows_div, kv_len, ctx, (long long)ldctx, (long long)rows);
+        (int)mem_rows_div, kv_len, nullptr, ctx, (long long)ldctx, (long long)rows);
     STAC_LAUNCH_CHECK();
   }
   const size_t smem = (size_t)(2 * lk + kHd + kThreads + 40) * sizeof(float);
@@ -430,6 +446,23 @@ extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, c
   attention_f32_kernel<<<(unsigned)(rows * lq), kThreads, smem, as_stream(stream)>>>(
       q, (long long)ldq, k, v, (long long)kv_batch_stride, (long long)kv_row_stride, (int)lq, (int)lk, (int)n_head, (int)mem_rows_div, causal, kv_len,
       reinterpret_cast<const long long*>(key_tokens), (long long)pad_idx, ctx, (long long)ldctx, weights);
+  STAC_LAUNCH_CHECK();
+}
+
+extern "C" int stac_attention_step_f32(const float* q, int64_t ldq, const float* k, const float* v,
+                                       int64_t kv_row_stride, int64_t kv_time_stride, int64_t rows, int64_t lk,
+                                       int64_t n_head, const int32_t* row_map, float* ctx, int64_t ldctx, void* stream) {
+  STAC_REQUIRE(q && k && v && ctx && rows > 0 && lk > 0 && n_head > 0);
+  STAC_REQUIRE(ldq >= n_head * kHd && kv_row_stride >= n_head * kHd && kv_time_stride > 0 && ldctx >= n_head * kHd);
+  if (kv_row_stride % 4 != 0 || kv_time_stride % 4 != 0 || ldq % 2 != 0 || ldctx % 2 != 0 ||
+      (reinterpret_cast<uintptr_t>(k) & 15) != 0 || (reinterpret_cast<uintptr_t>(v) & 7) != 0 ||
+      (reinterpret_cast<uintptr_t>(q) & 7) != 0 || (reinterpret_cast<uintptr_t>(ctx) & 7) != 0)
+    return STAC_ERR_UNSUPPORTED_SHAPE;
+  if (rows >= (1ll << 31) || lk >= (1 << 24) || n_head > 65535) return STAC_ERR_UNSUPPORTED_SHAPE;
+  const long long items = (long long)rows * n_head;
+  attention_step_warp_kernel<<<(unsigned)((items + kStepWarps - 1) / kStepWarps), kStepWarps * 32, 0, as_stream(stream)>>>(
+      q, (long long)ldq, k, v, (long long)kv_row_stride, (long long)kv_time_stride, (int)lk, (int)n_head, 1, nullptr,
+      row_map, ctx, (long long)ldctx, (long long)rows);
   STAC_LAUNCH_CHECK();
 }
 

@@ -282,6 +282,11 @@ class DecoderCache:
         self.h = torch.empty(rows, d, **f32)
         self.q = torch.empty(rows, d, **f32)
         self.ctx = torch.empty(rows, d, **f32)
+        # lazy beam re-ordering: key / value j of hypothesis row r lives in cache row row_map[j, r]; reorder() permutes
+        # this table (max_len x rows int32) instead of gathering the cached prefix of every layer
+        self._iota = torch.arange(rows, device=dev, dtype=torch.int32)
+        self.row_map = self._iota.repeat(max_len, 1).contiguous()
+        self._permuted = False
         # per-head probabilities of the last layer's cross-attention (its head average is what step() returns)
         self.head_scratch = torch.empty(w.nhead, rows, t2, **f32)
         self.ff = torch.empty(rows, w.layers[0].w_1.shape[0], **f32)
@@ -290,6 +295,12 @@ class DecoderCache:
             self.h16 = torch.empty(rows, d, **b16)
             self.ctx16 = torch.empty(rows, d, **b16)
             self.ff16 = torch.empty(rows, w.layers[0].w_1.shape[0], **b16)
+
+    def _self_attention(self, cache, t):
+        """Self-attention of position t over the cached prefix; hypothesis rows are found through ``self.row_map``."""
+        d, r = self.d, self.rows
+        ops._call("stac_attention_step_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, t + 1,
+                  self.w.nhead, ptr(self.row_map, torch.int32) if self._permuted else ptr(None), ptr(self.ctx), d, stream())
 
     def _step_bf16(self, tok, weights):
         """One position on the tensor-core GEMMs (same sequence as the fp32 step)."""
@@ -303,8 +314,7 @@ class DecoderCache:
             slab = self.self_kv[n, t]                              # [rows, 2 d]: keys | values of position t
             ops._gemm(self.h16, wb["w_qkv"][d:], lw.b_qkv[d:], slab, "bf16", tag="dec_kv_self")
             cache = self.self_kv[n]
-            ops._call("stac_attention_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, 1, t + 1, h,
-                      1, 0, ptr(None), ptr(None), 0, ptr(self.ctx), d, ptr(None), stream())
+            self._self_attention(cache, t)
             ops._call("stac_cast_bf16", ptr(self.ctx), self.ctx.numel(), ptr(self.ctx16), stream())
             ops._gemm(self.ctx16, wb["w_o"], lw.b_o, x, "bf16", resid=x, tag="dec_out_proj")
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_bf16=self.h16)
@@ -341,8 +351,7 @@ class DecoderCache:
             slab = self.self_kv[n, t]                              # [rows, 2 d]: keys | values of position t
             ops._gemm(self.h, lw.w_qkv[d:], lw.b_qkv[d:], slab, "fp32", tag="dec_kv_self")
             cache = self.self_kv[n]
-            ops._call("stac_attention_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, 1, t + 1, h,
-                      1, 0, ptr(None), ptr(None), 0, ptr(self.ctx), d, ptr(None), stream())
+            self._self_attention(cache, t)
             ops._gemm(self.ctx, lw.w_o, lw.b_o, x, "fp32", resid=x, tag="dec_out_proj")
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_q2, lw.b_q2, self.q, "fp32", tag="dec_q")
@@ -359,11 +368,16 @@ class DecoderCache:
 
     def reorder(self, index: torch.Tensor):
         """Beam re-ordering (``permute_mem``, mutitask_decoder.py:109-112): hypothesis row i continues row index[i].
-        Data movement only (a row gather of the cached prefix)."""
+        No cache data moves: only the row map is permuted (the first version gathered the cached prefix of every layer,
+        four passes over 2 x layers x t x rows x d_model floats per step - more than the step itself once the prefix
+        passes ~150 tokens)."""
         idx = index.to(device=self.self_kv.device, dtype=torch.int64)
         if idx.shape != (self.rows,):
             raise StacB200Error("one source row per hypothesis row is required")
-        self.self_kv[:, :self.t] = self.self_kv[:, :self.t].index_select(2, idx)
+        # (the caches stay where they are: position j of row i is now read from cache row row_map[j, index[i]]; the
+        # slab of a new position is always written at the hypothesis's own row, row_map[t] = 0 .. rows-1)
+        self.row_map[:self.t] = self.row_map[:self.t].index_select(1, idx)
+        self._permuted = True
 
 
 def decoder_params_version(decoder: nn.Module, tgt_module: nn.Module):

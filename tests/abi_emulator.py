@@ -96,6 +96,26 @@ class Emulator:
                 p = np.exp(s - s.max(1, keepdims=True))
                 out[b, :, h] = (p / p.sum(1, keepdims=True)) @ x[b, :nk, 2, h]
 
+    def stac_attention_step_f32(self, q, ldq, k, v, kv_rs, kv_ts, rows, lk, n_head, row_map, ctx, ldctx, stream):
+        """Self-attention of one decoding step over a time-major cache, key j of row r in cache row row_map[j, r]."""
+        d = n_head * 64
+        qq = _arr(q, (rows - 1) * ldq + d)
+        rm = _arr(row_map, lk * rows, np.int32)
+        span = (rows - 1) * kv_rs + (lk - 1) * kv_ts + d
+        kk, vv = _arr(k, span), _arr(v, span)
+        cc = _arr(ctx, (rows - 1) * ldctx + d)
+        for r in range(rows):
+            for h in range(n_head):
+                qv = qq[r * ldq + h * 64: r * ldq + h * 64 + 64].astype(np.float64)
+                offs = [(int(rm[j * rows + r]) if rm is not None else r) * kv_rs + j * kv_ts + h * 64 for j in range(lk)]
+                s = np.array([qv @ kk[o:o + 64] for o in offs])
+                pr = np.exp(s - s.max())
+                pr /= pr.sum()
+                acc = np.zeros(64)
+                for j, o in enumerate(offs):
+                    acc += pr[j] * vv[o:o + 64]
+                cc[r * ldctx + h * 64: r * ldctx + h * 64 + 64] = acc.astype(np.float32)
+
     def stac_attention_beam_f32(self, q, ldq, k, v, kv_bs, kv_rs, rows, group, lk, n_head, kv_len, ctx, ldctx, weights,
                                 head_scratch, stream):
         """One query per row, `group` rows per memory block: by its documentation the general attention with lq = 1."""

@@ -114,6 +114,7 @@ inline float __shfl_xor_sync(unsigned, float v, int o) {
   return __uint_as_float(simt_exchange(__float_as_uint(v), (simt::linear_tid & 31) ^ o));
 }
 inline float __shfl_sync(unsigned, float v, int src) { return __uint_as_float(simt_exchange(__float_as_uint(v), src & 31)); }
+inline int __shfl_sync(unsigned, int v, int src) { return (int)simt_exchange((uint32_t)v, src & 31); }
 inline int __shfl_xor_sync(unsigned, int v, int o) { return (int)simt_exchange((uint32_t)v, (simt::linear_tid & 31) ^ o); }
 inline unsigned __ballot_sync(unsigned, bool pred) {
   simt::Block* b = simt::cur;

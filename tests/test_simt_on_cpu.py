@@ -27,7 +27,7 @@ def simt():
     for name in ("stac_argmax_rows", "stac_ctc_spikes", "stac_embed_scale_pe", "stac_attention_f32",
                  "stac_pcm_i16_to_f32", "stac_utt_mean_std", "stac_layernorm", "stac_mha_f32", "stac_log_softmax",
                  "stac_kv_lengths", "stac_cast_bf16", "stac_gemm_f32", "stac_spec_augment", "stac_ctc_loss",
-                 "stac_attention_beam_f32"):
+                 "stac_attention_beam_f32", "stac_attention_step_f32"):
         res, args = _lib._SIGNATURES[name]
         getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
     return lib
@@ -130,6 +130,28 @@ def test_attention_step_warp_kernel(simt, rows, lk, h, div, with_len):
     if with_len:
         sc = sc.masked_fill((torch.arange(lk)[None, :] >= kv_len[:, None])[:, None, None, :], float("-inf"))
     want = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(rows, d)
+    assert (ctx.double() - want).norm() / want.norm() < 1e-5
+
+
+@pytest.mark.parametrize("rows,lk,h,with_map", [(3, 5, 2, False), (5, 40, 2, True), (2, 300, 1, True), (3, 530, 2, False)])
+def test_attention_step_kernel_with_row_map(simt, rows, lk, h, with_map):
+    """stac_attention_step_f32: time-major cache [max_len][rows][2 d], hypothesis rows found through the row map (lazy
+    beam re-ordering); caches longer than 256 keys run chunk by chunk with a running maximum / sum."""
+    g = torch.Generator().manual_seed(rows * 1000 + lk)
+    d = 64 * h
+    q = torch.randn(rows, d, generator=g)
+    cache = torch.randn(lk + 2, rows, 2 * d, generator=g)                   # (two unused positions behind the prefix)
+    rmap = torch.randint(0, rows, (lk, rows), generator=g, dtype=torch.int32) if with_map else None
+    ctx = torch.full((rows, d), float("nan"))
+    rc = simt.stac_attention_step_f32(P(q), d, P(cache), c_void_p(cache.data_ptr() + 4 * d), 2 * d, rows * 2 * d, rows, lk,
+                                      h, P(rmap), P(ctx), d, None)
+    assert rc == 0
+    src = rmap.long() if with_map else torch.arange(rows).repeat(lk, 1)
+    kv = cache[:lk].gather(1, src[:, :, None].expand(lk, rows, 2 * d))          # [lk, rows, 2d] as each row sees it
+    kk = kv[:, :, :d].permute(1, 0, 2).reshape(rows, lk, h, 64).permute(0, 2, 1, 3).double()
+    vv = kv[:, :, d:].permute(1, 0, 2).reshape(rows, lk, h, 64).permute(0, 2, 1, 3).double()
+    p = torch.softmax(q.view(rows, 1, h, 64).permute(0, 2, 1, 3).double() @ kk.transpose(-1, -2), -1)
+    want = (p @ vv).permute(0, 2, 1, 3).reshape(rows, d)
     assert (ctx.double() - want).norm() / want.norm() < 1e-5
 
 

@@ -76,6 +76,13 @@ torch.cuda.current_stream().wait_stream(s)
 ms_graph16 = timed(g.replay)
 print(f"rows {rows}  prefix {a.prefix}  frames {a.frames}:  full-prefix decode {ms_full:.3f} ms   cached step {ms_step:.3f} ms"
       f"   cached step, bf16 GEMMs {ms_step16:.3f} ms   the same as a CUDA graph {ms_graph16:.3f} ms")
+# beam re-ordering: the row map (what reorder() does) against gathering the cached prefix (what it did at first)
+idx = torch.randint(0, rows, (rows,), device="cuda")
+ms_reorder = timed(lambda: cache16.reorder(idx))
+ms_step_mapped = timed(one_step16)
+ms_gather = timed(lambda: cache16.self_kv[:, :t0].copy_(cache16.self_kv[:, :t0].index_select(2, idx)))
+print(f"beam re-ordering at prefix {t0}: row map {ms_reorder:.3f} ms (then a step through the map {ms_step_mapped:.3f} ms)"
+      f"   gather of the cached prefix {ms_gather:.3f} ms")
 if os.environ.get("STAC_DECODER_PROFILE", "1") != "0":
     # warm per-kernel device times of the graph-less bf16 step (CUPTI through torch.profiler; a breakdown, not a bench value)
     try:
