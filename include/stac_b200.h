@@ -277,7 +277,14 @@ int stac_ctc_spikes(const int32_t* ids, int64_t batch, int64_t t2, int32_t turn_
  *        k|v + src * kv_row_stride + j * kv_time_stride with src = row_map[j * rows + r] (int32 [lk, rows]) or src = r
  *        when row_map is NULL: a beam search re-orders its hypotheses by permuting the small map (DecoderCache.reorder)
  *        instead of gathering the cached prefix (reference: permute_mem / the index_select of
- *        /root/reference/stac-st/modules/mutitask_decoder.py:109-112 on the token memory; the reference has no cache). */
+ *        /root/reference/stac-st/modules/mutitask_decoder.py:109-112 on the token memory; the reference has no cache).
+ *        Append mode (t_dev, k_new, v_new given; else all NULL / 0): the position counter t lives on the device
+ *        (int32 [1]), lk is the capacity of the cache, the step attends keys 0 .. t where key t is row r of
+ *        k_new / v_new (row stride ld_new: the output of the step's K|V projection) and is stored into slab t of the
+ *        cache by this kernel - no argument of the launch depends on the step, so one captured launch sequence serves a
+ *        whole search.
+ * stac_embed_step: stac_embed_scale_pe for one position per row with the position read from the device
+ *        (out[row] = emb[tokens[row]] * scale + pe[*pos_dev]). */
 int stac_embed_scale_pe(const int64_t* tokens, const float* emb, const float* pe, int64_t rows, int64_t seq_len,
                         int64_t d_model, int64_t vocab, float scale, float* out, void* stream);
 int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
@@ -285,9 +292,12 @@ int stac_attention_f32(const float* q, int64_t ldq, const float* k, const float*
                        int64_t mem_rows_div, int causal,
                        const int32_t* kv_len, const int64_t* key_tokens, int64_t pad_idx, float* ctx, int64_t ldctx,
                        float* weights, void* stream);
-int stac_attention_step_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_row_stride,
+int stac_embed_step(const int64_t* tokens, const float* emb, const float* pe, int64_t rows, int64_t d_model,
+                    int64_t vocab, float scale, const int32_t* pos_dev, float* out, void* stream);
+int stac_attention_step_f32(const float* q, int64_t ldq, float* k, float* v, int64_t kv_row_stride,
                             int64_t kv_time_stride, int64_t rows, int64_t lk, int64_t n_head, const int32_t* row_map,
-                            float* ctx, int64_t ldctx, void* stream);
+                            const float* k_new, const float* v_new, int64_t ld_new, const int32_t* t_dev, float* ctx,
+                            int64_t ldctx, void* stream);
 int stac_attention_beam_f32(const float* q, int64_t ldq, const float* k, const float* v, int64_t kv_batch_stride,
                             int64_t kv_row_stride, int64_t rows, int64_t group, int64_t lk, int64_t n_head,
                             const int32_t* kv_len, float* ctx, int64_t ldctx, float* weights, float* head_scratch,

@@ -62,7 +62,9 @@ _SIGNATURES = {
     "stac_embed_scale_pe": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_int64, c_float, _P, _P]),
     "stac_attention_f32": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
                                    _P, _P, c_int64, _P, c_int64, _P, _P]),
-    "stac_attention_step_f32": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
+    "stac_embed_step": (c_int, [_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
+    "stac_attention_step_f32": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P,
+                                        c_int64, _P, _P, c_int64, _P]),
     "stac_attention_beam_f32": (c_int, [_P, c_int64, _P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P,
                                         c_int64, _P, _P, _P]),
     "stac_pcm_i16_to_f32": (c_int, [_P, c_int64, _P, _P]),

@@ -25,8 +25,9 @@ constexpr int kThreads = 128;
 __global__ void __launch_bounds__(256)
 embed_scale_pe_kernel(const long long* __restrict__ tokens, const float* __restrict__ emb,
                       const float* __restrict__ pe, long long rows, int seq_len, int d_model, int vocab, float scale,
-                      float* __restrict__ out) {
+                      const int* __restrict__ pos_dev, float* __restrict__ out) {
   const int d4 = d_model >> 2;
+  if (pos_dev != nullptr) pe += (long long)(*pos_dev) * d_model;      // position counter kept on the device (graph replay)
   const long long n = rows * d4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / d4;
@@ -121,9 +122,10 @@ attention_f32_kernel(const float* __restrict__ q, long long ldq, const float* __
 constexpr int kStepWarps = 8, kStepMaxKeys = 256;
 
 __global__ void __launch_bounds__(kStepWarps * 32)
-attention_step_warp_kernel(const float* __restrict__ q, long long ldq, const float* __restrict__ k,
-                           const float* __restrict__ v, long long kv_bs, long long kv_rs, int lk, int n_head,
-                           int mem_rows_div, const int* __restrict__ kv_len, const int* __restrict__ row_map,
+attention_step_warp_kernel(const float* __restrict__ q, long long ldq, const float* k, const float* v, long long kv_bs,
+                           long long kv_rs, int lk, int n_head, int mem_rows_div, const int* __restrict__ kv_len,
+                           const int* __restrict__ row_map, const float* __restrict__ k_new,
+                           const float* __restrict__ v_new, long long ld_new, const int* __restrict__ t_dev,
                            float* __restrict__ ctx, long long ldctx, long long rows) {
   __shared__ __align__(16) float qs[kStepWarps][kHd];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,14 +134,34 @@ attention_step_warp_kernel(const float* __restrict__ q, long long ldq, const flo
   const long long row = item / n_head;
   const int h = (int)(item % n_head);
   const int rb = (int)(row / mem_rows_div);
-  int n_keys = lk;
-  if (kv_len != nullptr) n_keys = min(max(kv_len[row], 0), lk);
   reinterpret_cast<float2*>(qs[warp])[lane] = *reinterpret_cast<const float2*>(q + row * ldq + h * kHd + 2 * lane);
   __syncwarp();
-  const float* kb = k + h * kHd;
-  const float* vb = v + h * kHd + 2 * lane;
   float m_run = -INFINITY, l_run = 0.f;
   float2 acc = make_float2(0.f, 0.f);
+  // append mode (t_dev given): the position counter lives on the device, the keys / values of position t = *t_dev come
+  // from the projection's output rows (k_new / v_new) and are stored into slab t of the cache here; the step attends
+  // the cached keys 0 .. t-1 and the new one.  One launch sequence then serves every step of a search (DecoderCache
+  // replays it as a CUDA graph).  The new key opens the running softmax: score by the whole warp, weight 1.
+  if (t_dev != nullptr) {
+    const int t_new = min(*t_dev, lk - 1);           // (lk = capacity of the cache in this mode)
+    lk = t_new;                                      // cached keys to attend
+    const long long o_new = row * ld_new + h * kHd + 2 * lane;
+    const long long o_cache = row * kv_bs + (long long)t_new * kv_rs + h * kHd + 2 * lane;
+    const float2 kn = *reinterpret_cast<const float2*>(k_new + o_new);
+    const float2 vn = *reinterpret_cast<const float2*>(v_new + o_new);
+    *reinterpret_cast<float2*>(const_cast<float*>(k) + o_cache) = kn;
+    *reinterpret_cast<float2*>(const_cast<float*>(v) + o_cache) = vn;
+    float s_new = fmaf(qs[warp][2 * lane], kn.x, qs[warp][2 * lane + 1] * kn.y);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s_new += __shfl_xor_sync(0xffffffffu, s_new, o);
+    m_run = s_new;
+    l_run = 1.f;
+    acc = vn;
+  }
+  int n_keys = lk;
+  if (kv_len != nullptr) n_keys = min(max(kv_len[row], 0), lk);
+  const float* kb = k + h * kHd;
+  const float* vb = v + h * kHd + 2 * lane;
   for (int base = 0; base < n_keys; base += kStepMaxKeys) {
     float p[kStepMaxKeys / 32];
     int src[kStepMaxKeys / 32];                      // cache row of my key in each 32-key group
@@ -182,19 +204,19 @@ attention_step_warp_kernel(const float* __restrict__ q, long long ldq, const flo
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     l_run = l_run * scale + sum;
     m_run = m_new;
+    // P . V without a branch per key: keys past the end carry p = 0 and read the last valid row (finite values), so
+    // the sixteen loads of an unrolled group are issued back to back
 #pragma unroll
     for (int i = 0; i < kStepMaxKeys / 32; ++i) {
       if (base + 32 * i < n_keys) {                  // (warp-uniform)
 #pragma unroll 16
         for (int jj = 0; jj < 32; ++jj) {
           const float pj = __shfl_sync(0xffffffffu, p[i], jj);
-          const int rj = __shfl_sync(0xffffffffu, src[i], jj);
-          const int j = base + 32 * i + jj;
-          if (j < n_keys) {
-            const float2 vv = __ldg(reinterpret_cast<const float2*>(vb + (long long)rj * kv_bs + (long long)j * kv_rs));
-            acc.x = fmaf(pj, vv.x, acc.x);
-            acc.y = fmaf(pj, vv.y, acc.y);
-          }
+          const int jl = min(base + 32 * i + jj, n_keys - 1);
+          const int rj = __shfl_sync(0xffffffffu, src[i], jl & 31);
+          const float2 vv = __ldg(reinterpret_cast<const float2*>(vb + (long long)rj * kv_bs + (long long)jl * kv_rs));
+          acc.x = fmaf(pj, vv.x, acc.x);
+          acc.y = fmaf(pj, vv.y, acc.y);
         }
       }
     }
@@ -411,7 +433,18 @@ extern "C" int stac_embed_scale_pe(const int64_t* tokens, const float* emb, cons
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(rows * (d_model / 4), 256), 148 * 16);
   embed_scale_pe_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(tokens), emb, pe,
                                                             (long long)rows, (int)seq_len, (int)d_model, (int)vocab,
-                                                            scale, out);
+                                                            scale, nullptr, out);
+  STAC_LAUNCH_CHECK();
+}
+
+extern "C" int stac_embed_step(const int64_t* tokens, const float* emb, const float* pe, int64_t rows, int64_t d_model,
+                               int64_t vocab, float scale, const int32_t* pos_dev, float* out, void* stream) {
+  STAC_REQUIRE(tokens && emb && pe && out && pos_dev && rows > 0 && vocab > 0 && d_model > 0);
+  if (d_model % 4 != 0 || vocab >= (1ll << 31)) return STAC_ERR_UNSUPPORTED_SHAPE;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(rows * (d_model / 4), 256), 148 * 16);
+  embed_scale_pe_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(tokens), emb, pe,
+                                                            (long long)rows, 1, (int)d_model, (int)vocab, scale,
+                                                            pos_dev, out);
   STAC_LAUNCH_CHECK();
 }
 
@@ -434,7 +467,7 @@ extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, c
     const int lk_eff = causal ? 1 : (int)lk;
     attention_step_warp_kernel<<<(unsigned)((items + kStepWarps - 1) / kStepWarps), kStepWarps * 32, 0, as_stream(stream)>>>(
         q, (long long)ldq, k, v, (long long)kv_batch_stride, (long long)kv_row_stride, lk_eff, (int)n_head,
-        (int)mem_rows_div, kv_len, nullptr, ctx, (long long)ldctx, (long long)rows);
+        (int)mem_rows_div, kv_len, nullptr, nullptr, nullptr, 0, nullptr, ctx, (long long)ldctx, (long long)rows);
     STAC_LAUNCH_CHECK();
   }
   const size_t smem = (size_t)(2 * lk + kHd + kThreads + 40) * sizeof(float);
@@ -449,20 +482,25 @@ extern "C" int stac_attention_f32(const float* q, int64_t ldq, const float* k, c
   STAC_LAUNCH_CHECK();
 }
 
-extern "C" int stac_attention_step_f32(const float* q, int64_t ldq, const float* k, const float* v,
-                                       int64_t kv_row_stride, int64_t kv_time_stride, int64_t rows, int64_t lk,
-                                       int64_t n_head, const int32_t* row_map, float* ctx, int64_t ldctx, void* stream) {
+extern "C" int stac_attention_step_f32(const float* q, int64_t ldq, float* k, float* v, int64_t kv_row_stride,
+                                       int64_t kv_time_stride, int64_t rows, int64_t lk, int64_t n_head,
+                                       const int32_t* row_map, const float* k_new, const float* v_new, int64_t ld_new,
+                                       const int32_t* t_dev, float* ctx, int64_t ldctx, void* stream) {
   STAC_REQUIRE(q && k && v && ctx && rows > 0 && lk > 0 && n_head > 0);
   STAC_REQUIRE(ldq >= n_head * kHd && kv_row_stride >= n_head * kHd && kv_time_stride > 0 && ldctx >= n_head * kHd);
+  STAC_REQUIRE(t_dev == nullptr || (k_new && v_new && ld_new >= n_head * kHd));
   if (kv_row_stride % 4 != 0 || kv_time_stride % 4 != 0 || ldq % 2 != 0 || ldctx % 2 != 0 ||
       (reinterpret_cast<uintptr_t>(k) & 15) != 0 || (reinterpret_cast<uintptr_t>(v) & 7) != 0 ||
       (reinterpret_cast<uintptr_t>(q) & 7) != 0 || (reinterpret_cast<uintptr_t>(ctx) & 7) != 0)
+    return STAC_ERR_UNSUPPORTED_SHAPE;
+  if (t_dev != nullptr && (ld_new % 4 != 0 || (reinterpret_cast<uintptr_t>(k_new) & 15) != 0 ||
+                           (reinterpret_cast<uintptr_t>(v_new) & 7) != 0))
     return STAC_ERR_UNSUPPORTED_SHAPE;
   if (rows >= (1ll << 31) || lk >= (1 << 24) || n_head > 65535) return STAC_ERR_UNSUPPORTED_SHAPE;
   const long long items = (long long)rows * n_head;
   attention_step_warp_kernel<<<(unsigned)((items + kStepWarps - 1) / kStepWarps), kStepWarps * 32, 0, as_stream(stream)>>>(
       q, (long long)ldq, k, v, (long long)kv_row_stride, (long long)kv_time_stride, (int)lk, (int)n_head, 1, nullptr,
-      row_map, ctx, (long long)ldctx, (long long)rows);
+      row_map, k_new, v_new, (long long)ld_new, t_dev, ctx, (long long)ldctx, (long long)rows);
   STAC_LAUNCH_CHECK();
 }
 

@@ -246,8 +246,11 @@ class DecoderCache:
 
     * the cross-attention keys / values of every layer are projected ONCE from the encoder output, per utterance (not
       per hypothesis row: row r reads memory[r // beam]);
-    * the self-attention keys / values of the prefix live in a time-major cache [layer][max_len][rows][2 d], so the
-      projection of step t is written by the GEMM straight into slab t and a beam re-ordering is a row gather;
+    * the self-attention keys / values of the prefix live in a time-major cache [layer][max_len][rows][2 d]; the
+      self-attention kernel of a step stores the new position's keys / values into slab t itself and finds the rows of
+      a re-ordered beam through a [max_len, rows] row map, so a beam re-ordering moves no cache data;
+    * the position counter lives on the device: no kernel argument of a step depends on t, and with ``graph=True`` a
+      step is ONE CUDA-graph replay (captured at the second step) instead of ~90 launches issued from Python;
     * ``step(tokens)`` returns what ``decode(prefix)[0][:, -1]`` and ``decode(prefix)[1][:, -1]`` return.
     precision "fp32": the entry points of ``decoder_stack`` (CUDA cores).  precision "bf16": every projection and the
     feed-forward block run on the tensor cores (``stac_gemm_bf16``: bf16 operands, fp32 accumulation; the residual
@@ -255,7 +258,7 @@ class DecoderCache:
     sizes: 640 rows x seven small GEMMs per layer.  No CPU fallback."""
 
     def __init__(self, w: DecoderWeights, memory: torch.Tensor, rows: int, max_len: int,
-                 mem_len: Optional[torch.Tensor] = None, precision: str = "fp32"):
+                 mem_len: Optional[torch.Tensor] = None, precision: str = "fp32", graph: bool = False):
         bm, t2, d = memory.shape
         if d != w.d_model or rows % bm != 0:
             raise StacB200Error("encoder_out does not match the decoder (d_model / rows not a multiple of its batch)")
@@ -282,11 +285,16 @@ class DecoderCache:
         self.h = torch.empty(rows, d, **f32)
         self.q = torch.empty(rows, d, **f32)
         self.ctx = torch.empty(rows, d, **f32)
+        self.kv_new = torch.empty(rows, 2 * d, **f32)             # keys | values of the position being decoded
+        self.t_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # the position counter the kernels read
+        self.use_graph, self._graph = bool(graph), None
+        self.tok_buf = torch.zeros(rows, device=dev, dtype=torch.int64)
+        self.out = torch.empty(rows, d, **f32)
+        self.weights = torch.empty(rows, t2, **f32)
         # lazy beam re-ordering: key / value j of hypothesis row r lives in cache row row_map[j, r]; reorder() permutes
         # this table (max_len x rows int32) instead of gathering the cached prefix of every layer
         self._iota = torch.arange(rows, device=dev, dtype=torch.int32)
         self.row_map = self._iota.repeat(max_len, 1).contiguous()
-        self._permuted = False
         # per-head probabilities of the last layer's cross-attention (its head average is what step() returns)
         self.head_scratch = torch.empty(w.nhead, rows, t2, **f32)
         self.ff = torch.empty(rows, w.layers[0].w_1.shape[0], **f32)
@@ -296,25 +304,25 @@ class DecoderCache:
             self.ctx16 = torch.empty(rows, d, **b16)
             self.ff16 = torch.empty(rows, w.layers[0].w_1.shape[0], **b16)
 
-    def _self_attention(self, cache, t):
-        """Self-attention of position t over the cached prefix; hypothesis rows are found through ``self.row_map``."""
+    def _self_attention(self, cache):
+        """Self-attention of the position ``t_dev`` counts: the kernel stores ``kv_new`` into slab t of the cache and
+        attends keys 0 .. t; hypothesis rows are found through ``self.row_map``."""
         d, r = self.d, self.rows
-        ops._call("stac_attention_step_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, t + 1,
-                  self.w.nhead, ptr(self.row_map, torch.int32) if self._permuted else ptr(None), ptr(self.ctx), d, stream())
+        ops._call("stac_attention_step_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, self.max_len,
+                  self.w.nhead, ptr(self.row_map, torch.int32), ptr(self.kv_new), _off(self.kv_new, d), 2 * d,
+                  ptr(self.t_dev, torch.int32), ptr(self.ctx), d, stream())
 
-    def _step_bf16(self, tok, weights):
+    def _step_bf16(self, weights):
         """One position on the tensor-core GEMMs (same sequence as the fp32 step)."""
-        w, r, d, t, t2 = self.w, self.rows, self.d, self.t, self.t2
+        w, r, d, t2 = self.w, self.rows, self.d, self.t2
         h, x = w.nhead, self.x
         for n, lw in enumerate(w.layers):
             wb = self.wb[n]
             last = n == len(w.layers) - 1
             ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_bf16=self.h16)
             ops._gemm(self.h16, wb["w_qkv"][:d], lw.b_qkv[:d], self.q, "bf16", tag="dec_q_self")
-            slab = self.self_kv[n, t]                              # [rows, 2 d]: keys | values of position t
-            ops._gemm(self.h16, wb["w_qkv"][d:], lw.b_qkv[d:], slab, "bf16", tag="dec_kv_self")
-            cache = self.self_kv[n]
-            self._self_attention(cache, t)
+            ops._gemm(self.h16, wb["w_qkv"][d:], lw.b_qkv[d:], self.kv_new, "bf16", tag="dec_kv_self")
+            self._self_attention(self.self_kv[n])
             ops._call("stac_cast_bf16", ptr(self.ctx), self.ctx.numel(), ptr(self.ctx16), stream())
             ops._gemm(self.ctx16, wb["w_o"], lw.b_o, x, "bf16", resid=x, tag="dec_out_proj")
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_bf16=self.h16)
@@ -327,31 +335,20 @@ class DecoderCache:
             ops._gemm(self.h16, wb["w_1"], lw.b_1, self.ff16, "bf16", act=ACT_GELU_ERF, tag="dec_ffn1")
             ops._gemm(self.ff16, wb["w_2"], lw.b_2, x, "bf16", resid=x, tag="dec_ffn2")
 
-    def step(self, tokens: torch.Tensor):
-        """tokens int64 [rows]: the token at position t of every hypothesis.  Returns (prediction [rows, d],
-        head-averaged cross-attention weights of the last layer [rows, T2]) for that position."""
-        w, r, d, t, t2 = self.w, self.rows, self.d, self.t, self.t2
-        if t >= self.max_len:
-            raise StacB200Error("decoder cache is full")
-        if tokens.shape != (r,):
-            raise StacB200Error("one token per hypothesis row is required")
-        h = w.nhead
-        x = self.x
-        tok = tokens.to(device=x.device, dtype=torch.int64).contiguous()
-        # position t of the table: pe + t * d with a period of one row
-        ops._call("stac_embed_scale_pe", ptr(tok, torch.int64), ptr(w.emb), _off(w.pe, t * d), r, 1, d, w.vocab,
-                  math.sqrt(d), ptr(x), stream())
-        weights = torch.empty(r, t2, device=x.device, dtype=torch.float32)
+    def _step_body(self):
+        """Every launch of one step; reads ``tok_buf`` and ``t_dev``, writes ``out`` / ``weights``, advances ``t_dev``."""
+        w, r, d, t2 = self.w, self.rows, self.d, self.t2
+        h, x, weights = w.nhead, self.x, self.weights
+        ops._call("stac_embed_step", ptr(self.tok_buf, torch.int64), ptr(w.emb), ptr(w.pe), r, d, w.vocab, math.sqrt(d),
+                  ptr(self.t_dev, torch.int32), ptr(x), stream())
         if self.precision == "bf16":
-            self._step_bf16(tok, weights)
+            self._step_bf16(weights)
         for n, lw in enumerate(w.layers if self.precision == "fp32" else []):
             last = n == len(w.layers) - 1
             ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_qkv[:d], lw.b_qkv[:d], self.q, "fp32", tag="dec_q_self")
-            slab = self.self_kv[n, t]                              # [rows, 2 d]: keys | values of position t
-            ops._gemm(self.h, lw.w_qkv[d:], lw.b_qkv[d:], slab, "fp32", tag="dec_kv_self")
-            cache = self.self_kv[n]
-            self._self_attention(cache, t)
+            ops._gemm(self.h, lw.w_qkv[d:], lw.b_qkv[d:], self.kv_new, "fp32", tag="dec_kv_self")
+            self._self_attention(self.self_kv[n])
             ops._gemm(self.ctx, lw.w_o, lw.b_o, x, "fp32", resid=x, tag="dec_out_proj")
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_q2, lw.b_q2, self.q, "fp32", tag="dec_q")
@@ -361,10 +358,33 @@ class DecoderCache:
             ops._layernorm(x, lw.ln3_g, lw.ln3_b, 1e-6, out_f32=self.h)
             ops._gemm(self.h, lw.w_1, lw.b_1, self.ff, "fp32", act=ACT_GELU_ERF, tag="dec_ffn1")
             ops._gemm(self.ff, lw.w_2, lw.b_2, x, "fp32", resid=x, tag="dec_ffn2")
-        out = torch.empty(r, d, device=x.device, dtype=torch.float32)
-        ops._layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=out)
-        self.t = t + 1
-        return out, weights
+        ops._layernorm(x, w.lnf_g, w.lnf_b, 1e-6, out_f32=self.out)
+        self.t_dev.add_(1)
+
+    def step(self, tokens: torch.Tensor):
+        """tokens int64 [rows]: the token at position t of every hypothesis.  Returns (prediction [rows, d],
+        head-averaged cross-attention weights of the last layer [rows, T2]) for that position."""
+        if self.t >= self.max_len:
+            raise StacB200Error("decoder cache is full")
+        if tokens.shape != (self.rows,):
+            raise StacB200Error("one token per hypothesis row is required")
+        self.tok_buf.copy_(tokens, non_blocking=True)
+        if not self.use_graph or self.t == 0:
+            self._step_body()                      # (the first step also sets kernel attributes: not capturable)
+        else:
+            if self._graph is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):              # (capture records the launches; the replay below runs them)
+                    self._step_body()
+                self._graph = g
+            self._graph.replay()
+        self.t += 1
+        return self.out.clone(), self.weights.clone()      # (the buffers are rewritten by the next step)
+
+    def rewind(self, t: int):
+        """Set the position counter (host and device) back to ``t``: the next step recomputes position t."""
+        self.t = int(t)
+        self.t_dev.fill_(int(t))
 
     def reorder(self, index: torch.Tensor):
         """Beam re-ordering (``permute_mem``, mutitask_decoder.py:109-112): hypothesis row i continues row index[i].
@@ -377,7 +397,6 @@ class DecoderCache:
         # (the caches stay where they are: position j of row i is now read from cache row row_map[j, index[i]]; the
         # slab of a new position is always written at the hypothesis's own row, row_map[t] = 0 .. rows-1)
         self.row_map[:self.t] = self.row_map[:self.t].index_select(1, idx)
-        self._permuted = True
 
 
 def decoder_params_version(decoder: nn.Module, tgt_module: nn.Module):

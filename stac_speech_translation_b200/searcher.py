@@ -65,10 +65,12 @@ class CachedStepMixin:
             if rows % beam != 0 or enc_states.shape[0] != rows:
                 raise StacB200Error("forward_step expects encoder states inflated to one row per hypothesis")
             # the searcher inflated the encoder states x beam (repeat_interleave): keep one copy per utterance
-            # (decoder_precision = "bf16" on the searcher: the step's GEMMs on the tensor cores)
+            # (decoder_precision = "bf16" on the searcher: the step's GEMMs on the tensor cores; decoder_graph = True: a
+            # step is one CUDA-graph replay)
             cache = self.model.decoder_cache(enc_states[::beam].contiguous(), rows=rows,
                                              max_len=self._cache_len(memory.shape[1], enc_states.shape[1]),
-                                             precision=getattr(self, "decoder_precision", "fp32"))
+                                             precision=getattr(self, "decoder_precision", "fp32"),
+                                             graph=bool(getattr(self, "decoder_graph", False)))
             self._kv_cache = cache
             for t in range(memory.shape[1]):              # the [bos, source_lang, target_lang] prefix
                 pred, attn = cache.step(memory[:, t].contiguous())

@@ -200,16 +200,18 @@ class TransformerMultiTask(nn.Module):
             self._packed_dec_key = key
         return self._packed_dec
 
-    def decoder_cache(self, encoder_out, rows: int, max_len: int, enc_len=None, precision: str = "fp32") -> dec.DecoderCache:
+    def decoder_cache(self, encoder_out, rows: int, max_len: int, enc_len=None, precision: str = "fp32",
+                      graph: bool = False) -> dec.DecoderCache:
         """KV-cached incremental decoding over `encoder_out` [B, T2, d] for `rows` hypothesis rows (a multiple of B;
         row r belongs to utterance r // (rows // B)): ``cache.step(tokens)`` gives what ``decode(prefix)`` gives for
         its last position, ``cache.reorder(index)`` follows a beam re-ordering.  precision "bf16": the step's GEMMs on the
-        tensor cores (decoder.DecoderCache)."""
+        tensor cores; graph=True: a step is one CUDA-graph replay (decoder.DecoderCache)."""
         self._need_decoder()
         if self._external_decoder:
             raise StacB200Error("decoder_cache drives the built-in decoder; an external one is attached")
         mem_len = None if enc_len is None else enc_len.to(device=encoder_out.device, dtype=torch.int32).contiguous()
-        return dec.DecoderCache(self.packed_decoder(), encoder_out, rows, max_len, mem_len, precision=precision)
+        return dec.DecoderCache(self.packed_decoder(), encoder_out, rows, max_len, mem_len, precision=precision,
+                                graph=graph)
 
     def forward(self, src, tgt, wav_len=None, pad_idx=0):
         """Reference :144-209: encoder with the ``make_masks`` length rule, decoder over the whole target with the

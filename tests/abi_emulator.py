@@ -96,13 +96,28 @@ class Emulator:
                 p = np.exp(s - s.max(1, keepdims=True))
                 out[b, :, h] = (p / p.sum(1, keepdims=True)) @ x[b, :nk, 2, h]
 
-    def stac_attention_step_f32(self, q, ldq, k, v, kv_rs, kv_ts, rows, lk, n_head, row_map, ctx, ldctx, stream):
-        """Self-attention of one decoding step over a time-major cache, key j of row r in cache row row_map[j, r]."""
+    def stac_embed_step(self, tokens, emb, pe, rows, d_model, vocab, scale, pos_dev, out, stream):
+        pos = int(_arr(pos_dev, 1, np.int32)[0])
+        self.stac_embed_scale_pe(tokens, emb, pe + pos * d_model * 4, rows, 1, d_model, vocab, scale, out, stream)
+
+    def stac_attention_step_f32(self, q, ldq, k, v, kv_rs, kv_ts, rows, lk, n_head, row_map, k_new, v_new, ld_new, t_dev,
+                                ctx, ldctx, stream):
+        """Self-attention of one decoding step over a time-major cache, key j of row r in cache row row_map[j, r]; in
+        append mode the position counter is read from the device and the new keys / values are stored into slab t."""
         d = n_head * 64
+        if t_dev:
+            t = min(int(_arr(t_dev, 1, np.int32)[0]), lk - 1)
+            lk = t + 1
         qq = _arr(q, (rows - 1) * ldq + d)
         rm = _arr(row_map, lk * rows, np.int32)
         span = (rows - 1) * kv_rs + (lk - 1) * kv_ts + d
         kk, vv = _arr(k, span), _arr(v, span)
+        if t_dev:
+            kn, vn = _arr(k_new, (rows - 1) * ld_new + d), _arr(v_new, (rows - 1) * ld_new + d)
+            for r in range(rows):
+                o = r * kv_rs + t * kv_ts
+                kk[o:o + d] = kn[r * ld_new:r * ld_new + d]
+                vv[o:o + d] = vn[r * ld_new:r * ld_new + d]
         cc = _arr(ctx, (rows - 1) * ldctx + d)
         for r in range(rows):
             for h in range(n_head):

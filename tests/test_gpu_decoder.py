@@ -151,3 +151,30 @@ def test_kv_cached_steps_bf16_gemms_on_device():
         out, w = c16b.step(rows[:, t].contiguous())
     assert rel_l2(out[::beam], torch.from_numpy(d["pred"])[:, -1]) < BF16_TOL
     assert rel_l2(w[::beam], torch.from_numpy(d["attn"])[:, -1]) < BF16_TOL
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_kv_cached_steps_as_one_graph_replay(precision):
+    """DecoderCache(graph=True): from the second step on a step is one CUDA-graph replay (the position counter lives on
+    the device, the self-attention kernel appends to the cache itself).  Bit-identical to the eager steps, including a
+    beam re-ordering after the capture and a rewind."""
+    d, state = fixture()
+    tr = build(sb.TransformerMultiTask, state, precision="bf16").cuda()
+    prefix, enc_out = torch.from_numpy(d["prefix"]).cuda(), torch.from_numpy(d["enc_out"]).cuda()
+    rows = prefix.repeat_interleave(3, 0)
+    eager = tr.decoder_cache(enc_out, rows=rows.shape[0], max_len=rows.shape[1] + 2, precision=precision)
+    graph = tr.decoder_cache(enc_out, rows=rows.shape[0], max_len=rows.shape[1] + 2, precision=precision, graph=True)
+    index = torch.arange(rows.shape[0], device="cuda").roll(1)
+    for t in range(rows.shape[1]):
+        if t == 3:
+            eager.reorder(index)
+            graph.reorder(index)
+        oe, we = eager.step(rows[:, t].contiguous())
+        og, wg = graph.step(rows[:, t].contiguous())
+        assert torch.equal(oe, og) and torch.equal(we, wg), t
+    assert graph._graph is not None
+    eager.rewind(2)
+    graph.rewind(2)
+    oe, we = eager.step(rows[:, 2].contiguous())
+    og, wg = graph.step(rows[:, 2].contiguous())
+    assert torch.equal(oe, og) and torch.equal(we, wg)

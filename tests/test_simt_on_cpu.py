@@ -27,7 +27,7 @@ def simt():
     for name in ("stac_argmax_rows", "stac_ctc_spikes", "stac_embed_scale_pe", "stac_attention_f32",
                  "stac_pcm_i16_to_f32", "stac_utt_mean_std", "stac_layernorm", "stac_mha_f32", "stac_log_softmax",
                  "stac_kv_lengths", "stac_cast_bf16", "stac_gemm_f32", "stac_spec_augment", "stac_ctc_loss",
-                 "stac_attention_beam_f32", "stac_attention_step_f32"):
+                 "stac_attention_beam_f32", "stac_attention_step_f32", "stac_embed_step"):
         res, args = _lib._SIGNATURES[name]
         getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
     return lib
@@ -144,8 +144,26 @@ def test_attention_step_kernel_with_row_map(simt, rows, lk, h, with_map):
     rmap = torch.randint(0, rows, (lk, rows), generator=g, dtype=torch.int32) if with_map else None
     ctx = torch.full((rows, d), float("nan"))
     rc = simt.stac_attention_step_f32(P(q), d, P(cache), c_void_p(cache.data_ptr() + 4 * d), 2 * d, rows * 2 * d, rows, lk,
-                                      h, P(rmap), P(ctx), d, None)
+                                      h, P(rmap), None, None, 0, None, P(ctx), d, None)
     assert rc == 0
+    # append mode: the last position comes from the projection's rows, the counter from memory; same result, and the
+    # kernel has stored the new keys / values into slab lk - 1
+    cache2 = cache.clone()
+    kv_new = cache[lk - 1].clone()
+    cache2[lk - 1] = float("nan")
+    if with_map:
+        rmap[lk - 1] = torch.arange(rows, dtype=torch.int32)        # a new position always lives in its own row
+    t_dev = torch.tensor([lk - 1], dtype=torch.int32)
+    ctx_b = torch.full((rows, d), float("nan"))
+    rc = simt.stac_attention_step_f32(P(q), d, P(cache2), c_void_p(cache2.data_ptr() + 4 * d), 2 * d, rows * 2 * d, rows,
+                                      lk + 2, h, P(rmap), P(kv_new), c_void_p(kv_new.data_ptr() + 4 * d), 2 * d, P(t_dev),
+                                      P(ctx_b), d, None)
+    assert rc == 0 and torch.equal(cache2[lk - 1], kv_new)
+    if with_map:                                                    # (the first call read slab lk - 1 through the old map)
+        ctx = torch.full((rows, d), float("nan"))
+        assert simt.stac_attention_step_f32(P(q), d, P(cache), c_void_p(cache.data_ptr() + 4 * d), 2 * d, rows * 2 * d,
+                                            rows, lk, h, P(rmap), None, None, 0, None, P(ctx), d, None) == 0
+    assert torch.allclose(ctx_b, ctx, rtol=1e-5, atol=1e-6)       # (the new key opens the running softmax: other order)
     src = rmap.long() if with_map else torch.arange(rows).repeat(lk, 1)
     kv = cache[:lk].gather(1, src[:, :, None].expand(lk, rows, 2 * d))          # [lk, rows, 2d] as each row sees it
     kk = kv[:, :, :d].permute(1, 0, 2).reshape(rows, lk, h, 64).permute(0, 2, 1, 3).double()
@@ -183,6 +201,9 @@ def test_attention_time_major_cache_and_embedding(simt):
     rc = simt.stac_embed_scale_pe(P(tok3), P(emb), c_void_p(pe.data_ptr() + 3 * d * 4), r, 1, d, vocab,
                                   float(np.sqrt(d)), P(out1), None)
     assert rc == 0 and torch.allclose(out1, out.view(r, L, d)[:, 3], atol=1e-6)
+    out2, pos = torch.empty(r, d), torch.tensor([3], dtype=torch.int32)     # the same with the position read from memory
+    assert simt.stac_embed_step(P(tok3), P(emb), P(pe), r, d, vocab, float(np.sqrt(d)), P(pos), P(out2), None) == 0
+    assert torch.equal(out2, out1)
 
 
 @pytest.mark.parametrize("n", [1, 7, 8, 9, 4099])

@@ -47,7 +47,7 @@ t0 = cache.t
 
 
 def one_step():
-    cache.t = t0
+    cache.rewind(t0)
     cache.step(tok[:, t0].contiguous())
 
 
@@ -58,24 +58,29 @@ for t in range(a.prefix - 1):
 
 
 def one_step16():
-    cache16.t = t0
+    cache16.rewind(t0)
     cache16.step(tok[:, t0].contiguous())
 
 
 ms_step16 = timed(one_step16)
-# the same bf16 step replayed as a CUDA graph (what is left is the kernels, not the ~100 Python launches)
-g = torch.cuda.CUDAGraph()
-s = torch.cuda.Stream()
-s.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(s):
-    one_step16()
-    torch.cuda.synchronize()
-    with torch.cuda.graph(g, stream=s):
-        one_step16()
-torch.cuda.current_stream().wait_stream(s)
-ms_graph16 = timed(g.replay)
+# the same bf16 step with graph=True: DecoderCache replays one captured launch sequence per step (the position counter
+# lives on the device), so this is what a searcher's forward_step costs, tokens in / prediction out
+cache_g = tr.decoder_cache(enc, rows=rows, max_len=a.prefix + 8, precision="bf16", graph=True)
+for t in range(a.prefix - 1):
+    cache_g.step(tok[:, t].contiguous())
+
+
+def one_step_graph():
+    cache_g.rewind(t0)
+    cache_g.step(tok[:, t0].contiguous())
+
+
+ms_graph16 = timed(one_step_graph)
+ref_o, ref_w = cache16.step(tok[:, t0].contiguous()) if cache16.rewind(t0) is None else None
+got_o, got_w = cache_g.step(tok[:, t0].contiguous()) if cache_g.rewind(t0) is None else None
+assert torch.equal(ref_o, got_o) and torch.equal(ref_w, got_w), "graph replay differs from the eager step"
 print(f"rows {rows}  prefix {a.prefix}  frames {a.frames}:  full-prefix decode {ms_full:.3f} ms   cached step {ms_step:.3f} ms"
-      f"   cached step, bf16 GEMMs {ms_step16:.3f} ms   the same as a CUDA graph {ms_graph16:.3f} ms")
+      f"   cached step, bf16 GEMMs {ms_step16:.3f} ms   the same with graph=True (one replay per step) {ms_graph16:.3f} ms")
 # beam re-ordering: the row map (what reorder() does) against gathering the cached prefix (what it did at first)
 idx = torch.randint(0, rows, (rows,), device="cuda")
 ms_reorder = timed(lambda: cache16.reorder(idx))
