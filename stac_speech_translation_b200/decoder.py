@@ -285,7 +285,7 @@ class DecoderCache:
         self.h = torch.empty(rows, d, **f32)
         self.q = torch.empty(rows, d, **f32)
         self.ctx = torch.empty(rows, d, **f32)
-        self.kv_new = torch.empty(rows, 2 * d, **f32)             # keys | values of the position being decoded
+        self.qkv_new = torch.empty(rows, 3 * d, **f32)            # query | key | value of the position being decoded
         self.t_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # the position counter the kernels read
         self.use_graph, self._graph = bool(graph), None
         self.tok_buf = torch.zeros(rows, device=dev, dtype=torch.int64)
@@ -305,11 +305,12 @@ class DecoderCache:
             self.ff16 = torch.empty(rows, w.layers[0].w_1.shape[0], **b16)
 
     def _self_attention(self, cache):
-        """Self-attention of the position ``t_dev`` counts: the kernel stores ``kv_new`` into slab t of the cache and
-        attends keys 0 .. t; hypothesis rows are found through ``self.row_map``."""
-        d, r = self.d, self.rows
-        ops._call("stac_attention_step_f32", ptr(self.q), d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, self.max_len,
-                  self.w.nhead, ptr(self.row_map, torch.int32), ptr(self.kv_new), _off(self.kv_new, d), 2 * d,
+        """Self-attention of the position ``t_dev`` counts, from the fused q | k | v projection of that position: the
+        kernel stores the new keys / values into slab t of the cache and attends keys 0 .. t; hypothesis rows are found
+        through ``self.row_map``."""
+        d, r, n = self.d, self.rows, self.qkv_new
+        ops._call("stac_attention_step_f32", ptr(n), 3 * d, ptr(cache), _off(cache, d), 2 * d, r * 2 * d, r, self.max_len,
+                  self.w.nhead, ptr(self.row_map, torch.int32), _off(n, d), _off(n, 2 * d), 3 * d,
                   ptr(self.t_dev, torch.int32), ptr(self.ctx), d, stream())
 
     def _step_bf16(self, weights):
@@ -320,8 +321,7 @@ class DecoderCache:
             wb = self.wb[n]
             last = n == len(w.layers) - 1
             ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_bf16=self.h16)
-            ops._gemm(self.h16, wb["w_qkv"][:d], lw.b_qkv[:d], self.q, "bf16", tag="dec_q_self")
-            ops._gemm(self.h16, wb["w_qkv"][d:], lw.b_qkv[d:], self.kv_new, "bf16", tag="dec_kv_self")
+            ops._gemm(self.h16, wb["w_qkv"], lw.b_qkv, self.qkv_new, "bf16", tag="dec_qkv_self")
             self._self_attention(self.self_kv[n])
             ops._call("stac_cast_bf16", ptr(self.ctx), self.ctx.numel(), ptr(self.ctx16), stream())
             ops._gemm(self.ctx16, wb["w_o"], lw.b_o, x, "bf16", resid=x, tag="dec_out_proj")
@@ -346,8 +346,7 @@ class DecoderCache:
         for n, lw in enumerate(w.layers if self.precision == "fp32" else []):
             last = n == len(w.layers) - 1
             ops._layernorm(x, lw.ln1_g, lw.ln1_b, 1e-6, out_f32=self.h)
-            ops._gemm(self.h, lw.w_qkv[:d], lw.b_qkv[:d], self.q, "fp32", tag="dec_q_self")
-            ops._gemm(self.h, lw.w_qkv[d:], lw.b_qkv[d:], self.kv_new, "fp32", tag="dec_kv_self")
+            ops._gemm(self.h, lw.w_qkv, lw.b_qkv, self.qkv_new, "fp32", tag="dec_qkv_self")
             self._self_attention(self.self_kv[n])
             ops._gemm(self.ctx, lw.w_o, lw.b_o, x, "fp32", resid=x, tag="dec_out_proj")
             ops._layernorm(x, lw.ln2_g, lw.ln2_b, 1e-6, out_f32=self.h)
