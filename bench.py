@@ -334,6 +334,69 @@ def kernel_table(trace, n_steps, wt, pk):
     return table
 
 
+def graph_timeline(graphed, wt, pk, n_rep=3):
+    """Warm duration of every kernel INSIDE one replay of the path's CUDA graph, and the idle time between kernels (CUPTI
+    through torch.profiler).  The `kernels` table and `roofline` are CUDA events around eager launches (events cannot sit
+    inside a graph) and carry a few microseconds of launch overhead per launch; this is the same kernels as the timed
+    replays run them.  A breakdown that explains `value`, never a bench value; absent when CUPTI is not available."""
+    from torch.profiler import ProfilerActivity, profile
+    g = graphed.graph
+    g.replay()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(n_rep):
+            g.replay()
+        torch.cuda.synchronize()
+    ev = sorted((e for e in prof.events()
+                 if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.elapsed_us() > 0),
+                key=lambda e: e.time_range.start)
+    per = len(ev) // n_rep
+    if per == 0 or len(ev) != per * n_rep:
+        raise RuntimeError(f"{len(ev)} device events for {n_rep} replays")
+    ev = ev[-per:]                                                  # the last replay
+    sym = [e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0] for e in ev]
+    n_general = sum(1 for s_ in sym if s_.startswith("gemm_bf16_kernel<false>") or s_.startswith("gemm_bf16_kernel<0>"))
+    fixed = {"gemm_bf16_kernel<true>": "stac_conv1_bf16", "gemm_bf16_kernel<1>": "stac_conv1_bf16",
+             "mha2_bf16_kernel": "stac_mha_bf16_v2", "mha_bf16_kernel": "stac_mha_bf16",
+             "ffn_fused_kernel": "stac_ffn_fused_bf16", "conv0_tc_kernel": "stac_conv0_ln_lrelu",
+             "layernorm_kernel": "stac_layernorm", "fbank_tc2_kernel": "stac_fbank_logmel_tc2",
+             "fbank_tc_kernel": "stac_fbank_logmel_tc", "topdb_norm_kernel": "stac_fbank_topdb_norm"}
+    rows, n_wres, n_gen = {}, 0, 0
+    for s_, e in zip(sym, ev):
+        key, part = None, 1
+        for prefix, label in fixed.items():
+            if s_ == prefix or s_.startswith(prefix + "<"):
+                key = label
+        if s_.startswith("gemm_wres_kernel"):                       # QKV and out-proj alternate, layer by layer
+            key = "stac_gemm_bf16:qkv" if n_wres % 2 == 0 else "stac_gemm_bf16:out_proj"
+            n_wres += 1
+        elif (s_.startswith("gemm_bf16_kernel<false>") or s_.startswith("gemm_bf16_kernel<0>")) and n_general == 3:
+            key, part = ("stac_gemm_bf16:src_linear", 1) if n_gen == 0 else ("stac_ctc_head_bf16", 3)
+            n_gen += 1
+        elif s_.startswith("ctc_reduce_kernel") and n_general == 3:
+            key, part = "stac_ctc_head_bf16", 3                     # (pass 1, reduce, pass 2 = one launch of the head)
+        r = rows.setdefault(key or s_, [0.0, 0, part])
+        r[0] += e.time_range.elapsed_us()
+        r[1] += 1
+    table = []
+    for k, (us, n, part) in sorted(rows.items(), key=lambda kv_: -kv_[1][0]):
+        launches = max(n // part, 1)
+        row = {"kernel": k, "launches_per_step": launches, "avg_us": round(us / launches, 2), "us_per_step": round(us, 1)}
+        if k in wt:
+            bound, work, _ = wt[k]
+            ach = work / (us / launches * 1e-6) / (1e12 if bound == "tensor" else 1e9)
+            peak = pk["tflops_sustained"] if bound == "tensor" else pk["hbm_gbs"]
+            row.update({"bound": bound, "achieved": round(ach, 1), "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                        "frac": round(ach / peak, 4)})
+        table.append(row)
+    busy = sum(e.time_range.elapsed_us() for e in ev)
+    span = ev[-1].time_range.end - ev[0].time_range.start
+    return {"how": "torch.profiler (CUPTI) over graph replays run after the timed region; device time of every kernel of "
+                   "the last replay, labelled by kernel symbol and launch order",
+            "kernels_per_replay": per, "span_us": round(span, 1), "busy_us": round(busy, 1),
+            "idle_between_kernels_us": round(span - busy, 1), "kernels": table[:12]}
+
+
 def ops_mod():
     from stac_speech_translation_b200 import ops
     return ops
@@ -657,6 +720,12 @@ def run_ours(args, rank, world, local_rank):
         res = pipe(wavs, wl)                       # the batch every timed step ran on, same kernels
         torch.cuda.synchronize()
         parity = parity_block(res, ref, ref["enc_out"].shape[0], args.precision, wl_cpu)
+    timeline = None
+    if world == 1 and args.precision == "bf16":
+        try:
+            timeline = graph_timeline(graphed[0], wt, pk)
+        except Exception as exc:  # noqa: BLE001 - an optional breakdown must never cost the bench line
+            timeline = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     line = {
         "metric": METRIC, "value": round(total_audio / (ms * 1e-3), 1), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
@@ -680,6 +749,7 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "parity": parity,
         "kernels": [{k: v for k, v in r.items() if k != "work_per_launch"} for r in table[:8]],
+        **({"graph_timeline": timeline} if timeline else {}),
     }
     emit(line)
     if parity is not None and not parity["ok"]:
