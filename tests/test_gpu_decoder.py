@@ -178,3 +178,64 @@ def test_kv_cached_steps_as_one_graph_replay(precision):
     oe, we = eager.step(rows[:, 2].contiguous())
     og, wg = graph.step(rows[:, 2].contiguous())
     assert torch.equal(oe, og) and torch.equal(we, wg)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_cached_forward_step_drives_the_same_search_on_the_device(graph):
+    """searcher.CachedStepMixin on the device (row-map re-ordering, optionally one graph replay per step) against the
+    reference's forward_step / permute_mem bodies (mutitask_decoder.py:101-128: whole-prefix decode, index_select of
+    the token memory) under the same beam-search control flow: same hypotheses and back-pointers at every step."""
+    from stac_speech_translation_b200.searcher import CachedStepMixin, _update_mem
+    from test_host_emulated import _StubBeamSearcher
+    d, state = fixture()
+    tr = build(sb.TransformerMultiTask, state, precision="bf16").cuda()
+    torch.manual_seed(5)
+    fc = torch.nn.Linear(tr.d_model, tr.tgt_vocab).cuda()
+
+    class DeviceSearch(_StubBeamSearcher):
+        def search(self, enc_states, steps):
+            dev = enc_states.device
+            b, beam = enc_states.shape[0], self.beam_size
+            enc = enc_states.repeat_interleave(beam, 0)
+            memory = self.reset_mem(b * beam, dev)
+            inp = torch.full((b * beam,), self.bos_index, dtype=torch.long, device=dev)
+            scores = torch.zeros(b, beam, device=dev)
+            scores[:, 1:] = -1e9
+            trace = []
+            for _ in range(steps):
+                logp, memory, attn = self.forward_step(inp, memory, enc, None)
+                vocab = logp.shape[-1]
+                cand = (scores.view(b * beam, 1) + logp).view(b, beam * vocab)
+                scores, idx = cand.topk(beam, dim=-1)
+                pred = (idx // vocab + torch.arange(b, device=dev)[:, None] * beam).view(-1)
+                inp = (idx % vocab).view(-1)
+                memory = self.permute_mem(memory, pred)
+                trace.append((scores.clone(), inp.clone(), pred.clone(), attn[:, -1].clone()))
+            return memory, trace
+
+    class ReferenceStep(DeviceSearch):
+        def reset_mem(self, batch_size, device):
+            return torch.tensor([self.decoder_input_tokens] * batch_size).to(device)
+
+        def permute_mem(self, memory, index):
+            return torch.index_select(memory, dim=0, index=index)
+
+        def forward_step(self, inp_tokens, memory, enc_states, enc_lens):
+            if not torch.all(inp_tokens == self.bos_index):
+                memory = _update_mem(inp_tokens, memory)
+            pred, attn = self.model.decode(memory, enc_states)
+            prob_dist = self.softmax(self.fc(pred) / self.temperature)
+            return prob_dist[:, -1, :], memory, attn
+
+    class CachedStep(CachedStepMixin, DeviceSearch):
+        decoder_graph = graph
+
+    enc_out = torch.from_numpy(d["enc_out"]).cuda()
+    args = dict(model=tr, fc=fc, beam_size=3, bos_index=1, prefix=[1, 9, 12])
+    with torch.no_grad():
+        mem_ref, trace_ref = ReferenceStep(**args).search(enc_out, steps=7)
+        mem_new, trace_new = CachedStep(**args).search(enc_out, steps=7)
+    assert torch.equal(mem_ref, mem_new)
+    for (s0, i0, p0, a0), (s1, i1, p1, a1) in zip(trace_ref, trace_new):
+        assert torch.equal(i0, i1) and torch.equal(p0, p1)
+        assert rel_l2(s1, s0) < 1e-5 and rel_l2(a1, a0) < 1e-4
