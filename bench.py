@@ -334,6 +334,48 @@ def kernel_table(trace, n_steps, wt, pk):
     return table
 
 
+def timeline_table(sym, dur_us, wt, pk):
+    """Kernel symbols of one graph replay, in launch order, with their device times -> rows labelled like the `kernels`
+    table (work_table keys) with achieved rates.  Symbols that several entry points share are told apart by launch
+    order: the weight-resident GEMM alternates QKV / out-proj layer by layer; of the three general linear GEMMs of the
+    S path the first is the src-linear and the other two, with the row reduction between them, are one CTC head."""
+    n_general = sum(1 for s_ in sym if s_.startswith("gemm_bf16_kernel<false>") or s_.startswith("gemm_bf16_kernel<0>"))
+    fixed = {"gemm_bf16_kernel<true>": "stac_conv1_bf16", "gemm_bf16_kernel<1>": "stac_conv1_bf16",
+             "mha2_bf16_kernel": "stac_mha_bf16_v2", "mha_bf16_kernel": "stac_mha_bf16",
+             "ffn_fused_kernel": "stac_ffn_fused_bf16", "conv0_tc_kernel": "stac_conv0_ln_lrelu",
+             "layernorm_kernel": "stac_layernorm", "fbank_tc2_kernel": "stac_fbank_logmel_tc2",
+             "fbank_tc_kernel": "stac_fbank_logmel_tc", "topdb_norm_kernel": "stac_fbank_topdb_norm"}
+    rows, n_wres, n_gen = {}, 0, 0
+    for s_, us_ in zip(sym, dur_us):
+        key, part = None, 1
+        for prefix, label in fixed.items():
+            if s_ == prefix or s_.startswith(prefix + "<"):
+                key = label
+        if s_.startswith("gemm_wres_kernel"):                       # QKV and out-proj alternate, layer by layer
+            key = "stac_gemm_bf16:qkv" if n_wres % 2 == 0 else "stac_gemm_bf16:out_proj"
+            n_wres += 1
+        elif (s_.startswith("gemm_bf16_kernel<false>") or s_.startswith("gemm_bf16_kernel<0>")) and n_general == 3:
+            key, part = ("stac_gemm_bf16:src_linear", 1) if n_gen == 0 else ("stac_ctc_head_bf16", 3)
+            n_gen += 1
+        elif s_.startswith("ctc_reduce_kernel") and n_general == 3:
+            key, part = "stac_ctc_head_bf16", 3                     # (pass 1, reduce, pass 2 = one launch of the head)
+        r = rows.setdefault(key or s_, [0.0, 0, part])
+        r[0] += us_
+        r[1] += 1
+    table = []
+    for k, (us, n, part) in sorted(rows.items(), key=lambda kv_: -kv_[1][0]):
+        launches = max(n // part, 1)
+        row = {"kernel": k, "launches_per_step": launches, "avg_us": round(us / launches, 2), "us_per_step": round(us, 1)}
+        if k in wt:
+            bound, work, _ = wt[k]
+            ach = work / (us / launches * 1e-6) / (1e12 if bound == "tensor" else 1e9)
+            peak = pk["tflops_sustained"] if bound == "tensor" else pk["hbm_gbs"]
+            row.update({"bound": bound, "achieved": round(ach, 1), "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                        "frac": round(ach / peak, 4)})
+        table.append(row)
+    return table
+
+
 def graph_timeline(graphed, wt, pk, n_rep=3):
     """Warm duration of every kernel INSIDE one replay of the path's CUDA graph, and the idle time between kernels (CUPTI
     through torch.profiler).  The `kernels` table and `roofline` are CUDA events around eager launches (events cannot sit
@@ -355,40 +397,7 @@ def graph_timeline(graphed, wt, pk, n_rep=3):
         raise RuntimeError(f"{len(ev)} device events for {n_rep} replays")
     ev = ev[-per:]                                                  # the last replay
     sym = [e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0] for e in ev]
-    n_general = sum(1 for s_ in sym if s_.startswith("gemm_bf16_kernel<false>") or s_.startswith("gemm_bf16_kernel<0>"))
-    fixed = {"gemm_bf16_kernel<true>": "stac_conv1_bf16", "gemm_bf16_kernel<1>": "stac_conv1_bf16",
-             "mha2_bf16_kernel": "stac_mha_bf16_v2", "mha_bf16_kernel": "stac_mha_bf16",
-             "ffn_fused_kernel": "stac_ffn_fused_bf16", "conv0_tc_kernel": "stac_conv0_ln_lrelu",
-             "layernorm_kernel": "stac_layernorm", "fbank_tc2_kernel": "stac_fbank_logmel_tc2",
-             "fbank_tc_kernel": "stac_fbank_logmel_tc", "topdb_norm_kernel": "stac_fbank_topdb_norm"}
-    rows, n_wres, n_gen = {}, 0, 0
-    for s_, e in zip(sym, ev):
-        key, part = None, 1
-        for prefix, label in fixed.items():
-            if s_ == prefix or s_.startswith(prefix + "<"):
-                key = label
-        if s_.startswith("gemm_wres_kernel"):                       # QKV and out-proj alternate, layer by layer
-            key = "stac_gemm_bf16:qkv" if n_wres % 2 == 0 else "stac_gemm_bf16:out_proj"
-            n_wres += 1
-        elif (s_.startswith("gemm_bf16_kernel<false>") or s_.startswith("gemm_bf16_kernel<0>")) and n_general == 3:
-            key, part = ("stac_gemm_bf16:src_linear", 1) if n_gen == 0 else ("stac_ctc_head_bf16", 3)
-            n_gen += 1
-        elif s_.startswith("ctc_reduce_kernel") and n_general == 3:
-            key, part = "stac_ctc_head_bf16", 3                     # (pass 1, reduce, pass 2 = one launch of the head)
-        r = rows.setdefault(key or s_, [0.0, 0, part])
-        r[0] += e.time_range.elapsed_us()
-        r[1] += 1
-    table = []
-    for k, (us, n, part) in sorted(rows.items(), key=lambda kv_: -kv_[1][0]):
-        launches = max(n // part, 1)
-        row = {"kernel": k, "launches_per_step": launches, "avg_us": round(us / launches, 2), "us_per_step": round(us, 1)}
-        if k in wt:
-            bound, work, _ = wt[k]
-            ach = work / (us / launches * 1e-6) / (1e12 if bound == "tensor" else 1e9)
-            peak = pk["tflops_sustained"] if bound == "tensor" else pk["hbm_gbs"]
-            row.update({"bound": bound, "achieved": round(ach, 1), "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
-                        "frac": round(ach / peak, 4)})
-        table.append(row)
+    table = timeline_table(sym, [e.time_range.elapsed_us() for e in ev], wt, pk)
     busy = sum(e.time_range.elapsed_us() for e in ev)
     span = ev[-1].time_range.end - ev[0].time_range.start
     return {"how": "torch.profiler (CUPTI) over graph replays run after the timed region; device time of every kernel of "

@@ -411,3 +411,35 @@ def test_bench_configs_and_parity_block():
     assert out["ok"] and out["enc_rel_l2"] == 0 and out["greedy_frame"] == 1.0 and out["greedy_seq"] == 1.0
     res["enc_out"][0] *= 1.05
     assert not bench.parity_block(res, ref, 2, "bf16", wl)["ok"]
+
+
+def test_bench_graph_timeline_labels_the_launch_sequence_of_the_s_path():
+    """bench.timeline_table: the kernel symbols of one graph replay of configs[1] (83 launches, as CUPTI reports them)
+    are labelled with the work-table keys by symbol and launch order, and carry the same roofline arithmetic as the
+    `kernels` table."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    layer = ["layernorm_kernel<2, 4>", "gemm_wres_kernel<256>", "mha2_bf16_kernel", "gemm_wres_kernel<256>",
+             "layernorm_kernel<2, 4>", "ffn_fused_kernel"]
+    sym = (["Memset", "fbank_tc2_kernel<true>", "topdb_norm_kernel", "conv0_tc_kernel", "gemm_bf16_kernel<true>",
+            "kv_lengths_kernel", "gemm_bf16_kernel<false>"] + layer * 12 +
+           ["layernorm_kernel<2, 4>", "gemm_bf16_kernel<false>", "ctc_reduce_kernel", "gemm_bf16_kernel<false>"])
+    assert len(sym) == 83
+    dur = [10.0] * len(sym)
+    wt = bench.work_table(sb.MODEL_SIZES["S"], 64, 480000, 64 * 751 * 751)
+    pk = {"tflops_sustained": 1387.0, "hbm_gbs": 6550.0}
+    rows = {r["kernel"]: r for r in bench.timeline_table(sym, dur, wt, pk)}
+    assert rows["stac_gemm_bf16:qkv"]["launches_per_step"] == 12 and rows["stac_gemm_bf16:out_proj"]["launches_per_step"] == 12
+    assert rows["stac_layernorm"]["launches_per_step"] == 25 and rows["stac_mha_bf16_v2"]["launches_per_step"] == 12
+    assert rows["stac_gemm_bf16:src_linear"]["launches_per_step"] == 1
+    head = rows["stac_ctc_head_bf16"]                              # pass 1 + reduce + pass 2 = one launch of 30 us
+    assert head["launches_per_step"] == 1 and head["avg_us"] == 30.0
+    conv1 = rows["stac_conv1_bf16"]
+    assert conv1["bound"] == "tensor" and abs(conv1["achieved"] - wt["stac_conv1_bf16"][1] / 10e-6 / 1e12) < 0.1
+    assert abs(conv1["frac"] - conv1["achieved"] / 1387.0) < 1e-3
+    assert "frac" not in rows["Memset"] and "frac" not in rows["kv_lengths_kernel"]
+    # another model size (general GEMMs in the layers): no guessing, the shared symbol stays unlabelled
+    other = bench.timeline_table(["gemm_bf16_kernel<false>"] * 5, [1.0] * 5, wt, pk)
+    assert [r["kernel"] for r in other] == ["gemm_bf16_kernel<false>"]
